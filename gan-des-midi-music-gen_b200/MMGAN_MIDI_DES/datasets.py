@@ -1,0 +1,306 @@
+"""Drop-in mirror of the reference's ``MMGAN_MIDI_DES/datasets.py``
+(/root/reference/MMGAN_MIDI_DES/datasets.py:13-123): ``generate_piano_roll`` and the three
+``MaestroDataset*`` classes, with the note-event -> 128-pitch-grid rasterisation done by the CUDA
+kernel ``mmg_raster_piano_roll`` (csrc/raster.cu) instead of the CPython loop (:27-54).
+
+The third-party pieces stay on the host: SMF parsing + tick->second (mido 1.3.2 in the reference;
+here a small built-in reader that follows mido's merge/tempo rules, or any iterable of mido-like
+message objects) and the beat grid (pretty_midi 0.2.10 ``get_beats`` in the reference; here
+``EventStream.beats``).  Parity at those two boundaries is unpinned: the raster input
+is defined as the post-mido event stream.
+
+There is no CPU fallback: rasterisation needs a CUDA device and the built library.
+"""
+import glob
+import os
+import pickle
+import struct
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .. import _native as N
+
+KIND_OTHER, KIND_ON, KIND_OFF = 0, 1, 2
+_KIND_OF_TYPE = {"note_on": KIND_ON, "note_off": KIND_OFF}
+_TORCH_OUT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}
+
+
+class EventStream:
+    """One song as the post-mido message stream: ``dt`` seconds (float64) and packed ``meta``
+    (kind | pitch << 8 | velocity << 16), plus the beat times the reference takes from pretty_midi."""
+
+    def __init__(self, dt, meta, beats=(), filename=None):
+        self.dt = np.ascontiguousarray(dt, dtype=np.float64)
+        self.meta = np.ascontiguousarray(meta, dtype=np.uint32)
+        if self.dt.shape != self.meta.shape or self.dt.ndim != 1:
+            raise ValueError("dt and meta must be 1-D arrays of equal length")
+        self.beats = np.asarray(beats, dtype=np.float64)
+        self.filename = filename
+
+    def __len__(self):
+        return len(self.dt)
+
+    @classmethod
+    def from_arrays(cls, dt, kind, pitch, velocity, beats=(), filename=None):
+        meta = (np.asarray(kind, dtype=np.uint32) | (np.asarray(pitch, dtype=np.uint32) << 8) | (np.asarray(velocity, dtype=np.uint32) << 16))
+        return cls(dt, meta, beats, filename)
+
+    @classmethod
+    def from_messages(cls, messages, beats=(), filename=None):
+        """From any iterable of mido-like messages (``.type``, ``.time`` seconds, ``.note``, ``.velocity``)."""
+        dt, meta = [], []
+        for m in messages:
+            k = _KIND_OF_TYPE.get(m.type, KIND_OTHER)
+            dt.append(float(m.time))
+            meta.append(k | (int(m.note) << 8) | (int(m.velocity) << 16) if k else 0)
+        return cls(np.array(dt, dtype=np.float64), np.array(meta, dtype=np.uint32), beats, filename)
+
+    @classmethod
+    def from_midi_file(cls, path):
+        return read_smf(path)
+
+
+# ----------------------------------------------------------------------------------------------
+# Standard MIDI File reader (host side; follows mido 1.3.2: merge_tracks, tick2second, running tempo)
+# ----------------------------------------------------------------------------------------------
+def _vlq(buf, i):
+    v = 0
+    while True:
+        b = buf[i]
+        i += 1
+        v = (v << 7) | (b & 0x7F)
+        if not b & 0x80:
+            return v, i
+
+
+def _parse_track(buf):
+    """-> list of (abs_tick, kind, pitch, velocity, tempo_or_None, is_end_of_track)"""
+    i, t, status, out = 0, 0, 0, []
+    n = len(buf)
+    while i < n:
+        d, i = _vlq(buf, i)
+        t += d
+        b = buf[i]
+        if b == 0xFF:                                   # meta
+            typ = buf[i + 1]
+            ln, j = _vlq(buf, i + 2)
+            data = buf[j:j + ln]
+            i = j + ln
+            tempo = int.from_bytes(data, "big") if typ == 0x51 and ln == 3 else None
+            out.append((t, KIND_OTHER, 0, 0, tempo, typ == 0x2F))
+        elif b in (0xF0, 0xF7):                         # sysex
+            ln, j = _vlq(buf, i + 1)
+            i = j + ln
+            out.append((t, KIND_OTHER, 0, 0, None, False))
+        else:
+            if b & 0x80:
+                status = b
+                i += 1
+            hi = status & 0xF0
+            nbytes = 1 if hi in (0xC0, 0xD0) else 2
+            if status >= 0xF0:                           # system common / realtime
+                nbytes = {0xF1: 1, 0xF2: 2, 0xF3: 1}.get(status, 0)
+            d1 = buf[i] if nbytes >= 1 else 0
+            d2 = buf[i + 1] if nbytes >= 2 else 0
+            i += nbytes
+            kind = KIND_ON if hi == 0x90 else KIND_OFF if hi == 0x80 else KIND_OTHER
+            out.append((t, kind, d1 if kind else 0, d2 if kind else 0, None, False))
+    return out
+
+
+def read_smf(path):
+    """Parses a type-0/1 Standard MIDI File into an EventStream the way ``for msg in mido.MidiFile``
+    yields it (datasets.py:18,34): tracks merged by absolute tick (stable), end_of_track metas
+    dropped and one re-appended, delta seconds = ticks * (tempo * 1e-6 / ticks_per_beat) with the
+    tempo switching after each set_tempo message."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:4] != b"MThd":
+        raise ValueError(f"{path}: not a Standard MIDI File")
+    hlen, fmt, ntrk, div = struct.unpack(">IHHH", raw[4:14])
+    if div & 0x8000:
+        raise ValueError("SMPTE time division is not supported")
+    if fmt == 2:
+        raise TypeError("can't merge tracks in type 2 (asynchronous) file")
+    pos, events = 8 + hlen, []
+    for _ in range(ntrk):
+        while raw[pos:pos + 4] != b"MTrk":
+            pos += 8 + struct.unpack(">I", raw[pos + 4:pos + 8])[0]
+        ln = struct.unpack(">I", raw[pos + 4:pos + 8])[0]
+        events.extend(_parse_track(raw[pos + 8:pos + 8 + ln]))
+        pos += 8 + ln
+    events.sort(key=lambda e: e[0])                      # stable, like mido.merge_tracks
+    end_tick = max([e[0] for e in events], default=0)
+    events = [e for e in events if not e[5]] + [(end_tick, KIND_OTHER, 0, 0, None, True)]
+    ticks = np.array([e[0] for e in events], dtype=np.int64)
+    dticks = np.diff(ticks, prepend=0)
+    tempo, dt = 500000, np.zeros(len(events), dtype=np.float64)
+    for i, e in enumerate(events):
+        if dticks[i] > 0:
+            dt[i] = int(dticks[i]) * (tempo * 1e-6 / div)
+        if e[4] is not None:
+            tempo = e[4]
+    kind = np.array([e[1] for e in events], dtype=np.uint32)
+    meta = kind | (np.array([e[2] for e in events], dtype=np.uint32) << 8) | (np.array([e[3] for e in events], dtype=np.uint32) << 16)
+    # beat grid: quarter-note beats along the tempo map up to the last note event (host-side estimate of
+    # pretty_midi.get_beats; parity at this boundary is unpinned)
+    note_ticks = ticks[kind != 0]
+    beats = _beat_grid(events, div, int(note_ticks.max()) if len(note_ticks) else 0)
+    return EventStream(dt, meta, beats, filename=path)
+
+
+def _beat_grid(events, div, last_tick):
+    changes = [(0, 500000)] + [(e[0], e[4]) for e in events if e[4] is not None]
+    beats, t_sec, tick, k = [], 0.0, 0, 0
+    tempo = changes[0][1]
+    while tick <= last_tick:
+        beats.append(t_sec)
+        nxt = tick + div
+        while k + 1 < len(changes) and changes[k + 1][0] < nxt:      # integrate across tempo changes
+            k += 1
+            c_tick = max(changes[k][0], tick)
+            t_sec += (c_tick - tick) * (tempo * 1e-6 / div)
+            tick, tempo = c_tick, changes[k][1]
+        t_sec += (nxt - tick) * (tempo * 1e-6 / div)
+        tick = nxt
+    return np.array(beats, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+# rasterisation (device)
+# ----------------------------------------------------------------------------------------------
+def out_width(start, end):
+    """Width of what the reference returns after its re-slice (datasets.py:49-54)."""
+    return N.lib().mmg_raster_out_width(int(start), int(end))
+
+
+def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, out_dtype=torch.float32, status=False):
+    """Device-resident batch rasterisation: ``dt`` (E,) float64, ``meta`` (E,) int32-typed packed u32,
+    ``offsets`` (S+1,) int64, all CUDA tensors -> (S, 2, 128, Wout) tensor of ``out_dtype``."""
+    N.require_cuda(dt, meta, offsets)
+    if end - start < 0:
+        raise ValueError("end-start must be >= 0")
+    S, E = offsets.numel() - 1, dt.numel()
+    Wo = out_width(start, end)
+    out = torch.zeros(S, 2, 128, Wo, device=dt.device, dtype=out_dtype)
+    st = torch.zeros(S, device=dt.device, dtype=torch.int32) if status else None
+    ws_bytes = N.lib().mmg_raster_workspace_bytes(S, E)
+    ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8)
+    N.call("mmg_raster_piano_roll", N.ptr(dt), N.ptr(meta), N.ptr(offsets), S, E, -1 if sequence_length is None else int(sequence_length),
+           int(start), int(end), _TORCH_OUT[out_dtype], N.ptr(out), N.ptr(st), N.ptr(ws), ws_bytes, N.stream())
+    return (out, st) if status else out
+
+
+def pack_streams(streams, device="cuda"):
+    """Host EventStreams -> (dt, meta, offsets) CUDA tensors (one pinned staging copy each)."""
+    lens = np.array([len(s) for s in streams], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dt = np.concatenate([s.dt for s in streams]) if len(streams) else np.zeros(0)
+    meta = np.concatenate([s.meta for s in streams]) if len(streams) else np.zeros(0, dtype=np.uint32)
+    to = lambda a: torch.from_numpy(a).pin_memory().to(device, non_blocking=True)
+    return to(dt.astype(np.float64)), to(meta.astype(np.uint32).view(np.int32)), to(offsets)
+
+
+def rasterize_batch(streams, sequence_length=100, start=0, end=50, device="cuda", out_dtype=torch.float32):
+    """Batch of EventStreams -> (S, 2, 128, Wout) device tensor (plane 0 roll, plane 1 durations)."""
+    dt, meta, offsets = pack_streams(streams, device)
+    return rasterize_events(dt, meta, offsets, sequence_length, start, end, out_dtype)
+
+
+def _as_stream(midi_input):
+    if isinstance(midi_input, EventStream):
+        return midi_input
+    if isinstance(midi_input, str):
+        return read_smf(midi_input)
+    try:                                                  # a real mido.MidiFile, when mido is installed
+        import mido
+        if isinstance(midi_input, mido.MidiFile):
+            s = EventStream.from_messages(midi_input, filename=midi_input.filename)
+            try:
+                import pretty_midi
+                s.beats = np.asarray(pretty_midi.PrettyMIDI(midi_input.filename).get_beats(), dtype=np.float64)
+            except ImportError:
+                pass
+            return s
+    except ImportError:
+        pass
+    raise ValueError("midi_input must be a file path or a mido.MidiFile object")
+
+
+def generate_piano_roll(midi_input, sequence_length=100, beats_length=50, start=0, end=50):
+    """datasets.py:13-70 -- returns ``(piano_roll, durations, beats)`` as float64 numpy arrays of shape
+    (128, Wout), (128, Wout), (beats_length,).  ``midi_input``: a path, a ``mido.MidiFile`` (when mido is
+    installed) or an :class:`EventStream`."""
+    s = _as_stream(midi_input)
+    out = rasterize_batch([s], sequence_length, start, end)[0].cpu().numpy().astype(np.float64)
+    beats = np.asarray(s.beats, dtype=np.float64)
+    if len(beats) < beats_length:                         # :60-62
+        beats = np.pad(beats, (0, beats_length - len(beats)))
+    elif len(beats) > beats_length:                       # :63-65
+        beats = beats[:beats_length]
+    return out[0], out[1], beats
+
+
+# ----------------------------------------------------------------------------------------------
+# Dataset classes (datasets.py:73-123)
+# ----------------------------------------------------------------------------------------------
+def _data_path(*parts):
+    """The reference hard-codes Windows separators ('data\\\\name'); accept either layout."""
+    win = "\\".join(parts)
+    return win if os.path.exists(win) else os.path.join(*parts)
+
+
+class MaestroDatasetPickle(Dataset):
+    """Pickled list of (piano_roll (128,W), durations (128,W), beats (50,)) float tensors (datasets.py:73-87)."""
+
+    def __init__(self, pickle_file_name, sequence_length=100, beats_length=50, device="cpu"):
+        self.device = device
+        with open(_data_path("data", pickle_file_name), "rb") as f:
+            self.data = pickle.load(f)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        piano_roll, durations, beats = self.data[idx]
+        return piano_roll.to(self.device), durations.to(self.device), beats.to(self.device)
+
+
+class MaestroDatasetTorch(Dataset):
+    """One ``torch.save``d triple per item under data/tensors (datasets.py:90-100)."""
+
+    def __init__(self, root_dir, sequence_length=100, beats_length=50, device="cpu"):
+        self.data_dir = root_dir
+        self.device = device
+        self.file_list = sorted(glob.glob(_data_path("data", "tensors", "*.pt")))
+
+    def __len__(self):
+        return len(self.file_list)
+
+    def __getitem__(self, idx):
+        return torch.load(self.file_list[idx])
+
+
+class MaestroDatasetMidi(Dataset):
+    """Rasterises one MAESTRO .midi per item (datasets.py:103-123).  Like the reference it globs
+    data/maestro-v3.0.0 unless ``root_dir`` is an explicit list of paths / EventStreams."""
+
+    def __init__(self, root_dir, sequence_length=100, beats_length=50, device="cpu"):
+        self.root_dir = root_dir
+        self.sequence_length = sequence_length
+        self.beats_length = beats_length
+        self.device = device
+        if isinstance(root_dir, (list, tuple)):
+            self.file_list = list(root_dir)
+        else:
+            self.file_list = sorted(glob.glob(_data_path("data", "maestro-v3.0.0", "**", "*.midi"), recursive=True))
+
+    def __len__(self):
+        return len(self.file_list)
+
+    def __getitem__(self, idx):
+        piano_roll, durations, beats = generate_piano_roll(self.file_list[idx], self.sequence_length, self.beats_length)
+        f = lambda a: torch.from_numpy(a).float().to(self.device)
+        return f(piano_roll), f(durations), f(beats)

@@ -1,0 +1,92 @@
+"""ctypes binding of libmmgan_b200.so (C ABI declared in include/mmgan_b200.h).
+
+There is no CPU fallback: if the library is missing, or a tensor is not on a CUDA device, the
+call raises.  PyTorch is only used for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmgan_b200.so")
+
+_P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every function of include/mmgan_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "mmg_abi_version": (_I, []),
+    "mmg_last_error": (ctypes.c_char_p, []),
+    "mmg_launch_count": (ctypes.c_uint64, []),
+    "mmg_raster_out_width": (_I, [_I, _I]),
+    "mmg_raster_workspace_bytes": (_Z, [_L, _L]),
+    "mmg_raster_piano_roll": (_I, [_P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "mmg_bce_logits_f32": (_I, [_P, _P, _F, _L, _P, _I, _P, _F, _P, _P]),
+    "mmg_act_bwd_f32": (_I, [_P, _P, _P, _L, _I, _P]),
+    "mmg_adam_multi_tensor_f32": (_I, [_I, _P, _P, _F, _F, _F, _F, _L, _F, _P]),
+    "mmg_linear_fwd_f32": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P]),
+    "mmg_linear_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P]),
+    "mmg_bn_workspace_bytes": (_Z, [_L]),
+    "mmg_bn_fwd_train_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _F, _I, _P, _Z, _P]),
+    "mmg_bn_fwd_eval_f32": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _I, _P]),
+    "mmg_bn_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _P, _Z, _P]),
+    "mmg_conv2d_fwd_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
+    "mmg_conv2d_bwd_data_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
+    "mmg_conv2d_bwd_weight_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
+    "mmg_maxpool2_fwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
+    "mmg_maxpool2_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the library once; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mmg_last_error().decode(errors="replace")
+        if rc == -1 and "Expected more than 1 value per channel" in msg:
+            raise ValueError(msg)
+        if rc < 0:
+            raise ValueError(f"{what}: {msg} (code {rc})")
+        raise NativeError(f"{what}: {msg} (cudaError {rc})")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("mmgan_b200 kernels take CUDA tensors only (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise NativeError("mmgan_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeError("mmgan_b200 modules run on CUDA tensors only (there is no CPU fallback); got a CPU tensor")

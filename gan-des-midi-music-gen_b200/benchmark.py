@@ -1,0 +1,200 @@
+"""Measurement harness behind bench.py (our arm).  See bench.py for the contract."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from .MMGAN_MIDI_DES import datasets as ds
+from .MMGAN_MIDI_DES import network_tests as nt
+from .trainer import MMGANTrainer
+
+FLOP_PER_ROLL = 68.26e6
+METRIC = "mmgan_piano_rolls_per_sec_trained"
+
+
+def _peaks():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = os.path.join(root, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def _synth_rolls_u8(B, W, seed, device):
+    """(B,2,128,W) uint8 rolls: each cell non-zero with p=0.02, generated on host in
+    chunks so that large batches do not need a float64 staging array."""
+    rng = np.random.default_rng(seed)
+    out = torch.empty(B, 2, 128, W, dtype=torch.uint8)
+    for b0 in range(0, B, 4096):
+        n = min(4096, B - b0)
+        mask = rng.random((n, 2, 128, W), dtype=np.float32) < 0.02
+        vel = rng.integers(1, 128, size=(n, 128, W), dtype=np.uint8)
+        dur = rng.integers(1, W + 1, size=(n, 128, W), dtype=np.uint8)
+        out[b0:b0 + n] = torch.from_numpy(np.stack([vel, dur], axis=1) * mask)
+    return out
+
+
+def _timed(fn, steps, sync):
+    """CUDA-event timing of `steps` calls of fn on the current stream; returns seconds."""
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def _raster_leg(device, peaks, quick):
+    """Secondary metric (BASELINE config 4): notes/s of the rasteriser on MAESTRO-scale synthetic streams."""
+    import raster_oracle as ro        # bench.py's oracle use is limited to the cpu_baseline sample below
+    S, E, T = (1276, 15000, 300.0) if not quick else (128, 15000, 300.0)
+    dt, meta, off = ro.synth_songs(S, E, T, seed=0)
+    kinds = meta & 0xFF
+    d_dt, d_meta, d_off = (torch.from_numpy(a).to(device) for a in (dt, meta.view(np.int32), off))
+    fn = lambda i: ds.rasterize_events(d_dt, d_meta, d_off, 300, 0, 300)
+    out = fn(0)
+    for _ in range(3):
+        fn(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    times = []
+    for _ in range(5):
+        flush.zero_()                                   # L2 flush between timed iterations
+        times.append(_timed(fn, 1, torch.cuda.synchronize))
+    sec = min(times)
+    # notes actually applied (note_on before each song's cut-off): count from the output is ambiguous, use the oracle's count on a sample
+    sample = min(S, 64)
+    t0 = time.perf_counter()
+    _, notes_sample = ro.raster_batch_c(dt[:off[sample]], meta[:off[sample]], off[:sample + 1], 300, 0, 300)
+    cpu_sec = time.perf_counter() - t0
+    n_on = int((kinds == 1).sum())
+    alg_bytes = 12.0 * S * E + 2 * 128 * 300 * 4.0 * S
+    return {"notes_per_sec": n_on / sec, "messages_per_sec": S * E / sec, "ms": sec * 1e3, "songs": S, "messages_per_song": E, "window": 300,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                         "algorithmic_bytes": alg_bytes},
+            "cpu_baseline": {"value": (n_on * sample / S) / cpu_sec, "unit": "notes/s", "cores": 1, "kind": "port",
+                             "sample": f"first {sample} songs through oracle/raster_oracle.c"},
+            "checksum": float(out.double().sum().item())}
+
+
+def run(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    precision = args.precision or "fp32"
+    B = args.batch or (4096 if precision == "fp32" else 16384)
+    W = 50
+    peaks = _peaks()
+    sync = torch.cuda.synchronize
+
+    torch.manual_seed(1234 + rank)
+    mmgan = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, W), input_dim=50, output_dim=20, instrument=0, start=100,
+                             end=150, device=device)
+    mmgan.train()
+    trainer = MMGANTrainer(mmgan, lr=0.01, precision=precision)
+
+    # ---- host (pinned) and device copies of one step's inputs
+    h = {k: _synth_rolls_u8(B, W, 100 * rank + i, "cpu").pin_memory() for i, k in enumerate(("real", "fake_d", "fake_g"))}
+    h["beats"] = (25.0 * torch.rand(B, 50)).pin_memory()
+    d = {k: v.to(device) for k, v in h.items()}
+    noise = [torch.randn(B, 50, device=device) for _ in range(4)]
+
+    def step_resident(i):
+        return trainer.step(noise[0], noise[1], d["beats"], d["real"], d["fake_d"], d["fake_g"], noise[2], noise[3])
+
+    stage = {k: torch.empty_like(v, device=device) for k, v in h.items()}
+    losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        for k in stage:
+            stage[k].copy_(h[k], non_blocking=True)
+        n1, n2 = torch.randn(B, 50, device=device), torch.randn(B, 50, device=device)     # as network_tests.py:284-285
+        dl, gl = trainer.step(n1, n2, stage["beats"], stage["real"], stage["fake_d"], stage["fake_g"])
+        losses_host.copy_(torch.stack([dl, gl]), non_blocking=False)                        # .item() sync of :320-321
+        return losses_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        sync()
+
+    def measure(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        l0 = N.lib().mmg_launch_count()
+        sec = _timed(fn, args.steps, barrier)
+        launches = N.lib().mmg_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([sec], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = t.item()
+        return sec, launches
+
+    import bench as _b
+    with _b.ClockSampler(local) as clocks:
+        sec, launches = measure(step_resident)
+    sec_e2e, _ = measure(step_e2e)
+    rolls = B * world * args.steps
+    value, e2e = rolls / sec, rolls / sec_e2e
+    h2d = sum(v.numel() * v.element_size() for v in h.values())
+
+    # ---- roofline of the dominant kernel: D conv2 forward (3.15 MMAC/roll), timed alone on this stream
+    x1 = torch.randn(min(B, 4096), 16, 64, 25, device=device)
+    w2, b2 = mmgan.discriminator.conv2.weight.detach(), mmgan.discriminator.conv2.bias.detach()
+    y2 = torch.empty(x1.shape[0], 32, 32, 12, device=device)
+    conv = lambda i: N.call("mmg_conv2d_fwd_f32", N.ptr(x1), N.ptr(w2), N.ptr(b2), N.ptr(y2), x1.shape[0], 16, 64, 25, 32, 4, 4, 2, 1, 1, N.stream())
+    for _ in range(3):
+        conv(0)
+    ksec = _timed(conv, 10, sync) / 10
+    kflops = 2.0 * 3145728 * x1.shape[0]
+    roofline = {"bound": "tensor", "kernel": "conv2d_fwd_kernel (D conv2, fp32 SIMT)", "achieved": kflops / ksec / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": kflops / ksec / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None, "peak_src": peaks["src"],
+                "step_achieved_tflops": FLOP_PER_ROLL * B * args.steps / sec / 1e12}
+
+    line = {"metric": METRIC, "value": value, "unit": "rolls/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "MM-GAN G+D training iteration (network_tests.py:292-315), DES excluded", "batch_per_gpu": B, "global_batch": B * world,
+                       "roll_size": [2, 128, W], "adj_size": [64, 64], "z_dim": 50, "parallelism": f"dp{world}", "precision": precision,
+                       "l2": "inputs larger than L2 (per-step working set > 126 MB)" if B * 3 * 12800 > 126e6 else "working set may fit L2"},
+            "e2e": {"value": e2e, "unit": "rolls/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline}
+
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            import mmgan_oracle as mo
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            Bc = 256
+            sd = mo.synth_state(mo.mmgan_shapes(), seed=0, d_scale=0.25)
+            inp = mo.synth_inputs(Bc, seed=1)
+            adam = {}
+            mo.mmgan_iteration(sd, adam, inp)
+            t0 = time.perf_counter()
+            n_it = 0
+            while time.perf_counter() - t0 < 10.0 and n_it < 50:
+                mo.mmgan_iteration(sd, adam, inp)
+                n_it += 1
+            cs = (time.perf_counter() - t0) / n_it
+            line["cpu_baseline"] = {"value": Bc / cs, "unit": "rolls/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_it} iterations of batch {Bc} through oracle/mmgan_oracle.py (fp32, DES excluded)"}
+        if not args.no_raster:
+            line["raster"] = _raster_leg(device, peaks, quick=False)
+    if rank == 0:
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()

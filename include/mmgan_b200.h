@@ -1,0 +1,93 @@
+/* mmgan_b200 -- C ABI of the B200 (sm_100a) CUDA library behind the MM-GAN / GAN-DES hot path.
+ *
+ * The reference (marja-w/gan-des-midi-music-gen) has no FFI layer: its boundary is the Python API
+ * (nn.Module / Dataset / generate_piano_roll).  The Python mirror in gan-des-midi-music-gen_b200/
+ * keeps that API and calls these entry points through ctypes; a maintainer of the reference binds
+ * them the same way.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says HOST; the caller owns all buffers,
+ *     including `workspace` (size from the matching *_workspace_bytes); kernels never allocate.
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; calls are asynchronous, stream-ordered,
+ *     re-entrant across streams, and never synchronise the host.
+ *   - return value: 0 ok; <0 invalid argument (-1), unsupported shape (-2), workspace too small (-3);
+ *     >0 a cudaError_t.  mmg_last_error() returns a thread-local message.  Nothing throws.
+ *   - tensors are contiguous: activations NCHW or (rows, features); Linear weight (out,in);
+ *     Conv2d weight (Co,Ci,kh,kw); ConvTranspose2d weight (Ci,Co,kh,kw).
+ *   - `act`: 0 none, 1 LeakyReLU(0.2), 2 ReLU, 3 sigmoid.
+ */
+#ifndef MMGAN_B200_H
+#define MMGAN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int mmg_abi_version(void);
+const char* mmg_last_error(void);
+uint64_t mmg_launch_count(void);      /* kernels launched by this library so far (process-wide) */
+
+/* ---- piano-roll rasteriser: MMGAN_MIDI_DES/datasets.py:27-54 (generate_piano_roll raster core) ----
+ * Events are the post-mido stream: dt[i] seconds (float64), meta[i] = kind | pitch<<8 | velocity<<16 with
+ * kind 0 other / 1 note_on / 2 note_off; song s owns events [offsets[s], offsets[s+1]).
+ * sequence_length < 0 means None (end+20, datasets.py:14-15).  out: (n_songs, 2, 128, Wout), plane 0 =
+ * piano_roll, plane 1 = durations; out_dtype 0 float32, 1 bfloat16, 2 uint8 (saturating).
+ * status (may be NULL): per song, bit0 = negative time step met (dt < 0, outside the contract),
+ * bit1 = note with pitch >= 128 met (the reference's IndexError path). */
+int mmg_raster_out_width(int start, int end);                          /* datasets.py:49-54 re-slice */
+size_t mmg_raster_workspace_bytes(int64_t n_songs, int64_t total_events);
+int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t* offsets, int64_t n_songs,
+                          int64_t total_events, int sequence_length, int start, int end, int out_dtype, void* out,
+                          int32_t* status, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- losses / optimiser ----
+ * nn.BCEWithLogitsLoss() mean (network_tests.py:248,304-306,313; SIMNN.py:257): loss[0] (+)= mean(l_i);
+ * dlogits = (sigmoid(x) - y) * gscale * (*gscale_dev if not NULL).  targets NULL -> constant target. */
+int mmg_bce_logits_f32(const float* logits, const float* targets, float target_const, int64_t n, float* loss,
+                       int accumulate, float* dlogits, float gscale, const float* gscale_dev, void* stream);
+/* dz = dy * act'(y), y = act(z) */
+int mmg_act_bwd_f32(const float* y, const float* dy, float* dz, int64_t n, int act, void* stream);
+/* torch.optim.Adam (network_tests.py:253-254,308,315; SIMNN.py:258-259,316,331), one vectorised launch per
+ * <= 48 tensors.  ptrs: HOST array of 4*n_tensors device pointers [params | grads | exp_avg | exp_avg_sq];
+ * sizes: HOST array.  step is the 1-based step count AFTER increment; grads are multiplied by grad_scale. */
+int mmg_adam_multi_tensor_f32(int n_tensors, void* const* ptrs, const int64_t* sizes, float lr, float beta1,
+                              float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+/* ---- fp32 layers (full-precision path) ----
+ * nn.Linear (network_tests.py:77,139,154; SIMNN.py:127-128): y = act(x.w^T + b) */
+int mmg_linear_fwd_f32(const float* x, const float* w, const float* b, float* y, int64_t M, int64_t N, int64_t K,
+                       int act, void* stream);
+int mmg_linear_bwd_f32(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t M,
+                       int64_t N, int64_t K, int accumulate, void* stream);
+/* nn.BatchNorm1d / BatchNorm2d over (N, C, HW) fused with the following activation
+ * (network_tests.py:78-79; SIMNN.py:85-87,104-108).  Training: batch mean / biased variance, running stats
+ * updated with the unbiased variance (run_* may be NULL). */
+size_t mmg_bn_workspace_bytes(int64_t C);
+int mmg_bn_fwd_train_f32(const float* z, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                         float* y, float* save_mean, float* save_invstd, int64_t N, int64_t C, int64_t HW,
+                         float momentum, float eps, int act, void* workspace, size_t ws_bytes, void* stream);
+int mmg_bn_fwd_eval_f32(const float* z, const float* gamma, const float* beta, const float* run_mean,
+                        const float* run_var, float* y, int64_t N, int64_t C, int64_t HW, float eps, int act,
+                        void* stream);
+int mmg_bn_bwd_f32(const float* z, const float* dy, const float* gamma, const float* beta, const float* save_mean,
+                   const float* save_invstd, float* dz, float* dgamma, float* dbeta, int64_t N, int64_t C,
+                   int64_t HW, int act, int accumulate, void* workspace, size_t ws_bytes, void* stream);
+/* nn.Conv2d (network_tests.py:150-151; SIMNN.py:123-124) and, through the data gradient,
+ * nn.ConvTranspose2d (SIMNN.py:70-84). */
+int mmg_conv2d_fwd_f32(const float* x, const float* w, const float* b, float* y, int N, int Ci, int H, int W, int Co,
+                       int kh, int kw, int stride, int pad, int act, void* stream);
+int mmg_conv2d_bwd_data_f32(const float* dy, const float* w, const float* b, float* dx, int N, int Ci, int H, int W,
+                            int Co, int kh, int kw, int stride, int pad, int act, void* stream);
+int mmg_conv2d_bwd_weight_f32(const float* x, const float* dy, float* dw, float* db, int N, int Ci, int H, int W,
+                              int Co, int kh, int kw, int stride, int pad, int accumulate, void* stream);
+/* nn.MaxPool2d(2,2) (SIMNN.py:125,138-139) */
+int mmg_maxpool2_fwd_f32(const float* x, float* y, uint8_t* idx, int64_t NC, int H, int W, void* stream);
+int mmg_maxpool2_bwd_f32(const float* dy, const uint8_t* idx, float* dx, int64_t NC, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMGAN_B200_H */

@@ -1,0 +1,100 @@
+"""GPU parity: CUDA rasteriser (through the C ABI) vs the golden vectors frozen from the unmodified
+reference and vs the oracle; bit-exact (integer work)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import raster_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.cuda()
+
+
+def _run(dt, meta, off, sl, start, end, out_dtype=torch.float32, status=False):
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    return ds.rasterize_events(_dev(dt.astype(np.float64)), _dev(meta.astype(np.uint32).view(np.int32)), _dev(off.astype(np.int64)),
+                               sl, start, end, out_dtype, status)
+
+
+def test_golden_cases(golden_dir):
+    c = np.load(os.path.join(golden_dir, "raster_cases.npz"))
+    for name in c["names"]:
+        sl, start, end = (int(v) for v in c[name + ".args"])
+        sl = None if sl < 0 else sl
+        dt, meta = c[name + ".dt"], c[name + ".meta"]
+        out = _run(dt, meta, np.array([0, len(dt)]), sl, start, end).cpu().numpy()
+        assert out.shape[2:] == c[name + ".roll"].shape, name
+        assert np.array_equal(out[0, 0], c[name + ".roll"]), name
+        assert np.array_equal(out[0, 1], c[name + ".dur"]), name
+
+
+def test_golden_cases_as_one_ragged_batch(golden_dir):
+    """all default-argument cases in ONE launch (ragged offsets, an empty song included)."""
+    c = np.load(os.path.join(golden_dir, "raster_cases.npz"))
+    names = [n for n in c["names"] if tuple(c[n + ".args"]) == (100, 0, 50)]
+    assert "empty" in names and len(names) >= 4
+    dt = np.concatenate([c[n + ".dt"] for n in names])
+    meta = np.concatenate([c[n + ".meta"] for n in names])
+    off = np.concatenate([[0], np.cumsum([len(c[n + ".dt"]) for n in names])])
+    out = _run(dt, meta, off, 100, 0, 50).cpu().numpy()
+    for i, n in enumerate(names):
+        assert np.array_equal(out[i, 0], c[n + ".roll"]) and np.array_equal(out[i, 1], c[n + ".dur"]), n
+
+
+@pytest.mark.parametrize("args", [(100, 0, 50), (300, 0, 300), (40, 3, 33), (200, 10, 140), (None, 0, 17), (700, 0, 600)])
+def test_random_ragged_vs_oracle(args):
+    rng = np.random.default_rng(11)
+    lens = [0, 1, 17, 0, 900, 33, 2500, 64, 4096]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    E = int(off[-1])
+    dt = rng.exponential(0.07, size=E)
+    dt[rng.random(E) < 0.2] = 0.5            # exact .5 boundaries
+    meta = ro.pack_meta(rng.integers(0, 3, E), rng.integers(0, 128, E), rng.integers(0, 128, E))
+    want, _ = ro.raster_batch_c(dt, meta, off, *args)
+    got, st = _run(dt, meta, off, *args, status=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert not st.any()
+
+
+def test_maestro_scale_full_size_vs_c_oracle():
+    """BASELINE config 4 at full size: 1276 songs x 15000 messages, 300-step window, bit-exact."""
+    dt, meta, off = ro.synth_songs(1276, 15000, 300.0, seed=0)
+    want, notes = ro.raster_batch_c(dt, meta, off, 300, 0, 300, n_threads=os.cpu_count() or 1)
+    got = _run(dt, meta, off, 300, 0, 300)
+    g = got.cpu().numpy()
+    assert np.array_equal(g, want)
+    # size-independent properties: idempotence, and the uint8 output equals the saturated f32 output
+    again = _run(dt, meta, off, 300, 0, 300)
+    assert torch.equal(got, again)
+    u8 = _run(dt, meta, off, 300, 0, 300, torch.uint8).cpu().numpy()
+    assert np.array_equal(u8, np.minimum(want, 255).astype(np.uint8))
+    assert notes > 3_000_000
+
+
+def test_out_of_contract_inputs_are_flagged():
+    dt = np.array([1.0, -3.0, 1.0])
+    meta = ro.pack_meta([1, 1, 1], [60, 61, 62], [9, 9, 9])
+    out, st = _run(dt, meta, np.array([0, 3]), 100, 0, 50, status=True)
+    assert int(st[0]) & 1
+    assert out[0, 0, 60, 1] == 9 and out[0, 0, 61].sum() == 0
+
+
+def test_generate_piano_roll_api(golden_dir):
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    c = np.load(os.path.join(golden_dir, "raster_cases.npz"))
+    kind, pitch, vel = ro.unpack_meta(c["K1.meta"])
+    s = ds.EventStream.from_arrays(c["K1.dt"], kind, pitch, vel, beats=[0.5, 1.0])
+    roll, dur, beats = ds.generate_piano_roll(s)
+    assert roll.dtype == np.float64 and roll.shape == (128, 50)
+    assert np.array_equal(roll, c["K1.roll"]) and np.array_equal(dur, c["K1.dur"])
+    assert beats.shape == (50,) and beats[1] == 1.0 and not beats[2:].any()       # K10
+    roll4, _, _ = ds.generate_piano_roll(s, start=2, end=52)
+    assert np.array_equal(roll4, c["K4.roll"])
+    item = ds.MaestroDatasetMidi([s], 100, 50, device="cuda")[0]
+    assert item[0].shape == (128, 50) and item[0].dtype == torch.float32 and item[0].is_cuda
