@@ -184,10 +184,10 @@ def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, ou
         raise ValueError("end-start must be >= 0")
     S, E = offsets.numel() - 1, dt.numel()
     Wo = out_width(start, end)
-    out = torch.zeros(S, 2, 128, Wo, device=dt.device, dtype=out_dtype)
+    out = torch.empty(S, 2, 128, Wo, device=dt.device, dtype=out_dtype)      # the kernel writes every cell
     st = torch.zeros(S, device=dt.device, dtype=torch.int32) if status else None
     ws_bytes = N.lib().mmg_raster_workspace_bytes(S, E)
-    ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8)
+    ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8) if ws_bytes else None
     N.call("mmg_raster_piano_roll", N.ptr(dt), N.ptr(meta), N.ptr(offsets), S, E, -1 if sequence_length is None else int(sequence_length),
            int(start), int(end), _TORCH_OUT[out_dtype], N.ptr(out), N.ptr(st), N.ptr(ws), ws_bytes, N.stream())
     return (out, st) if status else out

@@ -22,6 +22,8 @@ SIGNATURES = {
     "mmg_raster_workspace_bytes": (_Z, [_L, _L]),
     "mmg_raster_piano_roll": (_I, [_P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mmg_bce_logits_f32": (_I, [_P, _P, _F, _L, _P, _I, _P, _F, _P, _P]),
+    "mmg_fill_scalar_f32": (_I, [_P, _P, _L, _P]),
+    "mmg_sum_f32": (_I, [_P, _L, _P, _I, _P]),
     "mmg_act_bwd_f32": (_I, [_P, _P, _P, _L, _I, _P]),
     "mmg_adam_multi_tensor_f32": (_I, [_I, _P, _P, _F, _F, _F, _F, _L, _F, _P]),
     "mmg_linear_fwd_f32": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P]),
@@ -35,6 +37,14 @@ SIGNATURES = {
     "mmg_conv2d_bwd_weight_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
     "mmg_maxpool2_fwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "mmg_maxpool2_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
+    "mmg_disc_packed_weights_bytes": (_Z, []),
+    "mmg_disc_pack_weights": (_I, [_P, _P, _P, _P, _P]),
+    "mmg_disc_conv1_fwd": (_I, [_P, _I, _P, _P, _P, _L, _P]),
+    "mmg_disc_conv2_fwd": (_I, [_P, _P, _P, _P, _P, _L, _P]),
+    "mmg_disc_fc_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _P]),
+    "mmg_disc_conv2_wgrad": (_I, [_P, _P, _P, _L, _P]),
+    "mmg_disc_conv2_dgrad": (_I, [_P, _P, _P, _P, _P, _L, _P]),
+    "mmg_disc_conv1_wgrad": (_I, [_P, _I, _P, _P, _L, _P]),
 }
 
 _lib = None

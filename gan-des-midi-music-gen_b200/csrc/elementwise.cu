@@ -33,6 +33,25 @@ __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restr
         dz[i] = dy[i] * mmg_act_grad(y[i], act);
 }
 
+__global__ void fill_scalar_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    const float v = src[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, long long n, float* __restrict__ out, int accumulate) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = red[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + (float)v;
+    }
+}
+
 constexpr int ADAM_MAX_TENSORS = 48;
 struct AdamTable {
     float* p[ADAM_MAX_TENSORS];
@@ -84,6 +103,23 @@ int mmg_bce_logits_f32(const float* logits, const float* targets, float target_c
     MMG_REQUIRE(n > 0 && logits, MMG_EINVAL, "bce: empty input");
     bce_logits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, targets, target_const, n, 1.f / (float)n, gscale_dev, gscale, loss,
                                                            accumulate, dlogits);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// dst[0..n) = *src  (e.g. logits initialised with the fc bias before the fused conv2+fc kernel accumulates into them)
+int mmg_fill_scalar_f32(float* dst, const float* src_dev, int64_t n, void* stream) {
+    MMG_REQUIRE(n >= 0 && (n == 0 || (dst && src_dev)), MMG_EINVAL, "fill_scalar: bad arguments");
+    if (n == 0) return MMG_OK;
+    fill_scalar_kernel<<<mmg_grid(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(dst, src_dev, n);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// out[0] (+)= sum(x)   (fc bias gradient = sum of dlogits)
+int mmg_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream) {
+    MMG_REQUIRE(n >= 0 && out, MMG_EINVAL, "sum: bad arguments");
+    sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out, accumulate);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

@@ -1,0 +1,68 @@
+"""bf16 tensor-core execution of DiscriminatorCNN (forward + backward) over the C ABI.
+
+``DiscTC`` wraps a ``DiscriminatorCNN`` module (fp32 master parameters, the reference's state-dict keys):
+it owns the packed bf16 weights and the activation buffers in the padded space-to-depth layout described
+in csrc/disc_tc.cu, and exposes ``forward(x) -> logits`` / ``backward(dlogit)`` which accumulates the six
+parameter gradients into ``param.grad`` (fp32), exactly where ``loss.backward()`` would put them.
+"""
+import torch
+
+from . import _native as N
+
+ROWS = 429
+_XD = {torch.float32: 0, torch.uint8: 2}
+
+
+class DiscTC:
+    def __init__(self, disc, max_batch, roll_size=(2, 128, 50)):
+        if tuple(roll_size) != (2, 128, 50) or disc.conv1.weight.shape != (16, 2, 4, 4) or disc.conv2.weight.shape != (32, 16, 4, 4):
+            raise ValueError("the tensor-core discriminator path is specialised to roll_size (2,128,50), hidden_dim 16")
+        self.d = disc
+        dev = disc.conv1.weight.device
+        N.require_cuda(disc.conv1.weight)
+        self.dev, self.cap = dev, int(max_batch)
+        self.packed = torch.zeros(N.lib().mmg_disc_packed_weights_bytes(), dtype=torch.uint8, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.p1 = torch.zeros(self.cap * ROWS, 64, **bf)            # pad cells stay zero forever
+        self.a2 = torch.empty(self.cap * ROWS, 32, **bf)
+        self.dz2 = torch.empty(self.cap * ROWS, 32, **bf)
+        self.dz1 = torch.empty(self.cap * ROWS, 64, **bf)
+        self.logits = torch.empty(self.cap, device=dev)
+        self.x, self.B = None, 0
+        self.pack()
+
+    def pack(self):
+        """Re-derive the operand layouts from the fp32 master weights (call after every optimiser step)."""
+        d = self.d
+        N.call("mmg_disc_pack_weights", N.ptr(d.conv1.weight.data), N.ptr(d.conv2.weight.data), N.ptr(d.fc.weight.data), N.ptr(self.packed), N.stream())
+
+    def forward(self, x):
+        """x: (B,2,128,50) uint8 or float32 CUDA tensor -> logits (B,) fp32 (a view of an internal buffer)."""
+        N.require_cuda(x)
+        B = x.shape[0]
+        if B > self.cap or tuple(x.shape[1:]) != (2, 128, 50) or x.dtype not in _XD:
+            raise ValueError(f"bad discriminator input {tuple(x.shape)} {x.dtype} (capacity {self.cap})")
+        x = x.contiguous()
+        d, s = self.d, N.stream()
+        logits = self.logits[:B]
+        N.call("mmg_fill_scalar_f32", N.ptr(logits), N.ptr(d.fc.bias.data), B, s)
+        N.call("mmg_disc_conv1_fwd", N.ptr(x), _XD[x.dtype], N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(self.p1), B, s)
+        N.call("mmg_disc_conv2_fwd", N.ptr(self.p1), N.ptr(self.packed), N.ptr(d.conv2.bias.data), N.ptr(self.a2), N.ptr(logits), B, s)
+        self.x, self.B = x, B
+        return logits
+
+    def _grad(self, p):
+        if p.grad is None:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return p.grad
+
+    def backward(self, dlogit):
+        """dlogit: (B,) fp32 = dLoss/dlogits of the last forward.  Accumulates into the six ``.grad`` tensors."""
+        B, d, s = self.B, self.d, N.stream()
+        dlogit = dlogit.contiguous()
+        g = {k: self._grad(p) for k, p in d.named_parameters()}
+        N.call("mmg_sum_f32", N.ptr(dlogit), B, N.ptr(g["fc.bias"]), 1, s)
+        N.call("mmg_disc_fc_bwd", N.ptr(self.a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(self.dz2), N.ptr(g["fc.weight"]), N.ptr(g["conv2.bias"]), B, s)
+        N.call("mmg_disc_conv2_wgrad", N.ptr(self.p1), N.ptr(self.dz2), N.ptr(g["conv2.weight"]), B, s)
+        N.call("mmg_disc_conv2_dgrad", N.ptr(self.dz2), N.ptr(self.packed), N.ptr(self.p1), N.ptr(self.dz1), N.ptr(g["conv1.bias"]), B, s)
+        N.call("mmg_disc_conv1_wgrad", N.ptr(self.x), _XD[self.x.dtype], N.ptr(self.dz1), N.ptr(g["conv1.weight"]), B, s)

@@ -48,6 +48,8 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
  * dlogits = (sigmoid(x) - y) * gscale * (*gscale_dev if not NULL).  targets NULL -> constant target. */
 int mmg_bce_logits_f32(const float* logits, const float* targets, float target_const, int64_t n, float* loss,
                        int accumulate, float* dlogits, float gscale, const float* gscale_dev, void* stream);
+int mmg_fill_scalar_f32(float* dst, const float* src_dev, int64_t n, void* stream);   /* dst[:] = *src_dev */
+int mmg_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream);  /* out[0] (+)= sum(x) */
 /* dz = dy * act'(y), y = act(z) */
 int mmg_act_bwd_f32(const float* y, const float* dy, float* dz, int64_t n, int act, void* stream);
 /* torch.optim.Adam (network_tests.py:253-254,308,315; SIMNN.py:258-259,316,331), one vectorised launch per
@@ -86,6 +88,21 @@ int mmg_conv2d_bwd_weight_f32(const float* x, const float* dy, float* dw, float*
 /* nn.MaxPool2d(2,2) (SIMNN.py:125,138-139) */
 int mmg_maxpool2_fwd_f32(const float* x, float* y, uint8_t* idx, int64_t NC, int H, int W, void* stream);
 int mmg_maxpool2_bwd_f32(const float* dy, const uint8_t* idx, float* dx, int64_t NC, int H, int W, void* stream);
+
+/* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
+ * Activations live in a padded space-to-depth layout (see csrc/disc_tc.cu): P1 / DZ1 are (B*429, 64) bf16,
+ * A2 / DZ2 are (B*429, 32) bf16; x is (B,2,128,50) uint8 (x_dtype 2) or float32 (x_dtype 0).
+ * `packed` = mmg_disc_packed_weights_bytes() bytes filled by mmg_disc_pack_weights from the fp32 nn.Parameters.
+ * P1's pad cells must be zero (allocate zeroed, reuse).  logits must be initialised (fc bias) before conv2_fwd.
+ * Gradient outputs are fp32, in the reference's parameter layouts, and are ACCUMULATED into (+=). */
+size_t mmg_disc_packed_weights_bytes(void);
+int mmg_disc_pack_weights(const float* conv1_w, const float* conv2_w, const float* fc_w, void* packed, void* stream);
+int mmg_disc_conv1_fwd(const void* x, int x_dtype, const void* packed, const float* conv1_b, void* p1, int64_t B, void* stream);
+int mmg_disc_conv2_fwd(const void* p1, const void* packed, const float* conv2_b, void* a2, float* logits, int64_t B, void* stream);
+int mmg_disc_fc_bwd(const void* a2, const float* dlogit, const void* packed, void* dz2, float* dfc_w, float* dconv2_b, int64_t B, void* stream);
+int mmg_disc_conv2_wgrad(const void* p1, const void* dz2, float* dconv2_w, int64_t B, void* stream);
+int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1, float* dconv1_b, int64_t B, void* stream);
+int mmg_disc_conv1_wgrad(const void* x, int x_dtype, const void* dz1, float* dconv1_w, int64_t B, void* stream);
 
 #ifdef __cplusplus
 }

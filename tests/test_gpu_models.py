@@ -140,7 +140,7 @@ def test_generator_backward_injected_grad():
     sd0 = mo.synth_state(shapes, seed=21)
     inp = mo.synth_inputs(B, seed=22)
     gout = torch.from_numpy(np.random.default_rng(23).standard_normal((B, 16)).astype(np.float32))
-    keys = [k for k in shapes if k.startswith("generator2") and (".0." in k or k.endswith(".1.weight") or k.endswith(".1.bias"))]
+    keys = [k for k in shapes if k.startswith("generator2") and k.endswith((".0.weight", ".0.bias", ".1.weight", ".1.bias"))]
     ref_sd = {k: (v.clone().requires_grad_(True) if k in keys else v.clone()) for k, v in sd0.items()}
     x_ref = inp["beats"].clone().requires_grad_(True)
     y = mo.gen_forward(ref_sd, "generator2", inp["noise2"], x_ref, training=True)
