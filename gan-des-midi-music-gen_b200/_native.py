@@ -23,6 +23,7 @@ SIGNATURES = {
     "mmg_raster_piano_roll": (_I, [_P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mmg_bce_logits_f32": (_I, [_P, _P, _F, _L, _P, _I, _P, _F, _P, _P]),
     "mmg_fill_scalar_f32": (_I, [_P, _P, _L, _P]),
+    "mmg_zero": (_I, [_P, _Z, _P]),
     "mmg_sum_f32": (_I, [_P, _L, _P, _I, _P]),
     "mmg_act_bwd_f32": (_I, [_P, _P, _P, _L, _I, _P]),
     "mmg_adam_multi_tensor_f32": (_I, [_I, _P, _P, _F, _F, _F, _F, _L, _F, _P]),

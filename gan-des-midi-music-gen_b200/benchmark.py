@@ -93,8 +93,8 @@ def run(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    precision = args.precision or "fp32"
-    B = args.batch or (4096 if precision == "fp32" else 16384)
+    precision = args.precision or "bf16"
+    B = args.batch or (4096 if precision == "fp32" else 8192)
     W = 50
     peaks = _peaks()
     sync = torch.cuda.synchronize
@@ -103,7 +103,7 @@ def run(args):
     mmgan = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, W), input_dim=50, output_dim=20, instrument=0, start=100,
                              end=150, device=device)
     mmgan.train()
-    trainer = MMGANTrainer(mmgan, lr=0.01, precision=precision)
+    trainer = MMGANTrainer(mmgan, lr=0.01, precision=precision, max_batch=B)
 
     # ---- host (pinned) and device copies of one step's inputs
     h = {k: _synth_rolls_u8(B, W, 100 * rank + i, "cpu").pin_memory() for i, k in enumerate(("real", "fake_d", "fake_g"))}
@@ -151,18 +151,30 @@ def run(args):
     value, e2e = rolls / sec, rolls / sec_e2e
     h2d = sum(v.numel() * v.element_size() for v in h.values())
 
-    # ---- roofline of the dominant kernel: D conv2 forward (3.15 MMAC/roll), timed alone on this stream
-    x1 = torch.randn(min(B, 4096), 16, 64, 25, device=device)
-    w2, b2 = mmgan.discriminator.conv2.weight.detach(), mmgan.discriminator.conv2.bias.detach()
-    y2 = torch.empty(x1.shape[0], 32, 32, 12, device=device)
-    conv = lambda i: N.call("mmg_conv2d_fwd_f32", N.ptr(x1), N.ptr(w2), N.ptr(b2), N.ptr(y2), x1.shape[0], 16, 64, 25, 32, 4, 4, 2, 1, 1, N.stream())
+    # ---- roofline of the tensor-core kernel (D conv2 forward, 3.15 MMAC/roll of the 34.1), timed alone on this stream
+    if precision == "bf16":
+        tcd = trainer.tc
+        Bk = min(B, tcd.cap)
+        conv = lambda i: N.call("mmg_disc_conv2_fwd", N.ptr(tcd.p1), N.ptr(tcd.packed), N.ptr(mmgan.discriminator.conv2.bias.data), N.ptr(tcd.a2),
+                                N.ptr(tcd.logits), Bk, N.stream())
+        kname = "conv2_fwd_tc_kernel (D conv2, tcgen05 tap-shift GEMM, bf16)"
+    else:
+        Bk = min(B, 4096)
+        x1 = torch.randn(Bk, 16, 64, 25, device=device)
+        w2, b2 = mmgan.discriminator.conv2.weight.detach(), mmgan.discriminator.conv2.bias.detach()
+        y2 = torch.empty(Bk, 32, 32, 12, device=device)
+        conv = lambda i: N.call("mmg_conv2d_fwd_f32", N.ptr(x1), N.ptr(w2), N.ptr(b2), N.ptr(y2), Bk, 16, 64, 25, 32, 4, 4, 2, 1, 1, N.stream())
+        kname = "conv2d_fwd_kernel (D conv2, fp32 SIMT)"
     for _ in range(3):
         conv(0)
     ksec = _timed(conv, 10, sync) / 10
-    kflops = 2.0 * 3145728 * x1.shape[0]
-    roofline = {"bound": "tensor", "kernel": "conv2d_fwd_kernel (D conv2, fp32 SIMT)", "achieved": kflops / ksec / 1e12, "peak": peaks["bf16_tflops_sustained"],
+    kflops = 2.0 * 3145728 * Bk
+    kbytes = Bk * 429 * (128 + 64.0)            # P1 read once + A2 written once (bf16 path)
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": kflops / ksec / 1e12, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": kflops / ksec / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None, "peak_src": peaks["src"],
-                "step_achieved_tflops": FLOP_PER_ROLL * B * args.steps / sec / 1e12}
+                "kernel_us": ksec * 1e6, "kernel_hbm_gbs": kbytes / ksec / 1e9 if precision == "bf16" else None,
+                "step_achieved_tflops": FLOP_PER_ROLL * B * args.steps / sec / 1e12,
+                "step_frac_of_bf16_peak": FLOP_PER_ROLL * B * args.steps / sec / 1e12 / peaks["bf16_tflops_sustained"]}
 
     line = {"metric": METRIC, "value": value, "unit": "rolls/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

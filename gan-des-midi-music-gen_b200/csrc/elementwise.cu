@@ -116,6 +116,13 @@ int mmg_fill_scalar_f32(float* dst, const float* src_dev, int64_t n, void* strea
     return MMG_OK;
 }
 
+// stream-ordered zero fill (gradient buffers)
+int mmg_zero(void* dst, size_t bytes, void* stream) {
+    MMG_REQUIRE(bytes == 0 || dst, MMG_EINVAL, "zero: null pointer");
+    if (bytes) MMG_CUDA(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream));
+    return MMG_OK;
+}
+
 // out[0] (+)= sum(x)   (fc bias gradient = sum of dlogits)
 int mmg_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream) {
     MMG_REQUIRE(n >= 0 && out, MMG_EINVAL, "sum: bad arguments");

@@ -10,63 +10,131 @@ The fake rolls are what the host DES bridge returned for the two generator forwa
 inputs.  Rolls may be float32 or uint8 (B,2,128,W) tensors (piano-roll values are integers 0..127 and
 durations < 256, so uint8 is exact and quarters the H2D / HBM traffic).
 
-precision='fp32' : the drop-in nn.Modules + autograd over the fp32 kernels (reference tolerance).
-Data parallel: with torch.distributed initialised (NCCL), the batch is sharded by rank, the D
-gradients are averaged with one all-reduce per optimiser step (84 KB) and the G-step D grads are not
-reduced (the reference discards them).
+precision='fp32' : the drop-in nn.Modules + autograd over the fp32 SIMT kernels (reference tolerance).
+precision='bf16' : discriminator on the tcgen05 tensor-core kernels (disc_tc.DiscTC): bf16 operands,
+                   fp32 accumulation, fp32 master weights / Adam state; fused BCE and multi-tensor Adam.
+Data parallel: with torch.distributed initialised (NCCL) the batch is sharded by rank, the D gradients
+live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step (the 1/world factor is
+folded into the Adam kernel), and the G-step D grads are not reduced (the reference discards them).
 """
 import torch
 
+from . import _native as N
 from . import functional as Fn
 from .optim import FusedAdam
 
 
+def shard_batch(t, rank, world):
+    """Rank's contiguous slice of a global batch tensor (dim 0); the global batch must divide evenly."""
+    n = t.shape[0]
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by world size {world}")
+    per = n // world
+    return t[rank * per:(rank + 1) * per]
+
+
 class MMGANTrainer:
-    def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", process_group=None, sync_bn=False):
-        if precision != "fp32":
-            raise NotImplementedError("bf16 tensor-core path: see trainer_bf16 (not wired yet)")
+    def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
         self.m = mmgan
         self.precision = precision
-        self.disc_opt = FusedAdam(mmgan.discriminator.parameters(), lr=lr, betas=betas, eps=eps)
+        D = mmgan.discriminator
+        self.d_params = list(D.parameters())
+        # one flat gradient buffer; every p.grad is a view into it (single memset / all-reduce / Adam launch)
+        self.flat_grad = torch.zeros(sum(p.numel() for p in self.d_params), device=self.d_params[0].device)
+        o = 0
+        for p in self.d_params:
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.disc_opt = FusedAdam(self.d_params, lr=lr, betas=betas, eps=eps)
         self.gen_opt = FusedAdam(list(mmgan.generator1.parameters()) + list(mmgan.generator2.parameters()), lr=lr, betas=betas, eps=eps)
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        self._flat = None
+        dist = torch.distributed
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.on_d_grads = None
+        self.tc = None
+        if precision == "bf16":
+            if max_batch is None:
+                raise ValueError("precision='bf16' needs max_batch (activation buffers are preallocated)")
+            from .disc_tc import DiscTC
+            self.tc = DiscTC(D, max_batch)
+        dev = self.flat_grad.device
+        self.loss_d = torch.zeros(1, device=dev)
+        self.loss_g = torch.zeros(1, device=dev)
+        self.dlogit = torch.empty(max_batch or 1, device=dev)
+
+    # ------------------------------------------------------------------ helpers
+    def _zero_d_grads(self):
+        N.call("mmg_zero", N.ptr(self.flat_grad), self.flat_grad.numel() * 4, N.stream())
+        o = 0
+        for p in self.d_params:       # re-attach in case something replaced .grad
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
 
     def _allreduce_d_grads(self):
-        if self.world == 1:
-            return
-        ps = [p for p in self.m.discriminator.parameters()]
-        flat = torch.cat([p.grad.reshape(-1) for p in ps])
-        torch.distributed.all_reduce(flat, group=self.pg)
-        flat.div_(self.world)
-        o = 0
-        for p in ps:
-            n = p.numel()
-            p.grad.copy_(flat[o:o + n].view_as(p))
-            o += n
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)       # sum; 1/world is applied inside the Adam kernel
 
+    def _disc_adam(self):
+        opt = self.disc_opt
+        g = opt.param_groups[0]
+        st = opt.state
+        for p in self.d_params:
+            if not st[p]:
+                st[p]["step"] = 0
+                st[p]["exp_avg"] = torch.zeros_like(p)
+                st[p]["exp_avg_sq"] = torch.zeros_like(p)
+            st[p]["step"] += 1
+        Fn.adam_step([p.data for p in self.d_params], [p.grad for p in self.d_params], [st[p]["exp_avg"] for p in self.d_params],
+                     [st[p]["exp_avg_sq"] for p in self.d_params], st[self.d_params[0]]["step"], g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                     grad_scale=1.0 / self.world)
+
+    def _generators(self, noise1, noise2, beats, inner):
+        m = self.m
+        with torch.no_grad():
+            self.g1_out = m.generator1(noise1, inner)
+            self.g2_out = m.generator2(noise2, beats)
+
+    def _d_pass(self, x, target, loss, accumulate):
+        """forward + BCE + backward of the discriminator on one batch; grads accumulate into flat_grad"""
+        B = x.shape[0]
+        if self.tc is not None:
+            logits = self.tc.forward(x)
+            dl = self.dlogit[:B]
+            N.call("mmg_bce_logits_f32", N.ptr(logits), None, float(target), B, N.ptr(loss), int(accumulate), N.ptr(dl), 1.0 / B, None, N.stream())
+            self.tc.backward(dl)
+            return logits
+        xf = x if x.dtype == torch.float32 else x.float()
+        logits = self.m.discriminator(xf).squeeze(-1)
+        lv = Fn.bce_with_logits(logits, float(target))
+        lv.backward()
+        if accumulate:
+            loss += lv.detach()
+        else:
+            loss.copy_(lv.detach().reshape(1))
+        return logits.detach()
+
+    # ------------------------------------------------------------------ one iteration
     def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None):
-        m, D = self.m, self.m.discriminator
-        B = len(noise1)
-        f = lambda t: t if t.dtype == torch.float32 else t.float()
         # ---- D step (:293-308)
-        self.disc_opt.zero_grad(set_to_none=True)
-        with torch.no_grad():
-            self.g1_out = m.generator1(noise1, inner_d)
-            self.g2_out = m.generator2(noise2, beats)
-        lf = Fn.bce_with_logits(D(f(fake_d)).squeeze(-1), 0.0)
-        lr_ = Fn.bce_with_logits(D(f(real)).squeeze(-1), 1.0)
-        disc_loss = lf + lr_
-        disc_loss.backward()
+        self._zero_d_grads()
+        self._generators(noise1, noise2, beats, inner_d)
+        self.logit_fake_d = self._d_pass(fake_d, 0.0, self.loss_d, False)
+        if self.tc is not None:
+            self.logit_fake_d = self.logit_fake_d.clone()
+        self.logit_real = self._d_pass(real, 1.0, self.loss_d, True)
         self._allreduce_d_grads()
-        self.disc_opt.step()
-        # ---- G step (:311-315)
+        if self.on_d_grads is not None:
+            self.on_d_grads(self)                  # observer hook: flat_grad holds the (summed) D-step gradients Adam is about to consume
+        self._disc_adam()
+        if self.tc is not None:
+            self.logit_real = self.logit_real.clone()
+            self.tc.pack()
+        # ---- G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them
         self.gen_opt.zero_grad(set_to_none=True)
-        with torch.no_grad():
-            self.g1_out = m.generator1(noise1, inner_g)
-            self.g2_out = m.generator2(noise2, beats)
-        gen_loss = Fn.bce_with_logits(D(f(fake_g)).squeeze(-1), 1.0)
-        gen_loss.backward()
+        self._generators(noise1, noise2, beats, inner_g)
+        self.logit_fake_g = self._d_pass(fake_g, 1.0, self.loss_g, False)
         self.gen_opt.step()          # no-op: generator grads are None
-        return disc_loss.detach(), gen_loss.detach()
+        return self.loss_d[0], self.loss_g[0]

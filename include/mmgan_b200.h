@@ -49,6 +49,7 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
 int mmg_bce_logits_f32(const float* logits, const float* targets, float target_const, int64_t n, float* loss,
                        int accumulate, float* dlogits, float gscale, const float* gscale_dev, void* stream);
 int mmg_fill_scalar_f32(float* dst, const float* src_dev, int64_t n, void* stream);   /* dst[:] = *src_dev */
+int mmg_zero(void* dst, size_t bytes, void* stream);                                   /* cudaMemsetAsync(dst, 0, bytes) */
 int mmg_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream);  /* out[0] (+)= sum(x) */
 /* dz = dy * act'(y), y = act(z) */
 int mmg_act_bwd_f32(const float* y, const float* dy, float* dz, int64_t n, int act, void* stream);

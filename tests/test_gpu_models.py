@@ -152,7 +152,10 @@ def test_generator_backward_injected_grad():
     m.generator2(inp["noise2"].to(DEV), x).backward(gout.to(DEV))
     named = dict(m.named_parameters())
     for k, gr in zip(keys, grads[:-1]):
-        _rel_l2(named[k].grad, gr.numpy(), tol=2e-4, what=k)
+        if k.endswith(".0.bias"):       # a bias in front of BatchNorm has an analytically zero gradient: both sides are rounding noise
+            assert named[k].grad.abs().max().item() < 1e-5 and np.abs(gr.numpy()).max() < 1e-5, k
+        else:
+            _rel_l2(named[k].grad, gr.numpy(), tol=2e-4, what=k)
     _rel_l2(x.grad, grads[-1].numpy(), tol=2e-4, what="dx")
 
 

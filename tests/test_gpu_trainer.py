@@ -1,0 +1,99 @@
+"""GPU parity of the fused training iteration (MMGANTrainer.step) against the vectors frozen from the
+unmodified reference loop body (tests/golden/mmgan_b16.npz), in both precisions.
+fp32: losses / logits rel 2e-5, grads and post-Adam weights rel-L2 1e-4.
+bf16: loss rel 1e-3, logits abs 0.5 % of scale, grads rel-L2 1e-2, generator outputs as fp32 (the
+generators still run on the fp32 kernels)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mmgan_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel_l2(a, b):
+    a = a.detach().cpu().double().numpy().ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("precision,u8", [("fp32", False), ("fp32", True), ("bf16", True), ("bf16", False)])
+def test_trainer_step_vs_reference_golden(golden_dir, precision, u8):
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    g = np.load(os.path.join(golden_dir, "mmgan_b16.npz"))
+    B, adj, out_dim, seed, iters = (int(v) for v in g["meta"])
+    sd0 = mo.synth_state(mo.mmgan_shapes(adj_size=(adj, adj), output_dim=out_dim), seed=seed, d_scale=0.25)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(adj, adj), roll_size=(2, 128, 50), input_dim=50, output_dim=out_dim, instrument=0, start=100,
+                         end=150, device=DEV)
+    m.load_state_dict(sd0)
+    m.train()
+    tr = MMGANTrainer(m, lr=0.01, precision=precision, max_batch=B)
+    strict = dict(loss=2e-5, logit=2e-5, grad=1e-4, par=1e-4) if precision == "fp32" else dict(loss=1e-3, logit=5e-3, grad=1e-2, par=2e-2)
+    # bf16 only: Adam's first steps move every weight by ~lr*sign(g), so bf16 rounding of near-zero gradient elements flips
+    # update signs; quantities computed AFTER an optimiser step are compared loosely here and strictly in the next test
+    loose = strict if precision == "fp32" else dict(loss=3e-2, logit=1e-1, grad=1.5e-1, par=1e-1)
+    snap = {}
+    tr.on_d_grads = lambda t: snap.__setitem__("g", t.flat_grad.clone())
+    for it in range(iters):
+        inp = {k: v.to(DEV) for k, v in mo.synth_inputs(B, seed=seed * 1000 + it).items()}
+        conv = (lambda t: t.to(torch.uint8)) if u8 else (lambda t: t)
+        pre = f"it{it}."
+        tol = strict if it == 0 else loose
+        dl, gl = tr.step(inp["noise1"], inp["noise2"], inp["beats"], conv(inp["real"]), conv(inp["fake_d"]), conv(inp["fake_g"]),
+                         torch.from_numpy(g[pre + "inner_d"]).to(DEV), torch.from_numpy(g[pre + "inner_g"]).to(DEV))
+        torch.cuda.synchronize()
+        assert abs(dl.item() - g[pre + "disc_loss"].item()) <= tol["loss"] * abs(g[pre + "disc_loss"].item()), ("disc_loss", it, dl.item())
+        assert abs(gl.item() - g[pre + "gen_loss"].item()) <= loose["loss"] * abs(g[pre + "gen_loss"].item()), ("gen_loss", it, gl.item())
+        for nm, got, tl in (("logit_fake_d", tr.logit_fake_d, tol), ("logit_real", tr.logit_real, tol), ("logit_fake_g", tr.logit_fake_g, loose)):
+            want = g[pre + nm].reshape(-1)
+            assert np.abs(got.cpu().numpy().reshape(-1) - want).max() <= tl["logit"] * np.abs(want).max() + 2e-6, (nm, it)
+        named = dict(m.discriminator.named_parameters())
+        o = 0
+        for k, p in named.items():
+            gd = snap["g"][o:o + p.numel()]
+            o += p.numel()
+            assert _rel_l2(gd, g[pre + "grad_d.discriminator." + k]) <= tol["grad"], ("grad_d." + k, it, _rel_l2(gd, g[pre + "grad_d.discriminator." + k]))
+            # after the G step .grad holds D-step + G-step gradients (reference: gen_opt.zero_grad() leaves them)
+            assert _rel_l2(p.grad, g[pre + "grad_g.discriminator." + k]) <= loose["grad"], ("grad_g." + k, it, _rel_l2(p.grad, g[pre + "grad_g.discriminator." + k]))
+            assert _rel_l2(p, g[pre + "param_d.discriminator." + k]) <= loose["par"], ("param." + k, it, _rel_l2(p, g[pre + "param_d.discriminator." + k]))
+        assert _rel_l2(tr.g2_out, g[pre + "g2_g"]) <= 2e-5
+        assert all(p.grad is None for p in m.generator1.parameters()) and len(tr.gen_opt.state) == 0
+    sd = m.state_dict()
+    for k in g.files:
+        if k.startswith("final.") and "num_batches" in k:
+            assert int(sd[k[6:]]) == int(g[k])
+
+
+def test_bf16_g_step_from_reference_weights(golden_dir):
+    """bf16 G-step pass (D forward on fake_g, BCE vs ones, backward) started from the REFERENCE's post-Adam weights, so that
+    the strict bf16 tolerances apply to post-update quantities too: loss rel 1e-3, logits 0.5 % of scale, grads rel-L2 1e-2."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    g = np.load(os.path.join(golden_dir, "mmgan_b16.npz"))
+    B, adj, out_dim, seed, iters = (int(v) for v in g["meta"])
+    sd0 = mo.synth_state(mo.mmgan_shapes(adj_size=(adj, adj), output_dim=out_dim), seed=seed, d_scale=0.25)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(adj, adj), roll_size=(2, 128, 50), input_dim=50, output_dim=out_dim, instrument=0, start=100,
+                         end=150, device=DEV)
+    m.load_state_dict(sd0)
+    tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=B)
+    for it in range(iters):
+        pre = f"it{it}."
+        with torch.no_grad():
+            for k, p in m.discriminator.named_parameters():
+                p.copy_(torch.from_numpy(g[pre + "param_d.discriminator." + k]))
+        tr.tc.pack()
+        tr._zero_d_grads()
+        inp = mo.synth_inputs(B, seed=seed * 1000 + it)
+        logits = tr._d_pass(inp["fake_g"].to(DEV).to(torch.uint8), 1.0, tr.loss_g, False)
+        torch.cuda.synchronize()
+        want = g[pre + "logit_fake_g"].reshape(-1)
+        assert np.abs(logits.cpu().numpy() - want).max() <= 5e-3 * np.abs(want).max() + 2e-6
+        assert abs(tr.loss_g.item() - g[pre + "gen_loss"].item()) <= 1e-3 * abs(g[pre + "gen_loss"].item())
+        for k, p in m.discriminator.named_parameters():
+            want_g = g[pre + "grad_g.discriminator." + k] - g[pre + "grad_d.discriminator." + k]       # the G-step contribution alone
+            assert _rel_l2(p.grad, want_g) <= 1e-2, (k, it, _rel_l2(p.grad, want_g))

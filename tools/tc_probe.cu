@@ -217,6 +217,71 @@ int main() {
             if (!m64) fails += r != 0;
         }
     }
+
+    // ---------------- E7: conv1 forward shape.  A = 16-byte rows (8 values per super pixel), K=16 = two OVERLAPPING rows
+    //                  (no swizzle, K-major: LBO = 16 B between the two K chunks, SBO = 128 B between 8-row groups)
+    {
+        Mat A(400, 8, 9), Bw(32, 8, 10);       // Bw flat rows: ((ty*2 + c)*2 + g)*8 + i  <->  n = g*8+i, k = ty*16 + c*8 + e
+        CUtensorMap mA, mB;
+        {
+            auto fn = tc::get_encode_fn();
+            cuuint64_t dims[2] = {8, 400}; cuuint64_t strides[1] = {16}; cuuint32_t box[2] = {8, 160}; cuuint32_t es[2] = {1, 1};
+            fn(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A.d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t dimsb[2] = {8, 32}; cuuint32_t boxb[2] = {8, 32};
+            fn(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bw.d, dimsb, strides, boxb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        maps[0] = mA; maps[1] = mB;
+        const uint64_t A_K = tc::smem_desc_base(16, 128, tc::SW_NONE), B_K = tc::smem_desc_base(256, 128, tc::SW_NONE);
+        Prog p{}; p.n_loads = 2; p.ncols = 32;
+        p.loads[0] = {0, 0, 40, 0, 160 * 16}; p.loads[1] = {1, 0, 0, 4096, 32 * 16};
+        p.n_mma = 2;
+        for (int ty = 0; ty < 2; ++ty) p.mma[ty] = {A_K, B_K, (uint32_t)(ty * 26 * 16), (uint32_t)(4096 + ty * 512), 0, tc::idesc_bf16(128, 16), (uint32_t)(ty > 0)};
+        std::vector<float> want(128 * 16);
+        for (int m = 0; m < 128; ++m) for (int n = 0; n < 16; ++n) {
+            float acc = 0;
+            for (int ty = 0; ty < 2; ++ty) for (int c = 0; c < 2; ++c) for (int e = 0; e < 8; ++e)
+                acc += A.at(40 + m + ty * 26 + c, e) * Bw.at(((ty * 2 + c) * 2 + (n >> 3)) * 8 + (n & 7), e);
+            want[m * 16 + n] = acc;
+        }
+        fails += run("E7 conv1-fwd: no-swizzle K-major, overlapping 16-byte rows (LBO=16)", maps, p, 8192, want, 128, 16, 32) != 0;
+
+        // ---------------- E8: conv1 wgrad shape.  A = same rows, MN-major no-swizzle: M = 64 = 8 atoms of 8 values, atom j = row + j (SBO = 16 B),
+        //                  K rows 16 B apart, 8-row groups 128 B apart (LBO);  B = G rows of 16 oc (32 B), MN-major SW32 (SBO = 256 B)
+        Mat G(400, 16, 11);
+        CUtensorMap mG;
+        tc::make_map_2d_bf16(&mG, G.d, 16, 400, 32, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
+        maps[1] = mG;
+        const uint64_t A_MN = tc::smem_desc_base(128, 16, tc::SW_NONE), B_MN = tc::smem_desc_base(0, 256, tc::SW_32B);
+        Prog q{}; q.n_loads = 2; q.ncols = 32;
+        q.loads[0] = {0, 0, 40, 0, 160 * 16}; q.loads[1] = {1, 0, 40, 4096, 64 * 32};
+        q.n_mma = 4;
+        for (int k = 0; k < 4; ++k) q.mma[k] = {A_MN, B_MN, (uint32_t)(k * 16 * 16), (uint32_t)(4096 + k * 16 * 32), 0, tc::idesc_bf16(64, 16, 1, 1), (uint32_t)(k > 0)};
+        std::vector<float> want2(64 * 16);
+        for (int m = 0; m < 64; ++m) for (int n = 0; n < 16; ++n) {
+            float acc = 0;
+            for (int r = 0; r < 64; ++r) acc += A.at(40 + r + (m >> 3), m & 7) * G.at(40 + r, n);
+            want2[m * 16 + n] = acc;
+        }
+        // M=64 results live in lanes (m%16) + 32*(m/16): compare through the lane map
+        {
+            Prog* dp; float* dout;
+            cudaMalloc(&dp, sizeof(Prog)); cudaMemcpy(dp, &q, sizeof(Prog), cudaMemcpyHostToDevice);
+            cudaMalloc(&dout, sizeof(float) * 128 * 32); cudaMemset(dout, 0, sizeof(float) * 128 * 32);
+            probe_kernel<<<1, 128, 8192 + 1024>>>(maps[0], maps[1], maps[2], maps[3], dp, dout);
+            cudaError_t e = cudaDeviceSynchronize();
+            std::vector<float> got(128 * 32);
+            cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost);
+            int bad = 0;
+            for (int m = 0; m < 64; ++m) for (int n = 0; n < 16; ++n) {
+                const int lane = (m % 16) + 32 * (m / 16);
+                if (fabs(got[lane * 32 + n] - want2[m * 16 + n]) > 1e-3) { if (bad < 4) printf("   [E8] m=%d n=%d got=%g want=%g\n", m, n, got[lane * 32 + n], want2[m * 16 + n]); ++bad; }
+            }
+            printf("[E8 conv1-wgrad: MN-major no-swizzle A (atoms 1 row apart) x MN-major SW32 B, M=64 N=16] %s (err=%s bad=%d)\n", bad || e ? "FAIL" : "PASS", cudaGetErrorString(e), bad);
+            fails += (bad || e) ? 1 : 0;
+        }
+    }
     printf("tc_probe: %d failing experiment(s)\n", fails);
     return 0;
 }
