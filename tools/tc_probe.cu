@@ -233,11 +233,6 @@ int main() {
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         maps[0] = mA; maps[1] = mB;
-        const uint64_t A_K = tc::smem_desc_base(16, 128, tc::SW_NONE), B_K = tc::smem_desc_base(256, 128, tc::SW_NONE);
-        Prog p{}; p.n_loads = 2; p.ncols = 32;
-        p.loads[0] = {0, 0, 40, 0, 160 * 16}; p.loads[1] = {1, 0, 0, 4096, 32 * 16};
-        p.n_mma = 2;
-        for (int ty = 0; ty < 2; ++ty) p.mma[ty] = {A_K, B_K, (uint32_t)(ty * 26 * 16), (uint32_t)(4096 + ty * 512), 0, tc::idesc_bf16(128, 16), (uint32_t)(ty > 0)};
         std::vector<float> want(128 * 16);
         for (int m = 0; m < 128; ++m) for (int n = 0; n < 16; ++n) {
             float acc = 0;
@@ -245,7 +240,42 @@ int main() {
                 acc += A.at(40 + m + ty * 26 + c, e) * Bw.at(((ty * 2 + c) * 2 + (n >> 3)) * 8 + (n & 7), e);
             want[m * 16 + n] = acc;
         }
-        fails += run("E7 conv1-fwd: no-swizzle K-major, overlapping 16-byte rows (LBO=16)", maps, p, 8192, want, 128, 16, 32) != 0;
+        // which of LBO / SBO is the K-direction stride for un-swizzled K-major operands?  try all four assignments
+        for (int va = 0; va < 2; ++va) for (int vb = 0; vb < 2; ++vb) {
+            const uint64_t A_K = va ? tc::smem_desc_base(128, 16, tc::SW_NONE) : tc::smem_desc_base(16, 128, tc::SW_NONE);
+            const uint64_t B_K = vb ? tc::smem_desc_base(128, 256, tc::SW_NONE) : tc::smem_desc_base(256, 128, tc::SW_NONE);
+            Prog p{}; p.n_loads = 2; p.ncols = 32;
+            p.loads[0] = {0, 0, 40, 0, 160 * 16}; p.loads[1] = {1, 0, 0, 4096, 32 * 16};
+            p.n_mma = 2;
+            for (int ty = 0; ty < 2; ++ty) p.mma[ty] = {A_K, B_K, (uint32_t)(ty * 26 * 16), (uint32_t)(4096 + ty * 512), 0, tc::idesc_bf16(128, 16), (uint32_t)(ty > 0)};
+            char nm[128]; snprintf(nm, sizeof nm, "E7 conv1-fwd no-swizzle K-major: A(K-stride in %s) B(K-stride in %s)", va ? "SBO" : "LBO", vb ? "SBO" : "LBO");
+            run(nm, maps, p, 8192, want, 128, 16, 32);
+        }
+        // B as a plain SW32 K-major operand [16 n][16 k] per ty (32-byte rows), A as above in both assignments
+        {
+            Mat B2(32, 16, 12);                  // rows ty*16 + n, 16 k values: k = c*8 + e
+            CUtensorMap mB2;
+            tc::make_map_2d_bf16(&mB2, B2.d, 16, 32, 32, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B);
+            maps[1] = mB2;
+            std::vector<float> want3(128 * 16);
+            for (int m = 0; m < 128; ++m) for (int n = 0; n < 16; ++n) {
+                float acc = 0;
+                for (int ty = 0; ty < 2; ++ty) for (int c = 0; c < 2; ++c) for (int e = 0; e < 8; ++e)
+                    acc += A.at(40 + m + ty * 26 + c, e) * B2.at(ty * 16 + n, c * 8 + e);
+                want3[m * 16 + n] = acc;
+            }
+            for (int va = 0; va < 2; ++va) {
+                const uint64_t A_K = va ? tc::smem_desc_base(128, 16, tc::SW_NONE) : tc::smem_desc_base(16, 128, tc::SW_NONE);
+                const uint64_t B_K = tc::smem_desc_base(0, 256, tc::SW_32B);
+                Prog p{}; p.n_loads = 2; p.ncols = 32;
+                p.loads[0] = {0, 0, 40, 0, 160 * 16}; p.loads[1] = {1, 0, 0, 4096, 32 * 32};
+                p.n_mma = 2;
+                for (int ty = 0; ty < 2; ++ty) p.mma[ty] = {A_K, B_K, (uint32_t)(ty * 26 * 16), (uint32_t)(4096 + ty * 512), 0, tc::idesc_bf16(128, 16), (uint32_t)(ty > 0)};
+                char nm[128]; snprintf(nm, sizeof nm, "E7b conv1-fwd: A no-swizzle (K-stride in %s), B SW32 K-major", va ? "SBO" : "LBO");
+                run(nm, maps, p, 8192, want3, 128, 16, 32);
+            }
+            maps[1] = mB;
+        }
 
         // ---------------- E8: conv1 wgrad shape.  A = same rows, MN-major no-swizzle: M = 64 = 8 atoms of 8 values, atom j = row + j (SBO = 16 B),
         //                  K rows 16 B apart, 8-row groups 128 B apart (LBO);  B = G rows of 16 oc (32 B), MN-major SW32 (SBO = 256 B)
