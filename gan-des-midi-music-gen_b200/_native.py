@@ -40,12 +40,13 @@ SIGNATURES = {
     "mmg_maxpool2_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "mmg_disc_packed_weights_bytes": (_Z, []),
     "mmg_disc_pack_weights": (_I, [_P, _P, _P, _P, _P]),
-    "mmg_disc_conv1_fwd": (_I, [_P, _I, _P, _P, _P, _L, _P]),
+    "mmg_disc_xs_pack": (_I, [_P, _I, _P, _L, _P]),
+    "mmg_disc_conv1_fwd": (_I, [_P, _P, _P, _P, _L, _P]),
     "mmg_disc_conv2_fwd": (_I, [_P, _P, _P, _P, _P, _L, _P]),
     "mmg_disc_fc_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _P]),
     "mmg_disc_conv2_wgrad": (_I, [_P, _P, _P, _L, _P]),
     "mmg_disc_conv2_dgrad": (_I, [_P, _P, _P, _P, _P, _L, _P]),
-    "mmg_disc_conv1_wgrad": (_I, [_P, _I, _P, _P, _L, _P]),
+    "mmg_disc_conv1_wgrad": (_I, [_P, _P, _P, _L, _P]),
 }
 
 _lib = None

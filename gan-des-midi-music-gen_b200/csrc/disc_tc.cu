@@ -1,9 +1,13 @@
 // bf16 tensor-core path of the MM-GAN discriminator (DiscriminatorCNN, network_tests.py:147-160):
-//   conv1 2->16 k4 s2 p1 + LeakyReLU   (SIMT, uint8 rolls in, writes the space-to-depth layout below)
+//   conv1 2->16 k4 s2 p1 + LeakyReLU   (tcgen05 tap-shift GEMM over the space-to-depth input XS, K = 2 x 16)
 //   conv2 16->32 k4 s2 p1 + LeakyReLU  (tcgen05 "tap-shift" implicit GEMM fed by TMA) + fc partial dot
 //
 // Data layout in HBM (all bf16 unless noted) -- "S2D" = padded space-to-depth(2):
 //   X    (B,2,128,50) uint8          piano roll / duration planes (values are small integers, exact in bf16)
+//   XS   (B*1690, 8)                 the zero-padded input (y' = iy+1, x' = ix+1) as 65x26 super pixels of 2x2 px x 2 ch:
+//                                    8 values = (dy,dx,ch), 16 bytes per row.  conv1 output row m = b*1690 + oy*26 + ox reads rows
+//                                    m + {0,1,26,27}; the two horizontally adjacent taps are 32 contiguous bytes = one K=16 step,
+//                                    expressed as an un-swizzled K-major operand whose second K chunk starts 16 B later (LBO=16).
 //   P1   (B*429, 64)                 conv1 activations.  Row R = b*429 + sy*13 + sx is one 2x2 super pixel of the
 //                                    zero-padded 66x26 map (y' = iy+1, x' = ix+1), 64 values = (dy,dx,c16).
 //                                    A stride-2 4x4 conv over the 64x25 map is then a stride-1 2x2 conv over the
@@ -24,17 +28,17 @@ constexpr int SG_W = 13;
 // ------------------------------------------------------------------------------------------------
 // weight packing (fp32 master -> operand layouts)
 // ------------------------------------------------------------------------------------------------
-// w1p  fp32 [32 k][16 oc]        k = (ch*4 + ky)*4 + kx, values rounded to bf16 (bf16-operand semantics)
+// w1b  bf16 [2 ty][16 oc][16 k]  k = tx*8 + (dy*2+dx)*2 + ch for ky = 2ty+dy, kx = 2tx+dx                          (conv1 fwd B)
 // w2p  bf16 [4 t][32 oc][64 k]   t = (ky>>1)*2 + (kx>>1), k = ((ky&1)*2 + (kx&1))*16 + ic      (conv2 fwd B, wgrad layout)
 // w2d  bf16 [4 t][64 n][32 oc]   n = ((ky&1)*2 + (kx&1))*16 + ic                                  (conv2 dgrad B)
 // wfcp fp32 [429 r][32 oc]       fc.weight[oc*384 + oy*12 + ox] at r = oy*13 + ox, 0 on junk rows
 __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wfc,
-                                    float* __restrict__ w1p, __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w2d,
+                                    __nv_bfloat16* __restrict__ w1b, __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w2d,
                                     float* __restrict__ wfcp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 512) {                                       // conv1.weight (16,2,4,4)
-        const int oc = i / 32, k = i % 32;
-        w1p[k * 16 + oc] = __bfloat162float(__float2bfloat16(w1[i]));
+        const int oc = i / 32, ch = (i / 16) % 2, ky = (i / 4) % 4, kx = i % 4;
+        w1b[((ky >> 1) * 16 + oc) * 16 + (kx >> 1) * 8 + ((ky & 1) * 2 + (kx & 1)) * 2 + ch] = __float2bfloat16(w1[i]);
     }
     if (i < 8192) {                                      // conv2.weight (32,16,4,4)
         const int oc = i / 256, ic = (i / 16) % 16, ky = (i / 4) % 4, kx = i % 4;
@@ -49,68 +53,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w1, const float* _
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// conv1 forward (SIMT): one CTA per sample, one thread per output position x 16 channels
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
-}
-
-template <typename InT>
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const InT* __restrict__ x, const float* __restrict__ w1p, const float* __restrict__ b1,
-                                                        __nv_bfloat16* __restrict__ p1, int B) {
-    __shared__ __align__(16) float ws[32 * 16];
-    __shared__ float bs[16];
-    __shared__ __nv_bfloat16 xs[2][130][52];             // zero-padded input planes (y' = iy+1, x' = ix+1), bf16 operand
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 512; i += 256) ws[i] = w1p[i];
-    if (tid < 16) bs[tid] = b1[tid];
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        __syncthreads();
-        for (int i = tid; i < 2 * 130 * 52; i += 256) (&xs[0][0][0])[i] = __float2bfloat16(0.f);
-        __syncthreads();
-        const InT* xb = x + (size_t)b * 2 * 128 * 50;
-        for (int i = tid; i < 2 * 128 * 50; i += 256) {
-            const int ch = i / 6400, iy = (i / 50) % 128, ix = i % 50;
-            xs[ch][iy + 1][ix + 1] = __float2bfloat16((float)xb[i]);
-        }
-        __syncthreads();
-        for (int pos = tid; pos < 64 * 25; pos += 256) {
-            const int oy = pos / 25, ox = pos % 25;
-            float acc[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = bs[c];
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch)
-#pragma unroll 1
-                for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 4; ++kx) {
-                        const float v = __bfloat162float(xs[ch][2 * oy + ky][2 * ox + kx]);
-                        const float4* wr = reinterpret_cast<const float4*>(&ws[((ch * 4 + ky) * 4 + kx) * 16]);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 w = wr[q];
-                            acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
-                            acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-                            acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
-                        }
-                    }
-            uint32_t o[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float a0 = acc[2 * c], a1 = acc[2 * c + 1];
-                o[c] = pack_bf16x2(a0 > 0.f ? a0 : 0.2f * a0, a1 > 0.f ? a1 : 0.2f * a1);
-            }
-            const int yp = oy + 1, xp = ox + 1;
-            const size_t row = (size_t)b * ROWS_PER_SAMPLE + (yp >> 1) * SG_W + (xp >> 1);
-            uint4* dst = reinterpret_cast<uint4*>(p1 + row * 64 + ((yp & 1) * 2 + (xp & 1)) * 16);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -247,27 +192,12 @@ extern "C" {
 
 size_t mmg_disc_packed_weights_bytes(void) { return 512 * 4 + 8192 * 2 + 8192 * 2 + ROWS_PER_SAMPLE * 32 * 4; }
 
-// packed: [w1p fp32 512][w2p bf16 8192][w2d bf16 8192][wfcp fp32 429*32]
+// packed: [w1b bf16 512, padded to 2 KB][w2p bf16 8192][w2d bf16 8192][wfcp fp32 429*32]
 int mmg_disc_pack_weights(const float* conv1_w, const float* conv2_w, const float* fc_w, void* packed, void* stream) {
     MMG_REQUIRE(conv1_w && conv2_w && fc_w && packed, MMG_EINVAL, "pack_weights: null pointer");
     unsigned char* p = (unsigned char*)packed;
     pack_weights_kernel<<<(ROWS_PER_SAMPLE * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        conv1_w, conv2_w, fc_w, (float*)p, (__nv_bfloat16*)(p + 2048), (__nv_bfloat16*)(p + 2048 + 16384), (float*)(p + 2048 + 32768));
-    MMG_LAUNCH_CHECK();
-    return MMG_OK;
-}
-
-// x: (B,2,128,50) uint8 (x_dtype 2) or float32 (x_dtype 0);  p1: (B*429, 64) bf16, pad cells must already be zero
-int mmg_disc_conv1_fwd(const void* x, int x_dtype, const void* packed, const float* conv1_b, void* p1, int64_t B, void* stream) {
-    MMG_REQUIRE(x && packed && conv1_b && p1 && B >= 0, MMG_EINVAL, "conv1_fwd: bad arguments");
-    if (B == 0) return MMG_OK;
-    const int grid = (int)(B < 8 * MMG_NUM_SMS ? B : 8 * MMG_NUM_SMS);
-    if (x_dtype == 2)
-        conv1_fwd_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, (const float*)packed, conv1_b, (__nv_bfloat16*)p1, (int)B);
-    else if (x_dtype == 0)
-        conv1_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)packed, conv1_b, (__nv_bfloat16*)p1, (int)B);
-    else
-        MMG_REQUIRE(false, MMG_EINVAL, "conv1_fwd: x_dtype must be 0 (f32) or 2 (u8)");
+        conv1_w, conv2_w, fc_w, (__nv_bfloat16*)p, (__nv_bfloat16*)(p + 2048), (__nv_bfloat16*)(p + 2048 + 16384), (float*)(p + 2048 + 32768));
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

@@ -5,8 +5,8 @@
 //   conv2 wgrad (tcgen05)          dW2[t][k64][oc] = sum_rows P1[row+shift_t][k] * DZ2[row][oc]    both operands MN-major:
 //                                  M = 128 = the two horizontally adjacent taps (second atom = same box, one row later)
 //   conv2 dgrad (tcgen05)          da1[R][n64] = sum_t DZ2[R-shift_t][oc] * W2d[t][n][oc];  epilogue: dz1 = da1*lrelu'(a1),
-//                                  pad cells -> 0, dconv1.b += dz1, DZ1 bf16 written in the P1 layout
-//   conv1 wgrad (SIMT)             dW1[k32][oc16] = sum_pos x_patch[pos][k] * dz1[pos][oc]
+//                                  dconv1.b += dz1, DZ1c bf16 written in conv1's own row space (B*1690, 16)
+//   conv1 wgrad: csrc/disc_tc_conv1.cu (tcgen05)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -242,11 +242,12 @@ __global__ void __launch_bounds__(192, 2) conv2_dgrad_tc_kernel(const __grid_con
                 }
                 if (in) {
                     const uint4* ap = reinterpret_cast<const uint4*>(p1 + (size_t)row * 64 + half * 32);
-                    uint4* op = reinterpret_cast<uint4*>(dz1 + (size_t)row * 64 + half * 32);
-                    const bool pad_y = (sy == 0 && half == 0) || (sy == 32 && half == 1);
+                    const int oy = 2 * sy + half - 1;                 // cell (dy = half, dx) of super pixel (sy,sx) is conv1 output (oy, ox)
 #pragma unroll
                     for (int dx = 0; dx < 2; ++dx) {
-                        const bool pad = pad_y || (sx == 0 && dx == 0);
+                        const int ox = 2 * sx + dx - 1;
+                        if (oy < 0 || oy >= 64 || ox < 0 || ox >= 25) continue;      // zero-padding cells of P1: no conv1 output behind them
+                        uint4* op = reinterpret_cast<uint4*>(dz1 + ((size_t)b * 1690 + oy * 26 + ox) * 16);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {                 // 8 channels per 16-byte vector
                             const uint4 av = ap[dx * 2 + h];
@@ -255,14 +256,13 @@ __global__ void __launch_bounds__(192, 2) conv2_dgrad_tc_kernel(const __grid_con
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int c = dx * 16 + h * 8 + 2 * j;
-                                float g0 = __uint_as_float(r[c]) * (bf_lo(au[j]) > 0.f ? 1.f : 0.2f);
-                                float g1 = __uint_as_float(r[c + 1]) * (bf_hi(au[j]) > 0.f ? 1.f : 0.2f);
-                                if (pad) { g0 = 0.f; g1 = 0.f; }
+                                const float g0 = __uint_as_float(r[c]) * (bf_lo(au[j]) > 0.f ? 1.f : 0.2f);
+                                const float g1 = __uint_as_float(r[c + 1]) * (bf_hi(au[j]) > 0.f ? 1.f : 0.2f);
                                 o[j] = pack_bf16x2(g0, g1);
                                 dbacc[h * 8 + 2 * j] += bf_lo(o[j]);
                                 dbacc[h * 8 + 2 * j + 1] += bf_hi(o[j]);
                             }
-                            op[dx * 2 + h] = make_uint4(o[0], o[1], o[2], o[3]);
+                            op[h] = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
@@ -278,72 +278,6 @@ __global__ void __launch_bounds__(192, 2) conv2_dgrad_tc_kernel(const __grid_con
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem, 128);
     if (threadIdx.x < 16) atomicAdd(&db1[threadIdx.x], db_s[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// conv1 weight gradient (SIMT): lane = patch index k (32), 16 channel accumulators per lane, a warp walks
-// output positions; DZ1 of the sample is staged in shared memory as fp32, the input planes as bf16.
-// ------------------------------------------------------------------------------------------------
-constexpr int C1W_THREADS = 512;
-constexpr int C1W_SMEM = 1600 * 16 * 4 + 2 * 130 * 52 * 2;
-
-template <typename InT>
-__global__ void __launch_bounds__(C1W_THREADS, 1) conv1_wgrad_kernel(const InT* __restrict__ x, const __nv_bfloat16* __restrict__ dz1,
-                                                                      float* __restrict__ dw1, int B) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    float* gs = reinterpret_cast<float*>(sm);                                   // [1600 pos][16 oc]
-    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sm + 1600 * 16 * 4);   // [2][130][52]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ch = lane >> 4, ky = (lane >> 2) & 3, kx = lane & 3;              // k = (ch*4+ky)*4+kx
-    float acc[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-    for (int i = tid; i < 2 * 130 * 52; i += C1W_THREADS) xs[i] = __float2bfloat16(0.f);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        __syncthreads();
-        const InT* xb = x + (size_t)b * 2 * 128 * 50;
-        for (int i = tid; i < 2 * 128 * 50; i += C1W_THREADS) {
-            const int c = i / 6400, iy = (i / 50) % 128, ix = i % 50;
-            xs[(c * 130 + iy + 1) * 52 + ix + 1] = __float2bfloat16((float)xb[i]);
-        }
-        // DZ1 (429 rows x 64) -> gs[pos][oc] fp32; each thread moves 8 channels (16 bytes) at a time
-        for (int i = tid; i < ROWS_PER_SAMPLE * 8; i += C1W_THREADS) {
-            const int rr = i >> 3, part = i & 7, cell = part >> 1, h = part & 1;
-            const int sy = rr / SG_W, sx = rr - sy * SG_W;
-            const int oy = 2 * sy + (cell >> 1) - 1, ox = 2 * sx + (cell & 1) - 1;
-            if (oy < 0 || oy >= 64 || ox < 0 || ox >= 25) continue;
-            const uint4 v = *reinterpret_cast<const uint4*>(dz1 + ((size_t)b * ROWS_PER_SAMPLE + rr) * 64 + cell * 16 + h * 8);
-            float4* d = reinterpret_cast<float4*>(gs + (oy * 25 + ox) * 16 + h * 8);
-            d[0] = make_float4(bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y));
-            d[1] = make_float4(bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w));
-        }
-        __syncthreads();
-        for (int pos = warp; pos < 1600; pos += C1W_THREADS / 32) {
-            const int oy = pos / 25, ox = pos - oy * 25;
-            const float xv = __bfloat162float(xs[(ch * 130 + 2 * oy + ky) * 52 + 2 * ox + kx]);
-            const float4* g = reinterpret_cast<const float4*>(gs + pos * 16);
-#pragma unroll
-            for (int qv = 0; qv < 4; ++qv) {
-                const float4 gv = g[qv];
-                acc[4 * qv + 0] = fmaf(xv, gv.x, acc[4 * qv + 0]);
-                acc[4 * qv + 1] = fmaf(xv, gv.y, acc[4 * qv + 1]);
-                acc[4 * qv + 2] = fmaf(xv, gv.z, acc[4 * qv + 2]);
-                acc[4 * qv + 3] = fmaf(xv, gv.w, acc[4 * qv + 3]);
-            }
-        }
-    }
-    // cross-warp reduction through shared memory, then one atomic per weight per CTA
-    __syncthreads();
-    float* red = gs;                                                            // [16 warps][32 k][16 oc]
-#pragma unroll
-    for (int c = 0; c < 16; ++c) red[(warp * 32 + lane) * 16 + c] = acc[c];
-    __syncthreads();
-    for (int i = tid; i < 512; i += C1W_THREADS) {
-        float s = 0.f;
-        for (int w = 0; w < C1W_THREADS / 32; ++w) s += red[w * 512 + i];
-        const int k = i >> 4, oc = i & 15;
-        atomicAdd(&dw1[oc * 32 + k], s);                                        // conv1.weight[oc][ch][ky][kx]
-    }
 }
 
 }  // namespace
@@ -383,7 +317,7 @@ int mmg_disc_conv2_wgrad(const void* p1, const void* dz2, float* dconv2_w, int64
     return MMG_OK;
 }
 
-// dz2 (B*429,32), p1 (B*429,64) -> dz1 (B*429,64) bf16 (pad cells 0);  dconv1_b (16,) fp32 +=
+// dz2 (B*429,32), p1 (B*429,64) -> dz1c (B*1690,16) bf16 in conv1's row space (junk rows untouched: allocate zeroed);  dconv1_b (16,) fp32 +=
 int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1, float* dconv1_b, int64_t B, void* stream) {
     MMG_REQUIRE(dz2 && packed && p1 && dz1 && dconv1_b && B >= 0, MMG_EINVAL, "conv2_dgrad: bad arguments");
     if (B == 0) return MMG_OK;
@@ -397,24 +331,6 @@ int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, vo
     const int grid = tiles < 2 * MMG_NUM_SMS ? tiles : 2 * MMG_NUM_SMS;
     MMG_CUDA(cudaFuncSetAttribute(conv2_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
     conv2_dgrad_tc_kernel<<<grid, 192, DG_SMEM, (cudaStream_t)stream>>>(map_dz2, map_w, (const __nv_bfloat16*)p1, (__nv_bfloat16*)dz1, dconv1_b, (int)rows, tiles);
-    MMG_LAUNCH_CHECK();
-    return MMG_OK;
-}
-
-// x (B,2,128,50) u8 (x_dtype 2) or f32 (0), dz1 (B*429,64) bf16 -> dconv1_w (16,2,4,4) fp32 +=
-int mmg_disc_conv1_wgrad(const void* x, int x_dtype, const void* dz1, float* dconv1_w, int64_t B, void* stream) {
-    MMG_REQUIRE(x && dz1 && dconv1_w && B >= 0, MMG_EINVAL, "conv1_wgrad: bad arguments");
-    if (B == 0) return MMG_OK;
-    const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
-    if (x_dtype == 2) {
-        MMG_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM));
-        conv1_wgrad_kernel<uint8_t><<<grid, C1W_THREADS, C1W_SMEM, (cudaStream_t)stream>>>((const uint8_t*)x, (const __nv_bfloat16*)dz1, dconv1_w, (int)B);
-    } else if (x_dtype == 0) {
-        MMG_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM));
-        conv1_wgrad_kernel<float><<<grid, C1W_THREADS, C1W_SMEM, (cudaStream_t)stream>>>((const float*)x, (const __nv_bfloat16*)dz1, dconv1_w, (int)B);
-    } else {
-        MMG_REQUIRE(false, MMG_EINVAL, "conv1_wgrad: x_dtype must be 0 (f32) or 2 (u8)");
-    }
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

@@ -9,7 +9,8 @@ import torch
 
 from . import _native as N
 
-ROWS = 429
+ROWS = 429         # conv1-activation / conv2 row space: 33 x 13 super pixels per sample
+XROWS = 1690       # input / conv1-output row space: 65 x 26 super pixels per sample
 _XD = {torch.float32: 0, torch.uint8: 2}
 
 
@@ -26,7 +27,8 @@ class DiscTC:
         self.p1 = torch.zeros(self.cap * ROWS, 64, **bf)            # pad cells stay zero forever
         self.a2 = torch.empty(self.cap * ROWS, 32, **bf)
         self.dz2 = torch.empty(self.cap * ROWS, 32, **bf)
-        self.dz1 = torch.empty(self.cap * ROWS, 64, **bf)
+        self.xs = torch.empty(self.cap * XROWS, 8, **bf)
+        self.dz1c = torch.zeros(self.cap * XROWS, 16, **bf)         # junk rows stay zero forever
         self.logits = torch.empty(self.cap, device=dev)
         self.x, self.B = None, 0
         self.pack()
@@ -46,7 +48,8 @@ class DiscTC:
         d, s = self.d, N.stream()
         logits = self.logits[:B]
         N.call("mmg_fill_scalar_f32", N.ptr(logits), N.ptr(d.fc.bias.data), B, s)
-        N.call("mmg_disc_conv1_fwd", N.ptr(x), _XD[x.dtype], N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(self.p1), B, s)
+        N.call("mmg_disc_xs_pack", N.ptr(x), _XD[x.dtype], N.ptr(self.xs), B, s)
+        N.call("mmg_disc_conv1_fwd", N.ptr(self.xs), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(self.p1), B, s)
         N.call("mmg_disc_conv2_fwd", N.ptr(self.p1), N.ptr(self.packed), N.ptr(d.conv2.bias.data), N.ptr(self.a2), N.ptr(logits), B, s)
         self.x, self.B = x, B
         return logits
@@ -64,5 +67,5 @@ class DiscTC:
         N.call("mmg_sum_f32", N.ptr(dlogit), B, N.ptr(g["fc.bias"]), 1, s)
         N.call("mmg_disc_fc_bwd", N.ptr(self.a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(self.dz2), N.ptr(g["fc.weight"]), N.ptr(g["conv2.bias"]), B, s)
         N.call("mmg_disc_conv2_wgrad", N.ptr(self.p1), N.ptr(self.dz2), N.ptr(g["conv2.weight"]), B, s)
-        N.call("mmg_disc_conv2_dgrad", N.ptr(self.dz2), N.ptr(self.packed), N.ptr(self.p1), N.ptr(self.dz1), N.ptr(g["conv1.bias"]), B, s)
-        N.call("mmg_disc_conv1_wgrad", N.ptr(self.x), _XD[self.x.dtype], N.ptr(self.dz1), N.ptr(g["conv1.weight"]), B, s)
+        N.call("mmg_disc_conv2_dgrad", N.ptr(self.dz2), N.ptr(self.packed), N.ptr(self.p1), N.ptr(self.dz1c), N.ptr(g["conv1.bias"]), B, s)
+        N.call("mmg_disc_conv1_wgrad", N.ptr(self.xs), N.ptr(self.dz1c), N.ptr(g["conv1.weight"]), B, s)

@@ -91,19 +91,21 @@ int mmg_maxpool2_fwd_f32(const float* x, float* y, uint8_t* idx, int64_t NC, int
 int mmg_maxpool2_bwd_f32(const float* dy, const uint8_t* idx, float* dx, int64_t NC, int H, int W, void* stream);
 
 /* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
- * Activations live in a padded space-to-depth layout (see csrc/disc_tc.cu): P1 / DZ1 are (B*429, 64) bf16,
- * A2 / DZ2 are (B*429, 32) bf16; x is (B,2,128,50) uint8 (x_dtype 2) or float32 (x_dtype 0).
+ * Activations live in padded space-to-depth layouts (see csrc/disc_tc.cu): XS (B*1690, 8) is the input, P1 (B*429, 64)
+ * the conv1 activations, A2 / DZ2 (B*429, 32) the conv2 activations / their gradient, DZ1C (B*1690, 16) the conv1
+ * pre-activation gradient (junk rows zero: allocate zeroed); all bf16.  x is (B,2,128,50) uint8 (x_dtype 2) or float32 (0).
  * `packed` = mmg_disc_packed_weights_bytes() bytes filled by mmg_disc_pack_weights from the fp32 nn.Parameters.
  * P1's pad cells must be zero (allocate zeroed, reuse).  logits must be initialised (fc bias) before conv2_fwd.
  * Gradient outputs are fp32, in the reference's parameter layouts, and are ACCUMULATED into (+=). */
 size_t mmg_disc_packed_weights_bytes(void);
 int mmg_disc_pack_weights(const float* conv1_w, const float* conv2_w, const float* fc_w, void* packed, void* stream);
-int mmg_disc_conv1_fwd(const void* x, int x_dtype, const void* packed, const float* conv1_b, void* p1, int64_t B, void* stream);
+int mmg_disc_xs_pack(const void* x, int x_dtype, void* xs, int64_t B, void* stream);
+int mmg_disc_conv1_fwd(const void* xs, const void* packed, const float* conv1_b, void* p1, int64_t B, void* stream);
 int mmg_disc_conv2_fwd(const void* p1, const void* packed, const float* conv2_b, void* a2, float* logits, int64_t B, void* stream);
 int mmg_disc_fc_bwd(const void* a2, const float* dlogit, const void* packed, void* dz2, float* dfc_w, float* dconv2_b, int64_t B, void* stream);
 int mmg_disc_conv2_wgrad(const void* p1, const void* dz2, float* dconv2_w, int64_t B, void* stream);
-int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1, float* dconv1_b, int64_t B, void* stream);
-int mmg_disc_conv1_wgrad(const void* x, int x_dtype, const void* dz1, float* dconv1_w, int64_t B, void* stream);
+int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1c, float* dconv1_b, int64_t B, void* stream);
+int mmg_disc_conv1_wgrad(const void* xs, const void* dz1c, float* dconv1_w, int64_t B, void* stream);
 
 #ifdef __cplusplus
 }
