@@ -5,7 +5,15 @@
 // Integer-only apart from the float64 running time sum, which stays SEQUENTIAL per song (a parallel
 // scan would not be bit-exact) and is rounded half-to-even exactly like Python's round().
 //
-// One fused kernel, one WARP per song (all songs in flight at once; nothing but the output leaves
+// Two paths.  FAST (S <= 65535 and a workspace is supplied):
+//   K1 raster_steps_kernel  one WARP per song: 32 lanes stage dt through shared memory, lane 0 runs the dependent
+//      t += dt chain, all lanes round to steps, evaluate the cut-off rule with ballots and COMPACT the surviving
+//      note_on / note_off messages into 4-byte records (step | off<<16 | pitch<<17 | vel<<24) in the workspace.
+//      Latency-bound by the fp64 chain, so every song is in flight at once (tiny footprint per warp).
+//   K2 raster_rows_kernel   one CTA per song: zero-fills the song's planes, stable-counting-sorts the notes by pitch
+//      (per-warp segment histograms, no atomics), then one warp per pitch replays the pitch's list 32 notes at a time
+//      with a closed form of the sequential rules, writing every touched cell exactly once (see the kernel's header).
+// GENERIC (any S, W): one fused kernel, one WARP per song (all songs in flight at once; nothing but the output leaves
 // the SM):
 //   1. the warp zero-fills its song's output planes (coalesced 16-byte stores);
 //   2. per chunk of 256 messages: 32 lanes stage dt into shared memory (coalesced, next chunk
@@ -16,7 +24,8 @@
 //      ballot (which note_on arms a note_off, which note_on is the last writer of a cell) and scatter
 //      velocities / duration fills straight into the output (each note touches a few cells).
 //      __syncwarp() between sub-steps gives the last-writer-wins order of the reference loop.
-// HBM traffic = 12 B per message read once + every output cell written once (+ the touched cells).
+// HBM traffic = 12 B per message read once + every output cell written once (+ the touched cells; fast path: + 4 B
+// per surviving note written and read back through the workspace).
 #include "common.cuh"
 
 namespace {
@@ -158,6 +167,259 @@ __global__ void __launch_bounds__(RW * 32) raster_fused_kernel(const double* __r
     if (status && lane == 0) status[song] = st;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fast path, K1: time chain + cut-off + note compaction (one warp per song)
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_WARPS = 4;
+constexpr int K1_CH = 512;            // messages per chain chunk
+constexpr int K1_CJ = K1_CH / 32;
+
+__global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
+                                                                      const int64_t* __restrict__ offsets, int64_t n_songs, int S, int W,
+                                                                      uint32_t* __restrict__ notes, int32_t* __restrict__ note_count,
+                                                                      int32_t* __restrict__ status) {
+    __shared__ double tbuf[K1_WARPS][K1_CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t song = (int64_t)blockIdx.x * K1_WARPS + warp;
+    if (song >= n_songs) return;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t a0 = offsets[song];
+    const int64_t n = offsets[song + 1] - a0;
+    double* tb = tbuf[warp];
+    uint32_t* nout = notes + a0;                                   // at most n records
+    double d[K1_CJ];
+    uint32_t m[K1_CJ];
+#pragma unroll
+    for (int j = 0; j < K1_CJ; ++j) {
+        const int64_t i = lane + 32 * j;
+        d[j] = i < n ? dt[a0 + i] : 0.0;
+        m[j] = i < n ? meta[a0 + i] : 0u;
+    }
+    double t = 0.0;
+    int st = 0, count = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += K1_CH) {
+        uint32_t cm[K1_CJ];
+#pragma unroll
+        for (int j = 0; j < K1_CJ; ++j) { tb[lane + 32 * j] = d[j]; cm[j] = m[j]; }
+#pragma unroll
+        for (int j = 0; j < K1_CJ; ++j) {                          // prefetch the next chunk behind the chain
+            const int64_t i = i0 + K1_CH + lane + 32 * j;
+            d[j] = i < n ? dt[a0 + i] : 0.0;
+            m[j] = i < n ? meta[a0 + i] : 0u;
+        }
+        __syncwarp();
+        const int cnt = (int)((n - i0) < K1_CH ? (n - i0) : K1_CH);
+        if (lane == 0) {                                           // sequential float64 running sum (datasets.py:35)
+            const int lim8 = (cnt + 7) & ~7;                       // padding holds 0.0: t + 0.0 == t
+            double v[8], w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = tb[u];
+            for (int k = 0; k < lim8; k += 8) {
+                if (k + 8 < lim8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) w[u] = tb[k + 8 + u];      // next 8 loaded behind the dependent adds
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { t = __dadd_rn(t, v[u]); tb[k + u] = t; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = w[u];
+            }
+        }
+        __syncwarp();
+        int first_halt = K1_CH;
+        uint32_t rec[K1_CJ];
+        unsigned keep = 0;                                         // bit j: message lane+32j is a note inside the contract
+#pragma unroll
+        for (int j = 0; j < K1_CJ; ++j) {
+            const int e = lane + 32 * j;
+            const long long step = __double2ll_rn(tb[e]);          // datasets.py:36 round-half-even
+            const uint32_t kind = cm[j] & 0xFFu, pitch = (cm[j] >> 8) & 0xFFu;
+            const bool note = kind == 1u || kind == 2u;
+            bool halt = step >= S;                                 // :37-38, every message kind
+            halt |= step < 0;                                      // dt < 0: outside the contract (flagged)
+            halt |= note && pitch >= 128u;                         // IndexError in the reference
+            halt |= kind == 1u && step >= W;                       // IndexError -> bare except (:41,:46)
+            const unsigned hm = __ballot_sync(0xffffffffu, e < cnt && halt);
+            if (hm && first_halt == K1_CH) {
+                const int src = __ffs(hm) - 1;
+                first_halt = 32 * j + src;
+                const int bits = (step < 0 ? 1 : 0) | ((note && pitch >= 128u) ? 2 : 0);
+                st = __shfl_sync(0xffffffffu, bits, src);
+            }
+            rec[j] = ((uint32_t)step & 0xFFFFu) | ((kind == 2u ? 1u : 0u) << 16) | ((pitch & 0x7Fu) << 17) | (((cm[j] >> 16) & 0xFFu) << 24);
+            if (note && e < cnt) keep |= 1u << j;
+        }
+        const int lim = cnt < first_halt ? cnt : first_halt;
+#pragma unroll
+        for (int j = 0; j < K1_CJ; ++j) {                          // ordered compaction, 32 messages per ballot
+            const bool k = ((keep >> j) & 1u) && (lane + 32 * j < lim);
+            const unsigned km = __ballot_sync(0xffffffffu, k);
+            if (k) nout[count + __popc(km & lt_mask)] = rec[j];
+            count += __popc(km);
+        }
+        if (first_halt < K1_CH) break;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        note_count[song] = count;
+        if (status) status[song] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path, K2: stable counting sort of the song's notes by pitch, then a write-once replay (one CTA per song)
+//
+// For one pitch the notes arrive in message order with non-decreasing steps, so the sequential rules of
+// datasets.py:39-45 have a closed form that needs only each note's neighbours in its pitch list:
+//   note_on  i : roll[p, s_i] = vel_i unless the NEXT note_on of the pitch has the same step (last writer wins);
+//   note_off j : a_j = step of the latest note_on before it (0 if none); it fills [a_j, s_j) with s_j - a_j, and is
+//                overwritten from a_{j'} onwards by the next note_off j' (a is non-decreasing, s is non-decreasing),
+//                so it OWNS exactly the columns [a_j, min(a_{j'}, s_j, W)).
+// Every cell is therefore written at most once after the CTA's zero fill (which stays in L2 for the few microseconds in
+// between: HBM sees each output line once).
+// ------------------------------------------------------------------------------------------------
+constexpr int K2_THREADS = 256;
+constexpr int K2_WARPS = K2_THREADS / 32;
+
+template <typename OutT>
+__global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t* __restrict__ notes, uint32_t* __restrict__ sorted,
+                                                                  const int32_t* __restrict__ note_count, const int64_t* __restrict__ offsets,
+                                                                  int W, int lo, int hi, OutT* __restrict__ out) {
+    __shared__ int hist[K2_WARPS][128];          // per-warp-segment pitch histogram, then running scatter base
+    __shared__ int pstart[129];
+    __shared__ int wsum[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~lt_mask & ~(1u << lane);
+    const int64_t song = blockIdx.x;
+    const uint32_t* nin = notes + offsets[song];
+    uint32_t* srt = sorted + offsets[song];
+    const int n = note_count[song];
+    const int Wo = hi - lo;
+    OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
+    OutT* __restrict__ odur = oroll + (size_t)128 * Wo;
+    {   // zero fill (2*128*Wo*sizeof(OutT) bytes, a multiple of 16; 16-byte aligned)
+        uint4* z = reinterpret_cast<uint4*>(oroll);
+        const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);
+        for (int i = tid; i < cnt; i += K2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < K2_WARPS * 128; i += K2_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    // 1. histogram of this warp's contiguous segment (multiple of 32 notes)
+    const int seg = ((n + K2_WARPS * 32 - 1) / (K2_WARPS * 32)) * 32;
+    const int s_lo = warp * seg, s_hi = min(n, s_lo + seg);
+    for (int i0 = s_lo; i0 < s_hi; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < s_hi;
+        const int p = valid ? (int)((nin[i] >> 17) & 0x7Fu) : 128 + lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, p);
+        if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
+        __syncwarp();
+    }
+    __syncthreads();
+    // 2. pitch offsets (exclusive scan over 128 pitches) and per-segment bases
+    if (tid < 128) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) tot += hist[w][tid];
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncwarp();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int base = inc - tot;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        pstart[tid] = base;
+        if (tid == 127) pstart[128] = base + tot;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) { const int c = hist[w][tid]; hist[w][tid] = base; base += c; }
+    }
+    __syncthreads();
+    // 3. stable scatter (each warp in message order over its own segment)
+    for (int i0 = s_lo; i0 < s_hi; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < s_hi;
+        const uint32_t r = valid ? nin[i] : 0u;
+        const int p = valid ? (int)((r >> 17) & 0x7Fu) : 128 + lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, p);
+        if (valid) {
+            const int b = hist[warp][p];
+            srt[b + __popc(grp & lt_mask)] = r;
+        }
+        __syncwarp();
+        if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
+        __syncwarp();
+    }
+    __syncthreads();            // zero fill and sorted[] are visible to the whole CTA
+    // 4. per-pitch replay, one warp per pitch, 32 notes at a time with the unresolved last on / off carried forward
+    for (int p = warp; p < 128; p += K2_WARPS) {
+        const int b0 = pstart[p], b1 = pstart[p + 1];
+        if (b0 == b1) continue;
+        OutT* rrow = oroll + (size_t)p * Wo - lo;
+        OutT* drow = odur + (size_t)p * Wo - lo;
+        int on_carry = 0;                                   // note_on_time[p] (:33)
+        int pend_on_s = -1, pend_on_v = 0;                  // last note_on seen, not yet known to be the last writer of its cell
+        int pend_a = 0, pend_s = -1;                        // last note_off seen, its right neighbour still unknown
+        for (int i0 = b0; i0 < b1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < b1;
+            const uint32_t r = valid ? srt[i] : 0u;
+            const int s = (int)(r & 0xFFFFu);
+            const bool is_off = valid && ((r >> 16) & 1u), is_on = valid && !((r >> 16) & 1u);
+            const unsigned onm = __ballot_sync(0xffffffffu, is_on), offm = __ballot_sync(0xffffffffu, is_off);
+            const unsigned lower_on = onm & lt_mask;
+            const int s_prev_on = __shfl_sync(0xffffffffu, s, lower_on ? 31 - __clz(lower_on) : 0);
+            const int a = lower_on ? s_prev_on : on_carry;                       // meaningful for note_offs
+            const unsigned higher_on = onm & gt_mask, higher_off = offm & gt_mask;
+            const int s_next_on = __shfl_sync(0xffffffffu, s, higher_on ? __ffs(higher_on) - 1 : 0);
+            const int a_next_off = __shfl_sync(0xffffffffu, a, higher_off ? __ffs(higher_off) - 1 : 0);
+            const int s_first_on = __shfl_sync(0xffffffffu, s, onm ? __ffs(onm) - 1 : 0);
+            const int a_first_off = __shfl_sync(0xffffffffu, a, offm ? __ffs(offm) - 1 : 0);
+            // resolve what the previous chunk left pending
+            if (onm && pend_on_s >= 0) {
+                if (lane == 0 && pend_on_s != s_first_on && pend_on_s >= lo && pend_on_s < hi) rrow[pend_on_s] = to_out<OutT>((unsigned)pend_on_v);
+                pend_on_s = -1;
+            }
+            if (offm && pend_s >= 0) {
+                int c1 = pend_s < W ? pend_s : W;
+                c1 = c1 < a_first_off ? c1 : a_first_off;
+                c1 = c1 < hi ? c1 : hi;
+                const OutT v = to_out<OutT>((unsigned)(pend_s - pend_a));
+                for (int c = (pend_a > lo ? pend_a : lo) + lane; c < c1; c += 32) drow[c] = v;
+                pend_s = -1;
+            }
+            // this chunk's notes
+            if (is_on && higher_on && s_next_on != s && s >= lo && s < hi) rrow[s] = to_out<OutT>(r >> 24);
+            if (is_off && higher_off) {
+                int c1 = s < W ? s : W;
+                c1 = c1 < a_next_off ? c1 : a_next_off;
+                c1 = c1 < hi ? c1 : hi;
+                const OutT v = to_out<OutT>((unsigned)(s - a));
+                for (int c = a > lo ? a : lo; c < c1; ++c) drow[c] = v;
+            }
+            if (onm) {
+                const int last = 31 - __clz(onm);
+                pend_on_s = __shfl_sync(0xffffffffu, s, last);
+                pend_on_v = __shfl_sync(0xffffffffu, (int)(r >> 24), last);
+                on_carry = pend_on_s;
+            }
+            if (offm) {
+                const int last = 31 - __clz(offm);
+                pend_a = __shfl_sync(0xffffffffu, a, last);
+                pend_s = __shfl_sync(0xffffffffu, s, last);
+            }
+        }
+        if (pend_on_s >= 0 && lane == 0 && pend_on_s >= lo && pend_on_s < hi) rrow[pend_on_s] = to_out<OutT>((unsigned)pend_on_v);
+        if (pend_s >= 0) {
+            int c1 = pend_s < W ? pend_s : W;
+            c1 = c1 < hi ? c1 : hi;
+            const OutT v = to_out<OutT>((unsigned)(pend_s - pend_a));
+            for (int c = (pend_a > lo ? pend_a : lo) + lane; c < c1; c += 32) drow[c] = v;
+        }
+    }
+}
+
 // python slice clip of [a:b) on a length-n axis
 inline void clip_slice(long a, long b, long n, long* lo, long* hi) {
     if (a < 0) { a += n; if (a < 0) a = 0; } else if (a > n) a = n;
@@ -177,17 +439,17 @@ int mmg_raster_out_width(int start, int end) {
     return (int)(hi - lo);
 }
 
-// the fused kernel keeps everything on chip: no scratch is needed (kept in the ABI for layout changes)
+// fast path scratch: two 4-byte records per message (compacted notes, then sorted by pitch) + one int32 note count per song.
+// A smaller (or NULL) workspace selects the generic single-kernel path, which needs none.
 size_t mmg_raster_workspace_bytes(int64_t n_songs, int64_t total_events) {
-    (void)n_songs; (void)total_events;
-    return 0;
+    if (n_songs < 0 || total_events < 0) return 0;
+    return (size_t)total_events * 8 + (size_t)n_songs * 4 + 32;
 }
 
 // out: (n_songs, 2, 128, Wout) of out_dtype (0 = float32, 1 = bfloat16, 2 = uint8 saturating); fully written.
 int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t* offsets, int64_t n_songs, int64_t total_events,
                           int sequence_length, int start, int end, int out_dtype, void* out, int32_t* status,
                           void* workspace, size_t ws_bytes, void* stream_) {
-    (void)workspace; (void)ws_bytes;
     cudaStream_t stream = (cudaStream_t)stream_;
     MMG_REQUIRE(n_songs >= 0 && total_events >= 0, MMG_EINVAL, "raster: negative sizes");
     const long W = (long)end - start;
@@ -208,7 +470,24 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
     if (end < 128) clip_slice(start, end, W, &lo, &hi); else clip_slice(0, end, W, &lo, &hi);
     if (hi - lo == 0) return MMG_OK;                                    // nothing to write
     const long long blocks = (n_songs + RW - 1) / RW;
-    MMG_REQUIRE(blocks <= 0x7fffffff, MMG_EUNSUPPORTED, "raster: too many songs");
+    MMG_REQUIRE(blocks <= 0x7fffffff && n_songs <= 0x7fffffff, MMG_EUNSUPPORTED, "raster: too many songs");
+    if (S <= 65535 && workspace && ws_bytes >= mmg_raster_workspace_bytes(n_songs, total_events) && ((uintptr_t)workspace & 3) == 0) {
+        const size_t rec_bytes = ((size_t)total_events * 4 + 15) & ~(size_t)15;
+        uint32_t* notes = (uint32_t*)workspace;
+        uint32_t* sorted = (uint32_t*)((unsigned char*)workspace + rec_bytes);
+        int32_t* counts = (int32_t*)((unsigned char*)workspace + 2 * rec_bytes);
+        raster_steps_kernel<<<(int)((n_songs + K1_WARPS - 1) / K1_WARPS), K1_WARPS * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, notes,
+                                                                                                   counts, status);
+        MMG_LAUNCH_CHECK();
+        if (out_dtype == 0)
+            raster_rows_kernel<float><<<(int)n_songs, K2_THREADS, 0, stream>>>(notes, sorted, counts, offsets, (int)W, (int)lo, (int)hi, (float*)out);
+        else if (out_dtype == 1)
+            raster_rows_kernel<__nv_bfloat16><<<(int)n_songs, K2_THREADS, 0, stream>>>(notes, sorted, counts, offsets, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out);
+        else
+            raster_rows_kernel<uint8_t><<<(int)n_songs, K2_THREADS, 0, stream>>>(notes, sorted, counts, offsets, (int)W, (int)lo, (int)hi, (uint8_t*)out);
+        MMG_LAUNCH_CHECK();
+        return MMG_OK;
+    }
     if (out_dtype == 0)
         raster_fused_kernel<float><<<(int)blocks, RW * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
     else if (out_dtype == 1)

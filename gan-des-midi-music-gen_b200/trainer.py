@@ -138,3 +138,56 @@ class MMGANTrainer:
         self.logit_fake_g = self._d_pass(fake_g, 1.0, self.loss_g, False)
         self.gen_opt.step()          # no-op: generator grads are None
         return self.loss_d[0], self.loss_g[0]
+
+
+class HostBatchPipeline:
+    """Feeds HOST batches (pinned tensors, e.g. what the DataLoader and the host DES bridge hand over) to
+    ``MMGANTrainer.step`` with the H2D copies of batch i+1 running on a copy stream underneath the compute of
+    batch i (double-buffered device staging; SURVEY 8f-1: network_tests.py:192-193 does B small blocking copies).
+    Every batch is copied exactly once; the two losses are read back (blocking, like the ``.item()`` calls at
+    network_tests.py:320-321) after every step."""
+
+    KEYS = ("beats", "real", "fake_d", "fake_g")
+
+    def __init__(self, trainer, example):
+        self.t = trainer
+        dev = trainer.flat_grad.device
+        self.stage = [{k: torch.empty_like(example[k], device=dev) for k in self.KEYS} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.KEYS)
+
+    def _issue(self, slot, batch, first_use):
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.free[slot])
+            for k in self.KEYS:
+                self.stage[slot][k].copy_(batch[k], non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, batches):
+        """Generator: yields the pinned (2,) tensor [disc_loss, gen_loss] after each batch's iteration."""
+        main = torch.cuda.current_stream()
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        self._issue(0, cur, True)
+        i = 0
+        while cur is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                self._issue(1 - slot, nxt, i == 0)
+            main.wait_event(self.ready[slot])
+            st = self.stage[slot]
+            B = st["real"].shape[0]
+            n1 = torch.randn(B, self.t.m.z_dim, device=st["real"].device)          # network_tests.py:284-285
+            n2 = torch.randn(B, self.t.m.z_dim, device=st["real"].device)
+            dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
+            self.free[slot].record(main)
+            self.losses_host.copy_(torch.stack([dl, gl]), non_blocking=False)
+            yield self.losses_host
+            cur, i = nxt, i + 1
