@@ -27,6 +27,7 @@ SIGNATURES = {
     "mmg_sum_f32": (_I, [_P, _L, _P, _I, _P]),
     "mmg_act_bwd_f32": (_I, [_P, _P, _P, _L, _I, _P]),
     "mmg_adam_multi_tensor_f32": (_I, [_I, _P, _P, _F, _F, _F, _F, _L, _F, _P]),
+    "mmg_adam_multi_tensor_dev_f32": (_I, [_I, _P, _P, _P, _P, _F, _P]),
     "mmg_linear_fwd_f32": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, _P]),
     "mmg_linear_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _P]),
     "mmg_bn_workspace_bytes": (_Z, [_L]),

@@ -92,6 +92,34 @@ __global__ void __launch_bounds__(256) adam_multi_tensor_kernel(AdamTable tab, f
     for (long long i = n4 * 4 + i0; i < n; i += stride) upd(p[i], g[i], m[i], v[i]);
 }
 
+// Device-resident hyper-parameters (CUDA-graph replay): hyper = [lr, beta1, beta2, eps], step_dev = number of
+// updates already applied; this launch applies update number *step_dev + 1 (the counter is bumped by adam_step_inc_kernel).
+__global__ void __launch_bounds__(256) adam_multi_tensor_dev_kernel(AdamTable tab, const float* __restrict__ hyper, const long long* __restrict__ step_dev,
+                                                                     float grad_scale) {
+    const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3];
+    const double step = (double)(step_dev[0] + 1);
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const int t = blockIdx.y;
+    const long long n = tab.n[t];
+    float* __restrict__ p = tab.p[t];
+    const float* __restrict__ g = tab.g[t];
+    float* __restrict__ m = tab.m[t];
+    float* __restrict__ v = tab.v[t];
+    const float w = 1.f - beta1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * grad_scale;
+        float mi = m[i], vi = v[i];
+        mi = (w < 0.5f) ? mi + w * (gi - mi) : gi - (gi - mi) * (1.f - w);      // at::lerp
+        vi = vi * beta2 + (1.f - beta2) * gi * gi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+        m[i] = mi; v[i] = vi;
+    }
+}
+__global__ void adam_step_inc_kernel(long long* step_dev) { step_dev[0] += 1; }
+
 }  // namespace
 
 extern "C" {
@@ -165,6 +193,33 @@ int mmg_adam_multi_tensor_f32(int n_tensors, void* const* ptrs, const int64_t* s
         adam_multi_tensor_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, step_size, bc2_sqrt, eps, grad_scale);
         MMG_LAUNCH_CHECK();
     }
+    return MMG_OK;
+}
+
+// Same update with the hyper-parameters and the step counter in DEVICE memory, so that the launch can be replayed from a
+// CUDA graph: hyper_dev = [lr, beta1, beta2, eps] (fp32), step_dev = updates applied so far (int64, incremented here).
+int mmg_adam_multi_tensor_dev_f32(int n_tensors, void* const* ptrs, const int64_t* sizes, const float* hyper_dev, int64_t* step_dev,
+                                  float grad_scale, void* stream) {
+    MMG_REQUIRE(n_tensors >= 0 && n_tensors <= ADAM_MAX_TENSORS && hyper_dev && step_dev, MMG_EINVAL, "adam_dev: bad arguments (at most %d tensors)", ADAM_MAX_TENSORS);
+    if (n_tensors == 0) return MMG_OK;
+    AdamTable tab;
+    long long maxn = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        tab.p[i] = (float*)ptrs[i];
+        tab.g[i] = (const float*)ptrs[n_tensors + i];
+        tab.m[i] = (float*)ptrs[2 * n_tensors + i];
+        tab.v[i] = (float*)ptrs[3 * n_tensors + i];
+        tab.n[i] = sizes[i];
+        MMG_REQUIRE(tab.n[i] >= 0 && (tab.n[i] == 0 || (tab.p[i] && tab.g[i] && tab.m[i] && tab.v[i])), MMG_EINVAL, "adam_dev: null tensor %d", i);
+        if (tab.n[i] > maxn) maxn = tab.n[i];
+    }
+    if (maxn) {
+        dim3 grid(mmg_grid(maxn, 256, 4), n_tensors);
+        adam_multi_tensor_dev_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab, hyper_dev, (const long long*)step_dev, grad_scale);
+        MMG_LAUNCH_CHECK();
+    }
+    adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_dev);
+    MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
 

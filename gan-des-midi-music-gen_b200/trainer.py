@@ -13,10 +13,18 @@ durations < 256, so uint8 is exact and quarters the H2D / HBM traffic).
 precision='fp32' : the drop-in nn.Modules + autograd over the fp32 SIMT kernels (reference tolerance).
 precision='bf16' : discriminator on the tcgen05 tensor-core kernels (disc_tc.DiscTC): bf16 operands,
                    fp32 accumulation, fp32 master weights / Adam state; fused BCE and multi-tensor Adam.
+CUDA graphs (``use_graph=True``, default for bf16): after one eager iteration on the same input buffers the iteration
+is captured (one graph, or two around the NCCL all-reduce when sharded) and later calls with the same buffers replay
+it: one launch per iteration instead of ~100.  Adam's step count and learning rate live in device memory for that
+(``mmg_adam_multi_tensor_dev_f32``), so ``StepLR`` keeps working.
+``inner_rng``: the reference's Generator draws its second input with ``torch.randn`` on the CPU generator inside forward
+(network_tests.py:83-84); 'reference' reproduces that draw (same global RNG consumption), 'device' draws on the GPU.
 Data parallel: with torch.distributed initialised (NCCL) the batch is sharded by rank, the D gradients
 live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step (the 1/world factor is
 folded into the Adam kernel), and the G-step D grads are not reduced (the reference discards them).
 """
+import ctypes
+
 import torch
 
 from . import _native as N
@@ -34,7 +42,8 @@ def shard_batch(t, rank, world):
 
 
 class MMGANTrainer:
-    def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None):
+    def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None, use_graph=None,
+                 inner_rng="reference"):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.m = mmgan
@@ -48,6 +57,8 @@ class MMGANTrainer:
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
         self.disc_opt = FusedAdam(self.d_params, lr=lr, betas=betas, eps=eps)
+        for p in self.d_params:                       # state exists from the start (the graph bakes these addresses in)
+            self.disc_opt.state[p].update(step=0, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
         self.gen_opt = FusedAdam(list(mmgan.generator1.parameters()) + list(mmgan.generator2.parameters()), lr=lr, betas=betas, eps=eps)
         self.pg = process_group
         dist = torch.distributed
@@ -60,6 +71,16 @@ class MMGANTrainer:
             from .disc_tc import DiscTC
             self.tc = DiscTC(D, max_batch)
         dev = self.flat_grad.device
+        if inner_rng not in ("reference", "device"):
+            raise ValueError("inner_rng must be 'reference' or 'device'")
+        self.inner_rng = inner_rng
+        self.use_graph = (precision == "bf16") if use_graph is None else bool(use_graph)
+        self._graphs, self._seen, self._inner = {}, {}, {}
+        self.graph_launches = 0                      # kernels inside one captured iteration (for launch accounting)
+        self.replayed_launches = 0                   # kernels launched through graph replays so far
+        self.adam_hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._lr_cached = lr
         self.loss_d = torch.zeros(1, device=dev)
         self.loss_g = torch.zeros(1, device=dev)
         self.dlogit = torch.empty(max_batch or 1, device=dev)
@@ -78,18 +99,36 @@ class MMGANTrainer:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)       # sum; 1/world is applied inside the Adam kernel
 
     def _disc_adam(self):
+        """Adam on the six discriminator tensors, one launch, hyper-parameters and step count read from device memory."""
         opt = self.disc_opt
-        g = opt.param_groups[0]
         st = opt.state
+        ps = self.d_params
+        ts = [p.data for p in ps] + [p.grad for p in ps] + [st[p]["exp_avg"] for p in ps] + [st[p]["exp_avg_sq"] for p in ps]
+        n = len(ps)
+        ptrs = (ctypes.c_void_p * (4 * n))(*[N.ptr(t) for t in ts])
+        sizes = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
+        N.call("mmg_adam_multi_tensor_dev_f32", n, ptrs, sizes, N.ptr(self.adam_hyper), N.ptr(self.adam_step), 1.0 / self.world, N.stream())
+
+    def _sync_hyper(self):
+        """Host-side bookkeeping that a graph replay cannot do: push a changed lr (StepLR) to the device, count the step."""
+        lr = self.disc_opt.param_groups[0]["lr"]
+        if lr != self._lr_cached:
+            self.adam_hyper[0:1].fill_(lr)
+            self._lr_cached = lr
         for p in self.d_params:
-            if not st[p]:
-                st[p]["step"] = 0
-                st[p]["exp_avg"] = torch.zeros_like(p)
-                st[p]["exp_avg_sq"] = torch.zeros_like(p)
-            st[p]["step"] += 1
-        Fn.adam_step([p.data for p in self.d_params], [p.grad for p in self.d_params], [st[p]["exp_avg"] for p in self.d_params],
-                     [st[p]["exp_avg_sq"] for p in self.d_params], st[self.d_params[0]]["step"], g["lr"], g["betas"][0], g["betas"][1], g["eps"],
-                     grad_scale=1.0 / self.world)
+            self.disc_opt.state[p]["step"] += 1
+
+    def _draw_inner(self, B, which):
+        """The Generator's in-forward ``randn`` (network_tests.py:83-84), into a static buffer (stable address for graph replay)."""
+        dim = self.m.generator1.input_tensor_dim
+        buf = self._inner.get((which, B))
+        if buf is None:
+            buf = self._inner[(which, B)] = torch.empty(B, dim, device=self.flat_grad.device)
+        if self.inner_rng == "device":
+            buf.normal_()
+        else:
+            buf.copy_(torch.randn(B, dim))
+        return buf
 
     def _generators(self, noise1, noise2, beats, inner):
         m = self.m
@@ -117,28 +156,70 @@ class MMGANTrainer:
         return logits.detach()
 
     # ------------------------------------------------------------------ one iteration
-    def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None):
-        # ---- D step (:293-308)
+    def _seg_d(self, noise1, noise2, beats, real, fake_d, inner_d):
+        """D step up to the gradients (:293-307)"""
         self._zero_d_grads()
         self._generators(noise1, noise2, beats, inner_d)
         self.logit_fake_d = self._d_pass(fake_d, 0.0, self.loss_d, False)
         if self.tc is not None:
             self.logit_fake_d = self.logit_fake_d.clone()
         self.logit_real = self._d_pass(real, 1.0, self.loss_d, True)
-        self._allreduce_d_grads()
-        if self.on_d_grads is not None:
-            self.on_d_grads(self)                  # observer hook: flat_grad holds the (summed) D-step gradients Adam is about to consume
-        self._disc_adam()
         if self.tc is not None:
             self.logit_real = self.logit_real.clone()
+
+    def _seg_g(self, noise1, noise2, beats, fake_g, inner_g):
+        """Adam on D (:308), then the G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them"""
+        self._disc_adam()
+        if self.tc is not None:
             self.tc.pack()
-        # ---- G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them
-        self.gen_opt.zero_grad(set_to_none=True)
         self._generators(noise1, noise2, beats, inner_g)
         self.logit_fake_g = self._d_pass(fake_g, 1.0, self.loss_g, False)
+
+    def _capture(self, fn, *args):
+        g = torch.cuda.CUDAGraph()
+        l0 = N.lib().mmg_launch_count()
+        with torch.cuda.graph(g):
+            fn(*args)
+        self.graph_launches += N.lib().mmg_launch_count() - l0
+        return g
+
+    def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None):
+        B = real.shape[0]
+        if inner_d is None:
+            inner_d = self._draw_inner(B, "d")
+        if inner_g is None:
+            inner_g = self._draw_inner(B, "g")
+        self.gen_opt.zero_grad(set_to_none=True)
+        a_d, a_g = (noise1, noise2, beats, real, fake_d, inner_d), (noise1, noise2, beats, fake_g, inner_g)
+        graphs = None
+        if self.use_graph and self.on_d_grads is None:
+            key = tuple(t.data_ptr() for t in (*a_d, fake_g, inner_g)) + (B, real.dtype, fake_d.dtype, fake_g.dtype)
+            graphs = self._graphs.get(key)
+            if graphs is None:
+                self._seen[key] = self._seen.get(key, 0) + 1
+                if self._seen[key] > 1:              # one eager iteration on these buffers first (allocator / lazy-init warm-up)
+                    torch.cuda.synchronize()
+                    self.graph_launches = 0
+                    if self.world == 1:
+                        graphs = (self._capture(lambda: (self._seg_d(*a_d), self._seg_g(*a_g))),)
+                    else:
+                        graphs = (self._capture(self._seg_d, *a_d), self._capture(self._seg_g, *a_g))
+                    self._graphs[key] = graphs       # capture does not execute: fall through to the replay below
+        self._sync_hyper()
+        if graphs is None:
+            self._seg_d(*a_d)
+            self._allreduce_d_grads()
+            if self.on_d_grads is not None:
+                self.on_d_grads(self)              # observer hook: flat_grad holds the (summed) D-step gradients Adam is about to consume
+            self._seg_g(*a_g)
+        else:
+            self.replayed_launches += self.graph_launches
+            graphs[0].replay()
+            if len(graphs) == 2:
+                self._allreduce_d_grads()
+                graphs[1].replay()
         self.gen_opt.step()          # no-op: generator grads are None
         return self.loss_d[0], self.loss_g[0]
-
 
 class HostBatchPipeline:
     """Feeds HOST batches (pinned tensors, e.g. what the DataLoader and the host DES bridge hand over) to
@@ -153,6 +234,8 @@ class HostBatchPipeline:
         self.t = trainer
         dev = trainer.flat_grad.device
         self.stage = [{k: torch.empty_like(example[k], device=dev) for k in self.KEYS} for _ in range(2)]
+        B = example["real"].shape[0]
+        self.noise = [[torch.empty(B, trainer.m.z_dim, device=dev) for _ in range(2)] for _ in range(2)]     # static: graph replay
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
@@ -183,9 +266,9 @@ class HostBatchPipeline:
                 self._issue(1 - slot, nxt, i == 0)
             main.wait_event(self.ready[slot])
             st = self.stage[slot]
-            B = st["real"].shape[0]
-            n1 = torch.randn(B, self.t.m.z_dim, device=st["real"].device)          # network_tests.py:284-285
-            n2 = torch.randn(B, self.t.m.z_dim, device=st["real"].device)
+            n1, n2 = self.noise[slot]
+            n1.normal_()                                                          # network_tests.py:284-285
+            n2.normal_()
             dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
             self.free[slot].record(main)
             self.losses_host.copy_(torch.stack([dl, gl]), non_blocking=False)

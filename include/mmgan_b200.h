@@ -59,6 +59,11 @@ int mmg_act_bwd_f32(const float* y, const float* dy, float* dz, int64_t n, int a
 int mmg_adam_multi_tensor_f32(int n_tensors, void* const* ptrs, const int64_t* sizes, float lr, float beta1,
                               float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
+/* the same update with [lr, beta1, beta2, eps] (hyper_dev, fp32) and the count of updates applied so far (step_dev, int64,
+ * incremented by the call) in DEVICE memory, so the launch can be replayed from a CUDA graph; at most 48 tensors. */
+int mmg_adam_multi_tensor_dev_f32(int n_tensors, void* const* ptrs, const int64_t* sizes, const float* hyper_dev,
+                                  int64_t* step_dev, float grad_scale, void* stream);
+
 /* ---- fp32 layers (full-precision path) ----
  * nn.Linear (network_tests.py:77,139,154; SIMNN.py:127-128): y = act(x.w^T + b) */
 int mmg_linear_fwd_f32(const float* x, const float* w, const float* b, float* y, int64_t M, int64_t N, int64_t K,

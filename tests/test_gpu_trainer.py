@@ -116,3 +116,39 @@ def test_bf16_g_step_from_reference_weights(golden_dir):
             want_g = g[pre + "grad_g.discriminator." + k] - g[pre + "grad_d.discriminator." + k]       # the G-step contribution alone
             errs[k] = _rel_l2(p.grad, want_g)
         assert all(v <= (5e-2 if k in ("conv1.weight", "conv2.weight") else 1e-2) for k, v in errs.items()), (it, errs)
+
+
+def test_graph_replay_matches_eager():
+    """The captured iteration (CUDA graph, device-side Adam step/lr) must do what the eager iteration does, including a
+    StepLR-style learning-rate change between replays."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    B = 64
+    torch.manual_seed(3)
+    rolls = [(torch.rand(B, 2, 128, 50) < 0.02).to(torch.uint8).cuda() * 77 for _ in range(3)]
+    noise = [torch.randn(B, 50).cuda() for _ in range(4)]
+    beats = (25 * torch.rand(B, 50)).cuda()
+    out = {}
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150,
+                             device="cuda").train()
+        tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=B, use_graph=use_graph)
+        losses = []
+        for it in range(6):
+            if it == 4:
+                tr.disc_opt.param_groups[0]["lr"] = 0.001
+            dl, gl = tr.step(noise[0], noise[1], beats, rolls[0], rolls[1], rolls[2], noise[2], noise[3])
+            losses.append((float(dl), float(gl)))
+        assert tr.disc_opt.state[tr.d_params[0]]["step"] == 6 and int(tr.adam_step) == 6
+        assert bool(tr._graphs) == use_graph
+        out[use_graph] = (losses, [p.detach().clone() for p in m.discriminator.parameters()],
+                          m.generator1.gen[0][1].running_mean.clone(), int(m.generator1.gen[0][1].num_batches_tracked))
+    (l0, p0, rm0, nb0), (l1, p1, rm1, nb1) = out[False], out[True]
+    assert nb0 == nb1 == 12
+    assert torch.allclose(rm0, rm1, rtol=1e-5, atol=1e-7)
+    for a, b in zip(l0, l1):
+        assert abs(a[0] - b[0]) <= 2e-3 * max(1.0, abs(a[0])) and abs(a[1] - b[1]) <= 2e-3 * max(1.0, abs(a[1])), (l0, l1)
+    for a, b in zip(p0, p1):       # atomics reorder fp32 sums; Adam amplifies sign flips of ~0 gradients by lr per step
+        assert (a - b).abs().max() <= 6 * 0.01 + 1e-6
+        assert _rel_l2(a, b.cpu().numpy()) < 0.05
