@@ -50,6 +50,24 @@ SIGNATURES = {
     "mmg_disc_conv1_wgrad": (_I, [_P, _P, _P, _L, _P]),
 }
 
+
+
+class GenLayerArgs(ctypes.Structure):
+    """mmg_gen_layer_args of include/mmgan_b200.h"""
+    _fields_ = [("x0", _P), ("x1", _P), ("k0", _I), ("k1", _I),
+                ("in_mode", _I), ("in_sums", _P), ("in_gamma", _P), ("in_beta", _P), ("in_run_mean", _P), ("in_run_var", _P),
+                ("w_packed", _P), ("bias", _P), ("N", _I),
+                ("z_out", _P), ("out_sums", _P), ("y_out", _P),
+                ("out_mode", _I), ("y_sums", _P), ("out_gamma", _P), ("out_beta", _P), ("out_run_mean", _P), ("out_run_var", _P),
+                ("momentum", _F), ("eps", _F), ("update_running", _I), ("M", _L)]
+
+
+SIGNATURES.update({
+    "mmg_gen_packed_weight_bytes": (_Z, [_I, _I]),
+    "mmg_gen_pack_weight": (_I, [_P, _I, _I, _P, _P]),
+    "mmg_gen_layer_fwd": (_I, [ctypes.POINTER(GenLayerArgs), _P]),
+})
+
 _lib = None
 
 

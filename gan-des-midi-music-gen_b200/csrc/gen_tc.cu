@@ -1,0 +1,360 @@
+// bf16 tensor-core path of the MM-GAN generators (Generator / BeatGenerator, network_tests.py:58-123):
+// every [Linear -> BatchNorm1d -> Sigmoid] block (network_tests.py:75-80) as ONE tcgen05 GEMM kernel per layer with the
+// normalisation folded into its two ends:
+//
+//   prologue  the A tile (128 batch rows x K input features, bf16, 128-byte-swizzled K-major) is BUILT IN SHARED MEMORY by
+//             the epilogue threads from the previous layer's fp32 pre-activations z: a = sigmoid(z * scale + shift), with
+//             scale / shift derived per CTA from that layer's batch sums (training) or running stats (eval).  The first
+//             layer builds it from the two raw inputs instead (the torch.cat of network_tests.py:86,122 never exists).
+//   GEMM      tcgen05.mma (M = 128, N <= 256, K = 16 per instruction), weights bf16 [N][Kp] streamed by TMA, fp32
+//             accumulators double-buffered in TMEM so that the MMAs of item i+1 run under the epilogue of item i.
+//   epilogue  + bias, then any of: store z (fp32), accumulate the per-column batch sums (sum z, sum z^2: in-tile
+//             shuffle transpose-reduction in fp32, cross-tile atomics in fp64), or y = sigmoid(BN(z)) stored fp32.
+//
+// Training-mode BatchNorm needs the statistics of the whole batch before anything can be normalised, so a layer's z is
+// written (hidden layers: <= 1 KB per sample) and normalised by the NEXT layer's prologue; the last layer (4096 wide for
+// the Generator = 16 KB per sample) is never written un-normalised: it runs twice, first accumulating only the sums, then
+// recomputing the GEMM (K = 64) and writing y once.  Running statistics follow torch (momentum, unbiased variance).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/mmgan_b200.h"
+
+namespace {
+
+constexpr int GT_THREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2-5 builders + epilogue
+constexpr int GT_MAX_K = 256;
+constexpr int GT_A_CHUNK = 128 * 128;           // 128 rows x 64 bf16
+constexpr int GT_W_STAGES = 2;
+constexpr int GT_SMEM_MIN = 120 * 1024;         // keeps one CTA per SM (every CTA allocates all 512 TMEM columns)
+
+struct GenDev {
+    const float* x0; const float* x1; int k0, k1;
+    int in_mode;                                // 0 raw, 1 BN(batch sums)+sigmoid, 2 BN(running)+sigmoid
+    const double* in_sums; const float* in_gamma; const float* in_beta; float* in_run_mean; float* in_run_var;
+    const float* bias; int N, NG, n_groups, K, Kp;
+    float* z_out; double* out_sums; float* y_out;
+    int out_mode;                               // for y_out: 1 batch sums (y_sums), 2 running stats
+    const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
+    float momentum, eps; int update_running;
+    long long M; int row_tiles;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// lane l ends up with sum over the warp's lanes of v[l]  (31 shuffles; v is clobbered)
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void bn_scale_shift(double s1, double s2, double count, float gamma, float beta, float eps, float& scale, float& shift,
+                                               float& mean_f, float& var_f) {
+    const double mu = s1 / count;
+    double var = s2 / count - mu * mu;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    scale = gamma * invstd;
+    shift = beta - (float)mu * scale;
+    mean_f = (float)mu;
+    var_f = (float)var;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __grid_constant__ CUtensorMap map_w, const GenDev a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t wfull[GT_W_STAGES], wempty[GT_W_STAGES], aready, tfull[2], tempty[2];
+    __shared__ uint32_t tmem_s;
+    __shared__ float in_scale[GT_MAX_K], in_shift[GT_MAX_K];
+    __shared__ float ep_bias[256], ep_scale[256], ep_shift[256];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kchunks = a.Kp / 64;
+    unsigned char* smem_a = smem;                                   // kchunks x 16 KB
+    const int w_stage_bytes = kchunks * a.NG * 128;
+    unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // GT_W_STAGES x w_stage_bytes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = a.row_tiles * a.n_groups;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GT_W_STAGES; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
+        tc::mbar_init(&aready, 128);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
+    // input-side BatchNorm folded to scale/shift (every CTA needs all K features; CTA 0 also updates the running stats)
+    if (a.in_mode != 0) {
+        for (int k = threadIdx.x; k < a.K; k += GT_THREADS) {
+            float sc, sh;
+            if (a.in_mode == 1) {
+                float mu, var;
+                bn_scale_shift(a.in_sums[k], a.in_sums[a.K + k], (double)a.M, a.in_gamma[k], a.in_beta[k], a.eps, sc, sh, mu, var);
+                if (a.update_running && blockIdx.x == 0 && a.in_run_mean) {
+                    const float unb = var * (float)((double)a.M / ((double)a.M - 1.0));
+                    a.in_run_mean[k] = (1.f - a.momentum) * a.in_run_mean[k] + a.momentum * mu;
+                    a.in_run_var[k] = (1.f - a.momentum) * a.in_run_var[k] + a.momentum * unb;
+                }
+            } else {
+                const float invstd = rsqrtf(a.in_run_var[k] + a.eps);
+                sc = a.in_gamma[k] * invstd;
+                sh = a.in_beta[k] - a.in_run_mean[k] * sc;
+            }
+            in_scale[k] = sc;
+            in_shift[k] = sh;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::tma_prefetch_desc(&map_w);
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+                const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
+                const int grp = item % a.n_groups;
+                tc::mbar_wait(&wempty[stage], phase ^ 1);
+                tc::mbar_expect_tx(&wfull[stage], w_stage_bytes);
+                for (int c = 0; c < kchunks; ++c)
+                    tc::tma_load_2d(smem_w + stage * w_stage_bytes + c * a.NG * 128, &map_w, &wfull[stage], c * 64, grp * a.NG);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);
+            const uint32_t idesc = tc::idesc_bf16(128, (uint32_t)a.NG);
+            const uint32_t a_addr = tc::smem_u32(smem_a), w_addr = tc::smem_u32(smem_w);
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+                const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
+                const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::mbar_wait(&aready, it & 1);
+                tc::mbar_wait(&wfull[stage], phase);
+                tc::tc_fence_after();
+                const uint32_t wb = w_addr + stage * w_stage_bytes;
+                for (int c = 0; c < kchunks; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_f16_ss(tmem + acc * 256, tc::smem_desc(KM128, a_addr + c * GT_A_CHUNK + k * 32),
+                                       tc::smem_desc(KM128, wb + c * a.NG * 128 + k * 32), idesc, (c | k) != 0);
+                tc::mma_commit(&wempty[stage]);
+                tc::mma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3, t = q * 32 + lane;               // t = row of the tile = TMEM lane
+        const int et = threadIdx.x - 64;                           // 0..127 over the builder/epilogue threads
+        // ---- A-tile builder: row t of row tile `rt`, all Kp features, swizzled 16-byte pieces
+        auto build = [&](int rt) {
+            const long long row = (long long)rt * 128 + t;
+            const bool live = row < a.M;
+            for (int c = 0; c < kchunks; ++c) {
+                unsigned char* dst = smem_a + c * GT_A_CHUNK + t * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = c * 64 + j * 8;
+                    float v[8];
+                    if (!live || k >= a.K) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    } else if (a.in_mode == 0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int kk = k + e;
+                            v[e] = kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < a.K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f);
+                        }
+                    } else {                                       // K is a multiple of 8 here (checked on the host)
+                        const float4 p0 = *reinterpret_cast<const float4*>(a.x0 + row * a.K + k);
+                        const float4 p1 = *reinterpret_cast<const float4*>(a.x0 + row * a.K + k + 4);
+                        const float z[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = sigmoidf_(fmaf(z[e], in_scale[k + e], in_shift[k + e]));
+                    }
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (t & 7)) << 4)) =
+                        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&aready);
+        };
+        int it = 0;
+        int item = blockIdx.x;
+        if (item < items) build(item / a.n_groups);
+        for (; item < items; item += gridDim.x, ++it) {
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int rt = item / a.n_groups, grp = item % a.n_groups, n0 = grp * a.NG;
+            // per-item column constants (bias; output-side BN folded to scale/shift)
+            asm volatile("bar.sync 1, 128;" ::: "memory");        // previous item's epilogue no longer reads ep_*
+            for (int c = et; c < a.NG; c += 128) {
+                const int n = n0 + c;
+                ep_bias[c] = (n < a.N && a.bias) ? a.bias[n] : 0.f;
+                if (a.y_out) {
+                    float sc = 0.f, sh = 0.f;
+                    if (n < a.N) {
+                        if (a.out_mode == 1) {
+                            float mu, var;
+                            bn_scale_shift(a.y_sums[n], a.y_sums[a.N + n], (double)a.M, a.out_gamma[n], a.out_beta[n], a.eps, sc, sh, mu, var);
+                            if (a.update_running && rt == 0 && a.out_run_mean) {       // exactly one item owns (row tile 0, column n)
+                                const float unb = var * (float)((double)a.M / ((double)a.M - 1.0));
+                                a.out_run_mean[n] = (1.f - a.momentum) * a.out_run_mean[n] + a.momentum * mu;
+                                a.out_run_var[n] = (1.f - a.momentum) * a.out_run_var[n] + a.momentum * unb;
+                            }
+                        } else {
+                            const float invstd = rsqrtf(a.out_run_var[n] + a.eps);
+                            sc = a.out_gamma[n] * invstd;
+                            sh = a.out_beta[n] - a.out_run_mean[n] * sc;
+                        }
+                    }
+                    ep_scale[c] = sc;
+                    ep_shift[c] = sh;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            tc::tc_fence_after();
+            // the MMAs of this item are complete: the A buffer is free, build the next item's tile so its MMAs overlap this epilogue
+            const int next = item + gridDim.x;
+            if (next < items) build(next / a.n_groups);
+            const long long row = (long long)rt * 128 + t;
+            const bool live = row < a.M;
+            for (int c0 = 0; c0 < a.NG; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, r);
+                tc::tmem_ld_wait();
+                float z[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) z[e] = __uint_as_float(r[e]) + ep_bias[c0 + e];
+                const int ncols = a.N - (n0 + c0);                  // columns of this chunk that exist (>= 32: all)
+                if (a.z_out && live) {
+                    float* zp = a.z_out + row * a.N + n0 + c0;
+                    if (ncols >= 32 && (a.N & 3) == 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(zp + e) = make_float4(z[e], z[e + 1], z[e + 2], z[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) zp[e] = z[e];
+                    }
+                }
+                if (a.y_out && live) {
+                    float* yp = a.y_out + row * a.N + n0 + c0;
+                    float y[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) y[e] = sigmoidf_(fmaf(z[e], ep_scale[c0 + e], ep_shift[c0 + e]));
+                    if (ncols >= 32 && (a.N & 3) == 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(yp + e) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) yp[e] = y[e];
+                    }
+                }
+                if (a.out_sums) {
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) { s1[e] = live ? z[e] : 0.f; s2[e] = s1[e] * s1[e]; }
+                    const float c1 = colsum32(s1, lane), c2 = colsum32(s2, lane);
+                    if (lane < ncols) {
+                        atomicAdd(&a.out_sums[n0 + c0 + lane], (double)c1);
+                        atomicAdd(&a.out_sums[a.N + n0 + c0 + lane], (double)c2);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+__global__ void gen_pack_weights_kernel(const float* __restrict__ w, int N, int K, int Np, int Kp, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np * Kp) return;
+    const int n = i / Kp, k = i - n * Kp;
+    out[i] = __float2bfloat16((n < N && k < K) ? w[(size_t)n * K + k] : 0.f);
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+// bytes of the bf16 operand copy of an nn.Linear weight (N, K): [Np][Kp], Np = N rounded up to 32 (to 256 when N > 256), Kp = K to 64
+size_t mmg_gen_packed_weight_bytes(int N, int K) {
+    if (N <= 0 || K <= 0) return 0;
+    const int Np = N > 256 ? round_up(N, 256) : round_up(N, 32);
+    return (size_t)Np * round_up(K, 64) * 2;
+}
+
+int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream) {
+    MMG_REQUIRE(w && packed && N > 0 && K > 0, MMG_EINVAL, "gen_pack_weight: bad arguments");
+    const int Np = N > 256 ? round_up(N, 256) : round_up(N, 32), Kp = round_up(K, 64);
+    gen_pack_weights_kernel<<<(Np * Kp + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, N, K, Np, Kp, (__nv_bfloat16*)packed);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
+    MMG_REQUIRE(p && p->x0 && p->w_packed && p->M > 0 && p->N > 0 && p->k0 > 0 && p->k1 >= 0, MMG_EINVAL, "gen_layer_fwd: bad arguments");
+    const int K = p->k0 + p->k1;
+    MMG_REQUIRE(K <= GT_MAX_K, MMG_EUNSUPPORTED, "gen_layer_fwd: at most %d input features (got %d)", GT_MAX_K, K);
+    MMG_REQUIRE(p->in_mode >= 0 && p->in_mode <= 2, MMG_EINVAL, "gen_layer_fwd: bad in_mode");
+    if (p->in_mode != 0) {
+        MMG_REQUIRE(p->k1 == 0 && (K & 7) == 0 && ((uintptr_t)p->x0 & 15) == 0, MMG_EUNSUPPORTED, "gen_layer_fwd: BN prologue needs one 16-byte-aligned input with K % 8 == 0");
+        MMG_REQUIRE(p->in_gamma && p->in_beta, MMG_EINVAL, "gen_layer_fwd: missing input BN affine");
+        MMG_REQUIRE(p->in_mode == 1 ? p->in_sums != nullptr : (p->in_run_mean && p->in_run_var), MMG_EINVAL, "gen_layer_fwd: missing input BN statistics");
+        MMG_REQUIRE(p->in_mode != 1 || p->M > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, K);
+    } else {
+        MMG_REQUIRE(p->k1 == 0 || p->x1, MMG_EINVAL, "gen_layer_fwd: missing second input");
+    }
+    if (p->y_out) {
+        MMG_REQUIRE(p->out_gamma && p->out_beta && (p->out_mode == 1 ? p->y_sums != nullptr : (p->out_mode == 2 && p->out_run_mean && p->out_run_var)), MMG_EINVAL,
+                    "gen_layer_fwd: missing output BN parameters");
+        MMG_REQUIRE(p->out_mode != 1 || p->M > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, p->N);
+    }
+    GenDev a;
+    a.x0 = p->x0; a.x1 = p->x1; a.k0 = p->k0; a.k1 = p->k1; a.in_mode = p->in_mode;
+    a.in_sums = p->in_sums; a.in_gamma = p->in_gamma; a.in_beta = p->in_beta; a.in_run_mean = p->in_run_mean; a.in_run_var = p->in_run_var;
+    a.bias = p->bias; a.N = p->N; a.K = K; a.Kp = round_up(K, 64);
+    a.NG = p->N > 256 ? 256 : round_up(p->N, 32);
+    a.n_groups = (p->N + a.NG - 1) / a.NG;
+    a.z_out = p->z_out; a.out_sums = p->out_sums; a.y_out = p->y_out; a.out_mode = p->out_mode; a.y_sums = p->y_sums;
+    a.out_gamma = p->out_gamma; a.out_beta = p->out_beta; a.out_run_mean = p->out_run_mean; a.out_run_var = p->out_run_var;
+    a.momentum = p->momentum; a.eps = p->eps; a.update_running = p->update_running; a.M = p->M;
+    const long long row_tiles = (p->M + 127) / 128;
+    MMG_REQUIRE(row_tiles * a.n_groups < (1LL << 30), MMG_EUNSUPPORTED, "gen_layer_fwd: batch too large");
+    a.row_tiles = (int)row_tiles;
+    const int Np = a.NG * a.n_groups;
+    CUtensorMap map_w;
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_w, p->w_packed, (uint64_t)a.Kp, (uint64_t)Np, (uint64_t)a.Kp * 2, 64, (uint32_t)a.NG, CU_TENSOR_MAP_SWIZZLE_128B) == 0,
+                MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(w) failed");
+    const int kchunks = a.Kp / 64;
+    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128;
+    if (smem < GT_SMEM_MIN) smem = GT_SMEM_MIN;
+    MMG_REQUIRE(smem <= 220 * 1024, MMG_EUNSUPPORTED, "gen_layer_fwd: tile does not fit shared memory");
+    const long long items = row_tiles * a.n_groups;
+    const int grid = (int)(items < MMG_NUM_SMS ? items : MMG_NUM_SMS);
+    MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    gen_layer_tc_kernel<<<grid, GT_THREADS, smem, (cudaStream_t)stream>>>(map_w, a);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+}  // extern "C"

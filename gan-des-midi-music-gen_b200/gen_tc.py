@@ -1,0 +1,97 @@
+"""bf16 tensor-core execution of the MM-GAN generators (forward, training or eval mode) over the C ABI.
+
+``GenTC`` wraps a ``Generator`` / ``BeatGenerator`` module (fp32 master parameters, the reference's state-dict keys,
+network_tests.py:58-123): it owns the packed bf16 weights, the fp32 pre-activation buffers of the hidden layers and the
+fp64 batch-sum buffers, and runs the 4-block stack as 5 launches of ``mmg_gen_layer_fwd`` (csrc/gen_tc.cu): one per
+layer, the last layer twice (batch sums, then normalise + sigmoid + the single write of the output).  Training mode
+updates ``running_mean`` / ``running_var`` / ``num_batches_tracked`` in place like ``nn.BatchNorm1d``.
+Forward only: the reference never back-propagates into the generators; the fp32 modules keep the
+differentiable path.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+
+
+class GenTC:
+    def __init__(self, gen, max_batch):
+        self.g = gen
+        self.blocks = [(blk[0], blk[1]) for blk in gen.gen]            # (Linear, BatchNorm1d)
+        dev = self.blocks[0][0].weight.device
+        N.require_cuda(self.blocks[0][0].weight)
+        self.dev, self.cap = dev, int(max_batch)
+        self.widths = [lin.out_features for lin, _ in self.blocks]
+        if self.blocks[0][0].in_features > 256 or any(w > 256 for w in self.widths[:-1]):
+            raise ValueError("the tensor-core generator path supports at most 256 input features per layer")
+        self.packed = [torch.empty(N.lib().mmg_gen_packed_weight_bytes(lin.out_features, lin.in_features), dtype=torch.uint8, device=dev)
+                       for lin, _ in self.blocks]
+        self._versions = None
+        self.z = [torch.empty(self.cap, w, device=dev) for w in self.widths[:-1]]
+        offs, o = [], 0
+        for w in self.widths:
+            offs.append(o)
+            o += 2 * w
+        self.sums = torch.zeros(o, dtype=torch.float64, device=dev)     # [layer][sum | sumsq][width]
+        self.sum_views = [self.sums[a:a + 2 * w] for a, w in zip(offs, self.widths)]
+        self.pack()
+
+    def pack(self, force=True):
+        """Re-derive the bf16 operand copies from the fp32 master weights (cheap; skipped when nothing changed)."""
+        vers = tuple(lin.weight._version for lin, _ in self.blocks)
+        if not force and vers == self._versions:
+            return
+        for (lin, _), pk in zip(self.blocks, self.packed):
+            N.call("mmg_gen_pack_weight", N.ptr(lin.weight.data), lin.out_features, lin.in_features, N.ptr(pk), N.stream())
+        self._versions = vers
+
+    def forward(self, noise, input_tensor, training=None, out=None):
+        """noise (B,z) and input_tensor (B,input_dim) fp32 CUDA tensors -> (B, out_features) fp32 (caller reshapes)."""
+        N.require_cuda(noise, input_tensor)
+        training = self.g.training if training is None else training
+        B = noise.shape[0]
+        if B > self.cap:
+            raise ValueError(f"batch {B} exceeds the preallocated capacity {self.cap}")
+        if training and B <= 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {(B, self.widths[0])}")
+        noise, input_tensor = noise.float().contiguous(), input_tensor.float().contiguous()
+        self.pack(force=False)
+        s = N.stream()
+        if training:
+            N.call("mmg_zero", N.ptr(self.sums), self.sums.numel() * 8, s)
+        y = out if out is not None else torch.empty(B, self.widths[-1], device=self.dev)
+        mode = 1 if training else 2
+        last = len(self.blocks) - 1
+        for i, (lin, bn) in enumerate(self.blocks):
+            a = N.GenLayerArgs()
+            if i == 0:
+                a.x0, a.k0, a.x1, a.k1, a.in_mode = N.ptr(noise), noise.shape[1], N.ptr(input_tensor), input_tensor.shape[1], 0
+            else:
+                pbn = self.blocks[i - 1][1]
+                a.x0, a.k0, a.x1, a.k1, a.in_mode = N.ptr(self.z[i - 1]), self.widths[i - 1], None, 0, mode
+                a.in_sums = N.ptr(self.sum_views[i - 1]) if training else None
+                a.in_gamma, a.in_beta = N.ptr(pbn.weight.data), N.ptr(pbn.bias.data)
+                a.in_run_mean, a.in_run_var = N.ptr(pbn.running_mean), N.ptr(pbn.running_var)
+            a.w_packed, a.bias, a.N = N.ptr(self.packed[i]), N.ptr(lin.bias.data), lin.out_features
+            a.momentum = bn.momentum if bn.momentum is not None else 0.1
+            a.eps, a.M = bn.eps, B
+            a.update_running = int(training)
+            if i < last:
+                a.z_out = N.ptr(self.z[i])
+                a.out_sums = N.ptr(self.sum_views[i]) if training else None
+                N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
+            else:
+                a.out_gamma, a.out_beta = N.ptr(bn.weight.data), N.ptr(bn.bias.data)
+                a.out_run_mean, a.out_run_var = N.ptr(bn.running_mean), N.ptr(bn.running_var)
+                if training:                       # pass 1: batch sums only (also the one update of the previous layer's running stats)
+                    a.out_sums = N.ptr(self.sum_views[i])
+                    N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
+                    a.out_sums = None
+                    a.in_run_mean = a.in_run_var = None      # already updated by pass 1
+                a.y_out, a.out_mode = N.ptr(y), mode
+                a.y_sums = N.ptr(self.sum_views[i]) if training else None
+                N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
+        if training:
+            torch._foreach_add_([bn.num_batches_tracked for _, bn in self.blocks], 1)
+        return y

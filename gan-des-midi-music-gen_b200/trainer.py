@@ -65,11 +65,15 @@ class MMGANTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.on_d_grads = None
         self.tc = None
+        self._g_out = None
         if precision == "bf16":
             if max_batch is None:
                 raise ValueError("precision='bf16' needs max_batch (activation buffers are preallocated)")
             from .disc_tc import DiscTC
+            from .gen_tc import GenTC
             self.tc = DiscTC(D, max_batch)
+            self.gtc1 = GenTC(mmgan.generator1, max_batch)
+            self.gtc2 = GenTC(mmgan.generator2, max_batch)
         dev = self.flat_grad.device
         if inner_rng not in ("reference", "device"):
             raise ValueError("inner_rng must be 'reference' or 'device'")
@@ -133,8 +137,16 @@ class MMGANTrainer:
     def _generators(self, noise1, noise2, beats, inner):
         m = self.m
         with torch.no_grad():
-            self.g1_out = m.generator1(noise1, inner)
-            self.g2_out = m.generator2(noise2, beats)
+            if self.tc is not None:          # bf16 tcgen05 blocks (csrc/gen_tc.cu); outputs land in static buffers
+                B = noise1.shape[0]
+                if self._g_out is None or self._g_out[0].shape[0] != B:
+                    self._g_out = (torch.empty(B, self.gtc1.widths[-1], device=noise1.device), torch.empty(B, self.gtc2.widths[-1], device=noise1.device))
+                a = m.generator1.adj_size
+                self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
+                self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
+            else:
+                self.g1_out = m.generator1(noise1, inner)
+                self.g2_out = m.generator2(noise2, beats)
 
     def _d_pass(self, x, target, loss, accumulate):
         """forward + BCE + backward of the discriminator on one batch; grads accumulate into flat_grad"""

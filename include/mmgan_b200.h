@@ -112,6 +112,32 @@ int mmg_disc_conv2_wgrad(const void* p1, const void* dz2, float* dconv2_w, int64
 int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1c, float* dconv1_b, int64_t B, void* stream);
 int mmg_disc_conv1_wgrad(const void* xs, const void* dz1c, float* dconv1_w, int64_t B, void* stream);
 
+/* ---- bf16 tensor-core generator blocks ([Linear -> BatchNorm1d -> Sigmoid], network_tests.py:75-80, as used by Generator
+ * :58-90 and BeatGenerator :93-123) ----
+ * One call = one Linear layer as a tcgen05 GEMM (bf16 operands, fp32 accumulate) with the neighbouring BatchNorm + sigmoid
+ * folded into its prologue / epilogue (csrc/gen_tc.cu).  Input rows are x0 (M,k0) [|| x1 (M,k1)] fp32:
+ *   in_mode 0: used as they are (first layer; the torch.cat of network_tests.py:86,122 is never materialised);
+ *   in_mode 1: x0 holds the PREVIOUS layer's pre-activations z; a = sigmoid(BN(z)) with batch statistics from in_sums
+ *              (sum z | sum z^2, fp64 [2][K]) and in_gamma / in_beta; if update_running, in_run_mean / in_run_var are updated
+ *              (momentum, unbiased variance) exactly once;
+ *   in_mode 2: the same with the running statistics (eval).
+ * w_packed = mmg_gen_pack_weight(weight (N,K)); bias (N,) fp32.  Outputs (any subset, NULL = skip):
+ *   z_out (M,N) fp32 pre-activations;  out_sums fp64 [2][N] += column sums of z and z^2 (zero them before the first layer call
+ *   of a forward);  y_out (M,N) fp32 = sigmoid(BN(z)) with out_mode 1 = batch statistics y_sums (complete sums of THIS layer,
+ *   i.e. a previous call accumulated them) or 2 = running statistics; out_run_* updated if update_running and out_mode 1.
+ * Train-mode statistics over M <= 1 rows fail with -1 and torch's "Expected more than 1 value per channel" message. */
+typedef struct mmg_gen_layer_args {
+    const float* x0; const float* x1; int k0; int k1;
+    int in_mode; const double* in_sums; const float* in_gamma; const float* in_beta; float* in_run_mean; float* in_run_var;
+    const void* w_packed; const float* bias; int N;
+    float* z_out; double* out_sums; float* y_out;
+    int out_mode; const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
+    float momentum; float eps; int update_running; int64_t M;
+} mmg_gen_layer_args;
+size_t mmg_gen_packed_weight_bytes(int N, int K);
+int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream);
+int mmg_gen_layer_fwd(const mmg_gen_layer_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""GPU parity of the bf16 tensor-core generator blocks (csrc/gen_tc.cu through the C ABI) against a plain PyTorch fp32
+restatement of the reference blocks (network_tests.py:75-80: Linear -> BatchNorm1d -> Sigmoid) and against the golden
+vectors frozen from the unmodified reference.  Tolerances: outputs abs 2e-2 (bf16 operands, fp32 accumulate),
+running statistics rel 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_ref(sd, prefix, x, training, momentum=0.1, eps=1e-5):
+    """fp32 CPU restatement; returns the output and the updated running stats"""
+    stats = []
+    for i in range(4):
+        p = f"{prefix}.gen.{i}"
+        z = F.linear(x, sd[p + ".0.weight"], sd[p + ".0.bias"])
+        rm, rv = sd[p + ".1.running_mean"].clone(), sd[p + ".1.running_var"].clone()
+        x = torch.sigmoid(F.batch_norm(z, rm, rv, sd[p + ".1.weight"], sd[p + ".1.bias"], training, momentum, eps))
+        stats.append((rm, rv))
+    return x, stats
+
+
+@pytest.mark.parametrize("B,which", [(16, "generator1"), (300, "generator1"), (16, "generator2"), (1000, "generator2"), (129, "generator2")])
+@pytest.mark.parametrize("training", [True, False])
+def test_gen_tc_vs_torch_fp32(B, which, training):
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    torch.manual_seed(B)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device="cuda")
+    g = getattr(m, which)
+    with torch.no_grad():                    # non-trivial affine / running stats
+        for blk in g.gen:
+            blk[1].weight.uniform_(0.5, 1.5); blk[1].bias.uniform_(-0.5, 0.5)
+            blk[1].running_mean.uniform_(-0.3, 0.3); blk[1].running_var.uniform_(0.5, 2.0)
+            blk[0].bias.uniform_(-0.2, 0.2)
+    g.train(training)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    noise = torch.randn(B, 50)
+    inp = torch.randn(B, 50) if which == "generator1" else 25 * torch.rand(B, 50)       # beats are raw seconds
+    want, stats = _torch_ref(sd, which, torch.cat((noise, inp), 1), training)
+    tc = GenTC(g, max_batch=B)
+    got = tc.forward(noise.cuda(), inp.cuda())
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    err = (got.cpu() - want).abs().max().item()
+    assert err < 2e-2, err
+    assert (got.cpu() - want).abs().mean().item() < 3e-3
+    for i, (rm, rv) in enumerate(stats):
+        bn = g.gen[i][1]
+        assert torch.allclose(bn.running_mean.cpu(), rm, rtol=2e-2, atol=2e-3), i
+        assert torch.allclose(bn.running_var.cpu(), rv, rtol=2e-2, atol=2e-3), i
+        assert int(bn.num_batches_tracked) == (1 if training else 0)
+
+
+def test_gen_tc_vs_reference_golden(golden_dir):
+    """Generator outputs of the unmodified reference (mmgan_b16.npz, first D-step forward) within the stated bf16 tolerance."""
+    import mmgan_oracle as mo
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    g = np.load(os.path.join(golden_dir, "mmgan_b16.npz"))
+    B, adj, out_dim, seed, iters = (int(v) for v in g["meta"])
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(adj, adj), roll_size=(2, 128, 50), input_dim=50, output_dim=out_dim, instrument=0, start=100, end=150, device="cuda")
+    m.load_state_dict(mo.synth_state(mo.mmgan_shapes(adj_size=(adj, adj), output_dim=out_dim), seed=seed, d_scale=0.25))
+    m.train()
+    inp = {k: v.cuda() for k, v in mo.synth_inputs(B, seed=seed * 1000).items()}
+    o1 = GenTC(m.generator1, B).forward(inp["noise1"], torch.from_numpy(g["it0.inner_d"]).cuda()).view(B, 1, adj, adj)
+    o2 = GenTC(m.generator2, B).forward(inp["noise2"], inp["beats"])
+    assert np.abs(o1.cpu().numpy()[:, :, ::4, ::4] - g["it0.g1_d.sub"]).max() < 2e-2
+    assert np.abs(o2.cpu().numpy() - g["it0.g2_d"]).max() < 2e-2
+
+
+def test_gen_tc_rejects_single_sample_in_training():
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    g = nt.Generator(z_dim=50, adj_size=(64, 64), device="cuda").cuda().train()
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        GenTC(g, 4).forward(torch.randn(1, 50).cuda(), torch.randn(1, 50).cuda())

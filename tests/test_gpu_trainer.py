@@ -78,7 +78,8 @@ def test_trainer_step_vs_reference_golden(golden_dir, precision, u8):
             for k, p in named.items():
                 ref_p = torch.from_numpy(g[pre + "param_d.discriminator." + k]).to(DEV)
                 assert (p - ref_p).abs().max().item() <= 2 * 0.01 * (it + 1) + 1e-6, k
-        assert _rel_l2(tr.g2_out, g[pre + "g2_g"]) <= 2e-5
+        assert _rel_l2(tr.g2_out, g[pre + "g2_g"]) <= (2e-5 if precision == "fp32" else 1e-2)      # bf16: tcgen05 generator blocks
+        assert np.abs(tr.g1_out.cpu().numpy()[:, :, ::4, ::4] - g[pre + "g1_g.sub"]).max() <= (1e-5 if precision == "fp32" else 2e-2)
         assert all(p.grad is None for p in m.generator1.parameters()) and len(tr.gen_opt.state) == 0
     sd = m.state_dict()
     for k in g.files:
