@@ -25,6 +25,7 @@ constexpr int GT_THREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps
 constexpr int GT_MAX_K = 256;
 constexpr int GT_A_CHUNK = 128 * 128;           // 128 rows x 64 bf16
 constexpr int GT_W_STAGES = 2;
+constexpr int GT_Y_STAGE = 128 * 128;           // 128 rows x 32 fp32
 constexpr int GT_SMEM_MIN = 120 * 1024;         // keeps one CTA per SM (every CTA allocates all 512 TMEM columns)
 
 struct GenDev {
@@ -43,7 +44,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid(x * scale + shift) with the two MUFU approximations (ex2, rcp: ~2 ulp), branch-free so that the 32-64 independent
+// evaluations of a row interleave; nl2e_* are scale / shift pre-multiplied by -log2(e)
+__device__ __forceinline__ float fast_sigmoid_affine(float x, float nl2e_scale, float nl2e_shift) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(x, nl2e_scale, nl2e_shift)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+constexpr float NEG_LOG2E = -1.4426950408889634f;
 
 // lane l ends up with sum over the warp's lanes of v[l]  (31 shuffles; v is clobbered)
 __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
@@ -72,7 +81,8 @@ __device__ __forceinline__ void bn_scale_shift(double s1, double s2, double coun
     var_f = (float)var;
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __grid_constant__ CUtensorMap map_w, const GenDev a) {
+__global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
+                                                                     const GenDev a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t wfull[GT_W_STAGES], wempty[GT_W_STAGES], aready, tfull[2], tempty[2];
     __shared__ uint32_t tmem_s;
@@ -83,6 +93,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
     unsigned char* smem_a = smem;                                   // kchunks x 16 KB
     const int w_stage_bytes = kchunks * a.NG * 128;
     unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // GT_W_STAGES x w_stage_bytes
+    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // 2 x 16 KB output staging (only when y_out)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = a.row_tiles * a.n_groups;
 
@@ -110,8 +121,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                 sc = a.in_gamma[k] * invstd;
                 sh = a.in_beta[k] - a.in_run_mean[k] * sc;
             }
-            in_scale[k] = sc;
-            in_shift[k] = sh;
+            in_scale[k] = sc * NEG_LOG2E;                          // pre-multiplied for fast_sigmoid_affine
+            in_shift[k] = sh * NEG_LOG2E;
         }
     }
     tc::tc_fence_before();
@@ -164,34 +175,36 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             const bool live = row < a.M;
             for (int c = 0; c < kchunks; ++c) {
                 unsigned char* dst = smem_a + c * GT_A_CHUNK + t * 128;
+                float v[64];                                       // all of the chunk's loads are issued before any is used
+                if (a.in_mode == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = c * 64 + j * 8;
-                    float v[8];
-                    if (!live || k >= a.K) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                    } else if (a.in_mode == 0) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int kk = k + e;
-                            v[e] = kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < a.K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f);
-                        }
-                    } else {                                       // K is a multiple of 8 here (checked on the host)
-                        const float4 p0 = *reinterpret_cast<const float4*>(a.x0 + row * a.K + k);
-                        const float4 p1 = *reinterpret_cast<const float4*>(a.x0 + row * a.K + k + 4);
-                        const float z[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = sigmoidf_(fmaf(z[e], in_scale[k + e], in_shift[k + e]));
+                    for (int e = 0; e < 64; ++e) {
+                        const int kk = c * 64 + e;
+                        v[e] = !live ? 0.f : (kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < a.K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f));
                     }
-                    *reinterpret_cast<uint4*>(dst + ((j ^ (t & 7)) << 4)) =
-                        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                } else {                                           // K is a multiple of 8 here (checked on the host)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = c * 64 + j * 4;
+                        const float4 p = (live && k < a.K) ? *reinterpret_cast<const float4*>(a.x0 + row * a.K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[4 * j] = p.x; v[4 * j + 1] = p.y; v[4 * j + 2] = p.z; v[4 * j + 3] = p.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 64; ++e) {
+                        const int k = c * 64 + e;
+                        v[e] = (live && k < a.K) ? fast_sigmoid_affine(v[e], in_scale[k], in_shift[k]) : 0.f;
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (t & 7)) << 4)) =
+                        make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                                   pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&aready);
         };
-        int it = 0;
+        int it = 0, ychunk = 0;
         int item = blockIdx.x;
         if (item < items) build(item / a.n_groups);
         for (; item < items; item += gridDim.x, ++it) {
@@ -219,8 +232,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                             sh = a.out_beta[n] - a.out_run_mean[n] * sc;
                         }
                     }
-                    ep_scale[c] = sc;
-                    ep_shift[c] = sh;
+                    ep_scale[c] = sc * NEG_LOG2E;                  // bias folded in: (acc + b) * sc + sh = acc * sc + (b * sc + sh)
+                    ep_shift[c] = (ep_bias[c] * sc + sh) * NEG_LOG2E;
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -236,8 +249,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                 tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, r);
                 tc::tmem_ld_wait();
                 float z[32];
+                if (a.z_out || a.out_sums) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) z[e] = __uint_as_float(r[e]) + ep_bias[c0 + e];
+                    for (int e = 0; e < 32; ++e) z[e] = __uint_as_float(r[e]) + ep_bias[c0 + e];
+                }
                 const int ncols = a.N - (n0 + c0);                  // columns of this chunk that exist (>= 32: all)
                 if (a.z_out && live) {
                     float* zp = a.z_out + row * a.N + n0 + c0;
@@ -249,18 +264,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                         for (int e = 0; e < 32; ++e) if (e < ncols) zp[e] = z[e];
                     }
                 }
-                if (a.y_out && live) {
-                    float* yp = a.y_out + row * a.N + n0 + c0;
+                if (a.y_out) {
+                    // y tile (128 rows x 32 fp32) -> 128-byte-swizzled staging buffer -> one TMA store (rows >= M and columns >= N are clipped)
+                    unsigned char* stg = smem_y + (ychunk & 1) * GT_Y_STAGE;
+                    if (et == 0) tc::bulk_wait_group_read<1>();        // the store issued from this buffer two chunks ago has read it
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                     float y[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) y[e] = sigmoidf_(fmaf(z[e], ep_scale[c0 + e], ep_shift[c0 + e]));
-                    if (ncols >= 32 && (a.N & 3) == 0) {
+                    for (int e = 0; e < 32; ++e) y[e] = fast_sigmoid_affine(__uint_as_float(r[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(yp + e) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (e < ncols) yp[e] = y[e];
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + t * 128 + ((j ^ (t & 7)) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    tc::fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        tc::tma_store_2d(&map_y, stg, n0 + c0, rt * 128);
+                        tc::bulk_commit_group();
                     }
+                    ++ychunk;
                 }
                 if (a.out_sums) {
                     float s1[32], s2[32];
@@ -277,6 +298,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
         }
+        if (et == 0) tc::bulk_wait_group_read<0>();                // staging buffers must outlive the last TMA store's reads
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -346,13 +368,19 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w, p->w_packed, (uint64_t)a.Kp, (uint64_t)Np, (uint64_t)a.Kp * 2, 64, (uint32_t)a.NG, CU_TENSOR_MAP_SWIZZLE_128B) == 0,
                 MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(w) failed");
     const int kchunks = a.Kp / 64;
-    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128;
+    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 2 * GT_Y_STAGE : 0);
+    CUtensorMap map_y = map_w;
+    if (p->y_out) {
+        MMG_REQUIRE(((uintptr_t)p->y_out & 15) == 0 && (p->N & 3) == 0, MMG_EUNSUPPORTED, "gen_layer_fwd: y_out must be 16-byte aligned with N % 4 == 0");
+        MMG_REQUIRE(tc::make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->y_out, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->N * 4, 32, 128,
+                                    CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(y) failed");
+    }
     if (smem < GT_SMEM_MIN) smem = GT_SMEM_MIN;
     MMG_REQUIRE(smem <= 220 * 1024, MMG_EUNSUPPORTED, "gen_layer_fwd: tile does not fit shared memory");
     const long long items = row_tiles * a.n_groups;
     const int grid = (int)(items < MMG_NUM_SMS ? items : MMG_NUM_SMS);
     MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    gen_layer_tc_kernel<<<grid, GT_THREADS, smem, (cudaStream_t)stream>>>(map_w, a);
+    gen_layer_tc_kernel<<<grid, GT_THREADS, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

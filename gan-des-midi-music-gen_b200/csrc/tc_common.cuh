@@ -48,6 +48,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// smem -> global tile store (bulk async group); the smem source must stay untouched until wait_group.read says so
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp; ncols power of 2 >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -114,17 +123,21 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     }
     return fn;
 }
-// 2-D bf16 tensor, dim0 contiguous (inner), dim1 rows with pitch `row_pitch_bytes` (multiple of 16).  Returns 0 on success.
-inline int make_map_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_inner,
-                            uint32_t box_rows, CUtensorMapSwizzle sw) {
+// 2-D tensor, dim0 contiguous (inner), dim1 rows with pitch `row_pitch_bytes` (multiple of 16).  Returns 0 on success.
+inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, int /*elem_bytes*/, const void* base, uint64_t inner, uint64_t rows,
+                       uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle sw) {
     auto fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t strides[1] = {row_pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    CUresult r = fn(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (int)r;
+}
+inline int make_map_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_inner,
+                            uint32_t box_rows, CUtensorMapSwizzle sw) {
+    return make_map_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner, rows, row_pitch_bytes, box_inner, box_rows, sw);
 }
 }  // namespace tc

@@ -66,6 +66,7 @@ class MMGANTrainer:
         self.on_d_grads = None
         self.tc = None
         self._g_out = None
+        self._side = torch.cuda.Stream(device=self.d_params[0].device) if precision == "bf16" else None
         if precision == "bf16":
             if max_batch is None:
                 raise ValueError("precision='bf16' needs max_batch (activation buffers are preallocated)")
@@ -142,8 +143,13 @@ class MMGANTrainer:
                 if self._g_out is None or self._g_out[0].shape[0] != B:
                     self._g_out = (torch.empty(B, self.gtc1.widths[-1], device=noise1.device), torch.empty(B, self.gtc2.widths[-1], device=noise1.device))
                 a = m.generator1.adj_size
+                # the two generators are independent: the beat generator runs on a side stream (fork / join, also under graph capture)
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
                 self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
-                self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
+                cur.wait_stream(self._side)
             else:
                 self.g1_out = m.generator1(noise1, inner)
                 self.g2_out = m.generator2(noise2, beats)
