@@ -15,7 +15,8 @@ _XD = {torch.float32: 0, torch.uint8: 2}
 
 
 class DiscTC:
-    def __init__(self, disc, max_batch, roll_size=(2, 128, 50)):
+    def __init__(self, disc, max_batch, roll_size=(2, 128, 50), fused_backward=True):
+        self.fused_backward = fused_backward
         if tuple(roll_size) != (2, 128, 50) or disc.conv1.weight.shape != (16, 2, 4, 4) or disc.conv2.weight.shape != (32, 16, 4, 4):
             raise ValueError("the tensor-core discriminator path is specialised to roll_size (2,128,50), hidden_dim 16")
         self.d = disc
@@ -64,6 +65,10 @@ class DiscTC:
         B, d, s = self.B, self.d, N.stream()
         dlogit = dlogit.contiguous()
         g = {k: self._grad(p) for k, p in d.named_parameters()}
+        if self.fused_backward:      # one persistent kernel: dz2 / dz1c never leave the SM (csrc/disc_tc_fused.cu)
+            N.call("mmg_disc_bwd_fused", N.ptr(self.xs), N.ptr(self.p1), N.ptr(self.a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(g["conv1.weight"]),
+                   N.ptr(g["conv1.bias"]), N.ptr(g["conv2.weight"]), N.ptr(g["conv2.bias"]), N.ptr(g["fc.weight"]), N.ptr(g["fc.bias"]), B, s)
+            return
         N.call("mmg_sum_f32", N.ptr(dlogit), B, N.ptr(g["fc.bias"]), 1, s)
         N.call("mmg_disc_fc_bwd", N.ptr(self.a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(self.dz2), N.ptr(g["fc.weight"]), N.ptr(g["conv2.bias"]), B, s)
         N.call("mmg_disc_conv2_wgrad", N.ptr(self.p1), N.ptr(self.dz2), N.ptr(g["conv2.weight"]), B, s)

@@ -112,6 +112,11 @@ int mmg_disc_conv2_wgrad(const void* p1, const void* dz2, float* dconv2_w, int64
 int mmg_disc_conv2_dgrad(const void* dz2, const void* packed, const void* p1, void* dz1c, float* dconv1_b, int64_t B, void* stream);
 int mmg_disc_conv1_wgrad(const void* xs, const void* dz1c, float* dconv1_w, int64_t B, void* stream);
 
+/* The whole backward of one pass in ONE persistent kernel (csrc/disc_tc_fused.cu): same inputs as the four calls above
+ * (xs, p1, a2 as left by the forward, dlogit), dz2 / dz1c stay in shared memory, all six gradients are accumulated (+=). */
+int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const float* dlogit, const void* packed, float* dconv1_w,
+                       float* dconv1_b, float* dconv2_w, float* dconv2_b, float* dfc_w, float* dfc_b, int64_t B, void* stream);
+
 /* ---- bf16 tensor-core generator blocks ([Linear -> BatchNorm1d -> Sigmoid], network_tests.py:75-80, as used by Generator
  * :58-90 and BeatGenerator :93-123) ----
  * One call = one Linear layer as a tcgen05 GEMM (bf16 operands, fp32 accumulate) with the neighbouring BatchNorm + sigmoid

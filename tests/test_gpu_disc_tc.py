@@ -29,14 +29,15 @@ def _rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("B,dtype", [(5, torch.uint8), (3, torch.float32), (37, torch.uint8)])
-def test_disc_tc_stages(B, dtype):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("B,dtype", [(5, torch.uint8), (3, torch.float32), (37, torch.uint8), (300, torch.uint8)])
+def test_disc_tc_stages(B, dtype, fused):
     from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
     from gan_des_midi_music_gen_b200.disc_tc import DiscTC
     sd = mo.synth_state(mo.mmgan_shapes(), seed=31, d_scale=0.25)
     D = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
     D.load_state_dict({k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")})
-    tc = DiscTC(D, max_batch=B + 2)
+    tc = DiscTC(D, max_batch=B + 2, fused_backward=fused)
     x8 = torch.from_numpy(mo.synth_rolls(B, 50, seed=32, p=0.05)).to(DEV)
     x = x8 if dtype == torch.uint8 else x8.float()
     logits = tc.forward(x).clone()
