@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(192, 2) conv2_fwd_tc_kernel(const __grid_const
     const uint32_t tmem = tmem_s;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::tma_prefetch_desc(&map_p1);
             tc::mbar_expect_tx(&wbar, C2F_W_BYTES);
             tc::tma_load_2d(smem_w, &map_w, &wbar, 0, 0);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(192, 2) conv2_fwd_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);
             constexpr uint32_t IDESC = tc::idesc_bf16(128, 32);
             const uint32_t w_addr = tc::smem_u32(smem_w), a_addr = tc::smem_u32(smem_a);

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(192, 1) conv2_wgrad_tc_kernel(const __grid_con
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
     if (c_hi > c_lo) {
-        if (warp == 0 && lane == 0) {
+        if (warp == 0 && tc::elect_one()) {
             for (int c = c_lo, it = 0; c < c_hi; ++c, ++it) {
                 const int stage = it % WG_STAGES, phase = (it / WG_STAGES) & 1;
                 tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(192, 1) conv2_wgrad_tc_kernel(const __grid_con
                 tc::tma_load_2d(st, &map_p1, &full[stage], 0, c * 128);
                 tc::tma_load_2d(st + WG_A_BYTES, &map_dz2, &full[stage], 0, c * 128);
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1 && tc::elect_one()) {
             constexpr uint64_t A_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);     // atom 1 = one row (128 B) later, 8-row K groups 1024 B apart
             constexpr uint64_t B_MN = tc::smem_desc_base(0, 512, tc::SW_64B);
             constexpr uint32_t IDESC = tc::idesc_bf16(128, 32, 1, 1);
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(192, 2) conv2_dgrad_tc_kernel(const __grid_con
     const uint32_t tmem = tmem_s;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::mbar_expect_tx(&wbar, DG_W_BYTES);
             tc::tma_load_2d(smem_w, &map_w, &wbar, 0, 0);
             int it = 0;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(192, 2) conv2_dgrad_tc_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint64_t KM64 = tc::smem_desc_base(0, 512, tc::SW_64B);
             constexpr uint32_t IDESC = tc::idesc_bf16(128, 64);
             const uint32_t w_addr = tc::smem_u32(smem_w), a_addr = tc::smem_u32(smem_a);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(192, 2) conv1_fwd_tc_kernel(const __grid_const
     const uint32_t tmem = tmem_s;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::mbar_expect_tx(&wbar, 1024);
             tc::tma_load_2d(smem_w, &map_w, &wbar, 0, 0);
             int it = 0;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(192, 2) conv1_fwd_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint64_t A_K = tc::smem_desc_base(16, 128, tc::SW_NONE);     // K chunk 1 = the next 16-byte row
             constexpr uint64_t B_K = tc::smem_desc_base(0, 256, tc::SW_32B);
             constexpr uint32_t IDESC = tc::idesc_bf16(128, 16);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(192, 2) conv1_wgrad_tc_kernel(const __grid_con
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
     if (c_hi > c_lo) {
-        if (warp == 0 && lane == 0) {
+        if (warp == 0 && tc::elect_one()) {
             for (int c = c_lo, it = 0; c < c_hi; ++c, ++it) {
                 const int stage = it % C1_STAGES, phase = (it / C1_STAGES) & 1;
                 tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(192, 2) conv1_wgrad_tc_kernel(const __grid_con
                 tc::tma_load_2d(st, &map_dz, &full[stage], 0, c * 128);
                 tc::tma_load_2d(st + C1W_B_BYTES, &map_xs, &full[stage], 0, c * 128);
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1 && tc::elect_one()) {
             constexpr uint64_t A_MN = tc::smem_desc_base(128, 16, tc::SW_NONE);    // atoms one row (16 B) apart, 8-row K groups 128 B apart
             constexpr uint64_t B_MN = tc::smem_desc_base(0, 256, tc::SW_32B);
             constexpr uint32_t IDESC = tc::idesc_bf16(64, 16, 1, 1);

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && n_my > 0) {
+        if (n_my > 0 && tc::elect_one()) {
+            const uint32_t leader = 1;
             constexpr uint64_t P1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);    // conv2 wgrad A: atom 1 = one row (128 B) later
             constexpr uint64_t DZ2_MN = tc::smem_desc_base(0, 512, tc::SW_64B);       // conv2 wgrad B
             constexpr uint64_t KM64 = tc::smem_desc_base(0, 512, tc::SW_64B);         // conv2 dgrad A (DZ2 rows) and B (W2d)
@@ -131,27 +132,29 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                 tc::tc_fence_after();
 #pragma unroll
                 for (int ty = 0; ty < 2; ++ty)
+#pragma unroll 9
                     for (int k = 0; k < K2_STEPS; ++k)
-                        tc::mma_f16_ss(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
-                                       ID_WG2, (it | k) != 0);
+                        tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
+                                       ID_WG2, (it | k) != 0, leader);
 #pragma unroll
                 for (int tile = 0; tile < 4; ++tile)
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            tc::mma_f16_ss(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
-                                           tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0);
-                tc::mma_commit(&mma1_done);
+                            tc::mma_f16_ss_pred(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
+                                           tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0, leader);
+                tc::mma_commit_pred(&mma1_done, leader);
                 tc::mbar_wait(&dz1_ready, ph);
                 tc::mbar_wait(&full_xs, ph);
                 tc::tc_fence_after();
 #pragma unroll
                 for (int ty = 0; ty < 2; ++ty)
+#pragma unroll 8
                     for (int k = 0; k < K1_STEPS; ++k)
-                        tc::mma_f16_ss(tmem + TM_W1 + ty * 16, tc::smem_desc(XS_MN, xs + (ty * XS_W + k * 16) * 16), tc::smem_desc(DZ1_MN, dz1 + k * 16 * 32),
-                                       ID_WG1, (it | k) != 0);
-                tc::mma_commit(&mma2_done);
+                        tc::mma_f16_ss_pred(tmem + TM_W1 + ty * 16, tc::smem_desc(XS_MN, xs + (ty * XS_W + k * 16) * 16), tc::smem_desc(DZ1_MN, dz1 + k * 16 * 32),
+                                       ID_WG1, (it | k) != 0, leader);
+                tc::mma_commit_pred(&mma2_done, leader);
             }
         }
     } else {

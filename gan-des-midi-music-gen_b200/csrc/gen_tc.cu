@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
     const uint32_t tmem = tmem_s;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::tma_prefetch_desc(&map_w);
             int it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);
             const uint32_t idesc = tc::idesc_bf16(128, (uint32_t)a.NG);
             const uint32_t a_addr = tc::smem_u32(smem_a), w_addr = tc::smem_u32(smem_w);

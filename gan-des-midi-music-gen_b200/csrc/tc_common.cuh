@@ -73,6 +73,23 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (ptxas then knows the guarded region runs in exactly one thread)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Warp-uniform issue: the WHOLE warp runs the issue loop (descriptors stay in uniform registers; under an `if (lane == 0)`
+// ptxas wraps every UTCHMMA in an ELECT / R2UR uniformisation loop of ~13 dependent instructions, which makes small-N MMA
+// streams issue-bound), and only the instruction itself is predicated on `issue` (1 in exactly one lane).
+__device__ __forceinline__ void mma_f16_ss_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t issue) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(issue) : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
