@@ -15,6 +15,7 @@
 // HBM per sample and pass: 110 KB read (the unfused chain: 382 KB read + 137 KB written).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 struct FusedBwdArgs {
     const float* dlogit; const float* wfcp;
     float* dw1; float* db1; float* dw2; float* db2; float* dwfc; float* dbfc;
-    int B;
+    int B; int dbg_skip;      // dbg_skip (env MMG_DBG_SKIP, timing experiments only): bit0 conv2 wgrad, bit1 conv2 dgrad, bit2 conv1 wgrad MMAs are not issued
 };
 
 __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_xs, const __grid_constant__ CUtensorMap map_p1,
@@ -131,13 +132,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                 tc::mbar_wait(&full_p1, ph);
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ty = 0; ty < 2; ++ty)
+                for (int ty = 0; ty < 2 && !(a.dbg_skip & 1); ++ty)
 #pragma unroll 9
                     for (int k = 0; k < K2_STEPS; ++k)
                         tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
                                        ID_WG2, (it | k) != 0, leader);
 #pragma unroll
-                for (int tile = 0; tile < 4; ++tile)
+                for (int tile = 0; tile < 4 && !(a.dbg_skip & 2); ++tile)
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                 tc::mbar_wait(&full_xs, ph);
                 tc::tc_fence_after();
 #pragma unroll
-                for (int ty = 0; ty < 2; ++ty)
+                for (int ty = 0; ty < 2 && !(a.dbg_skip & 4); ++ty)
 #pragma unroll 8
                     for (int k = 0; k < K1_STEPS; ++k)
                         tc::mma_f16_ss_pred(tmem + TM_W1 + ty * 16, tc::smem_desc(XS_MN, xs + (ty * XS_W + k * 16) * 16), tc::smem_desc(DZ1_MN, dz1 + k * 16 * 32),
@@ -174,11 +175,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
             for (int tile = 0; tile < 4; ++tile) tmem_st_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, zr);
             tmem_st_wait();
         }
-        unsigned char* dz2s = smem + SM_DZ2 + 1024;
+        const uint32_t dz2s = tc::smem_u32(smem + SM_DZ2) + 1024, p1s = tc::smem_u32(smem + SM_P1), dz1s = tc::smem_u32(smem + SM_DZ1);
+        // fc.weight slice of this thread's rows (the same rows for every sample): loaded once, kept in registers
+        float wreg[4][16];
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) {
+            const int R = tile * 128 + tl;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 w = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32 + h * 16)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                wreg[tile][4 * c4] = w.x; wreg[tile][4 * c4 + 1] = w.y; wreg[tile][4 * c4 + 2] = w.z; wreg[tile][4 * c4 + 3] = w.w;
+            }
+        }
+        float dl_next = n_my > 0 ? a.dlogit[blockIdx.x] : 0.f;
         for (int it = 0; it < n_my; ++it) {
-            const int b = blockIdx.x + it * gridDim.x;
             const uint32_t ph = (uint32_t)(it & 1);
-            const float dl = a.dlogit[b];
+            const float dl = dl_next;
+            if (it + 1 < n_my) dl_next = a.dlogit[blockIdx.x + (it + 1) * gridDim.x];      // in flight behind this sample's work
             if (threadIdx.x == 64) dbfc += dl;
             // ---- W1: A2 -> DZ2 in place, fc.weight / conv2.bias gradients
             tc::mbar_wait(&full_a2, ph);
@@ -186,19 +199,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
             for (int tile = 0; tile < 4; ++tile) {
                 const int R = tile * 128 + tl;
                 if (tile * 128 + q * 32 >= A2_LOAD_ROWS) continue;    // warp-uniform: this warp's 32 rows are all beyond the loaded rows
-                const bool real = R < P1_ROWS, loaded = R < A2_LOAD_ROWS;
-                unsigned char* rowp = dz2s + (loaded ? R : 0) * 64;
+                const bool loaded = R < A2_LOAD_ROWS;                 // rows 429..431 (the next sample's A2) have w = 0 -> they are zeroed
+                const uint32_t rowp = dz2s + (loaded ? R : 0) * 64;
                 const int sw = (R >> 1) & 3;
-                uint4* c0p = reinterpret_cast<uint4*>(rowp + (((2 * h) ^ sw) << 4));
-                uint4* c1p = reinterpret_cast<uint4*>(rowp + (((2 * h + 1) ^ sw) << 4));
-                uint4 av0 = make_uint4(0, 0, 0, 0), av1 = av0;
-                float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;
-                if (real) {
-                    av0 = *c0p; av1 = *c1p;
-                    const float4* wp = reinterpret_cast<const float4*>(a.wfcp + R * 32 + h * 16);
-                    w0 = wp[0]; w1 = wp[1]; w2 = wp[2]; w3 = wp[3];
-                }
-                const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+                const uint32_t c0p = rowp + (((2 * h) ^ sw) << 4), c1p = rowp + (((2 * h + 1) ^ sw) << 4);
+                const uint4 av0 = tc::lds128(c0p), av1 = tc::lds128(c1p);
                 const uint32_t au[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
                 uint32_t acc[16], o[8];
                 tc::tmem_ld_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, acc);    // .sync.aligned: every lane of the warp takes part
@@ -206,16 +211,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float x0 = bf_lo(au[j]), x1 = bf_hi(au[j]);
-                    const float g0 = dl * w[2 * j] * (x0 > 0.f ? 1.f : 0.2f), g1 = dl * w[2 * j + 1] * (x1 > 0.f ? 1.f : 0.2f);
-                    o[j] = pack_bf16x2(g0, g1);                        // rows 429..431 (next sample's A2) get w = 0, a = 0 -> zeros
+                    const float g0 = dl * wreg[tile][2 * j] * (x0 > 0.f ? 1.f : 0.2f), g1 = dl * wreg[tile][2 * j + 1] * (x1 > 0.f ? 1.f : 0.2f);
+                    o[j] = pack_bf16x2(g0, g1);
                     db2[2 * j] += bf_lo(o[j]); db2[2 * j + 1] += bf_hi(o[j]);          // what the MMAs will read
-                    acc[2 * j] = __float_as_uint(fmaf(dl, x0, __uint_as_float(acc[2 * j])));
-                    acc[2 * j + 1] = __float_as_uint(fmaf(dl, x1, __uint_as_float(acc[2 * j + 1])));
+                    const bool real = R < P1_ROWS;
+                    acc[2 * j] = __float_as_uint(fmaf(dl, real ? x0 : 0.f, __uint_as_float(acc[2 * j])));
+                    acc[2 * j + 1] = __float_as_uint(fmaf(dl, real ? x1 : 0.f, __uint_as_float(acc[2 * j + 1])));
                 }
                 tmem_st_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, acc);
                 if (loaded) {
-                    *c0p = make_uint4(o[0], o[1], o[2], o[3]);
-                    *c1p = make_uint4(o[4], o[5], o[6], o[7]);
+                    tc::sts128(c0p, make_uint4(o[0], o[1], o[2], o[3]));
+                    tc::sts128(c1p, make_uint4(o[4], o[5], o[6], o[7]));
                 }
             }
             tmem_st_wait();
@@ -235,18 +241,18 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                 const int sy = R / P1_W, sx = R - sy * P1_W;
                 const int oy = 2 * sy + h - 1;
                 if (oy < 0 || oy >= 64) continue;                     // zero-padding cells of P1: no conv1 output behind them
-                const unsigned char* prow = smem + SM_P1 + R * 128;
+                const uint32_t prow = p1s + R * 128;
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const int ox = 2 * sx + dx - 1;
                     if (ox < 0 || ox >= 25) continue;
                     const int m = oy * XS_W + ox;
-                    unsigned char* drow = smem + SM_DZ1 + m * 32;
+                    const uint32_t drow = dz1s + m * 32;
                     const int sw1 = (m >> 2) & 1;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {                  // 8 channels per 16-byte chunk
                         const int pc = (h * 2 + dx) * 2 + hh;
-                        const uint4 av = *reinterpret_cast<const uint4*>(prow + ((pc ^ (R & 7)) << 4));
+                        const uint4 av = tc::lds128(prow + ((pc ^ (R & 7)) << 4));
                         const uint32_t au[4] = {av.x, av.y, av.z, av.w};
                         uint32_t o[4];
 #pragma unroll
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                             db1[hh * 8 + 2 * j] += bf_lo(o[j]);
                             db1[hh * 8 + 2 * j + 1] += bf_hi(o[j]);
                         }
-                        *reinterpret_cast<uint4*>(drow + ((hh ^ sw1) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        tc::sts128(drow + ((hh ^ sw1) << 4), make_uint4(o[0], o[1], o[2], o[3]));
                     }
                 }
             }
@@ -345,6 +351,7 @@ int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const flo
     FusedBwdArgs a;
     a.dlogit = dlogit; a.wfcp = (const float*)(pk + 2048 + 32768);
     a.dw1 = dconv1_w; a.db1 = dconv1_b; a.dw2 = dconv2_w; a.db2 = dconv2_b; a.dwfc = dfc_w; a.dbfc = dfc_b; a.B = (int)B;
+    { const char* e = getenv("MMG_DBG_SKIP"); a.dbg_skip = e ? atoi(e) : 0; }
     const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
     MMG_CUDA(cudaFuncSetAttribute(disc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
     disc_bwd_fused_kernel<<<grid, FB_THREADS, SM_TOTAL + 1024, (cudaStream_t)stream>>>(map_xs, map_p1, map_a2, map_w, a);

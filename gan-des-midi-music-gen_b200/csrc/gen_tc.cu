@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             const long long row = (long long)rt * 128 + t;
             const bool live = row < a.M;
             for (int c = 0; c < kchunks; ++c) {
-                unsigned char* dst = smem_a + c * GT_A_CHUNK + t * 128;
+                const uint32_t dst = tc::smem_u32(smem_a) + c * GT_A_CHUNK + t * 128;
                 float v[64];                                       // all of the chunk's loads are issued before any is used
                 if (a.in_mode == 0) {
 #pragma unroll
@@ -197,9 +197,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(dst + ((j ^ (t & 7)) << 4)) =
-                        make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
-                                   pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                    tc::sts128(dst + ((j ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&aready);
@@ -274,7 +273,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                     for (int e = 0; e < 32; ++e) y[e] = fast_sigmoid_affine(__uint_as_float(r[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stg + t * 128 + ((j ^ (t & 7)) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                        tc::sts128(tc::smem_u32(stg) + t * 128 + ((j ^ (t & 7)) << 4), make_uint4(__float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
+                                                                                               __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3])));
                     tc::fence_proxy_async_smem();
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
