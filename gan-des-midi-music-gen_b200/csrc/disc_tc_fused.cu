@@ -373,3 +373,267 @@ int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const flo
 }
 
 }  // extern "C"
+
+// ================================================================================================================
+// Fused forward of the bf16 tensor-core discriminator (DiscriminatorCNN.forward, network_tests.py:156-160): ONE persistent
+// kernel per pass instead of xs_pack + conv1_fwd + conv2_fwd.  A CTA walks over whole samples:
+//   S1  workers   X (u8 staged through shared memory by a bulk copy, or fp32 read directly) -> XS rows in shared memory (+ global, for the backward)
+//   S2  tcgen05   conv1: 14 row tiles x 2 taps (M128 x N16 x K16) -> 224 TMEM columns
+//   S3  workers   bias + LeakyReLU -> bf16 -> P1 super-pixel rows in shared memory (128-byte swizzle); one TMA store sends P1 to global
+//   S4  tcgen05   conv2: 4 row tiles x 4 taps x 4 K steps (M128 x N32 x K16), tap-shifted descriptors over the SAME P1 rows
+//   S5  workers   bias + LeakyReLU -> A2 rows to global; fc partial dots reduced per sample -> logits[b] (with the fc bias; no atomics)
+// P1 never makes the HBM round trip between conv1 and conv2.  HBM per sample: 12.8 KB read, 110 KB written (what the backward reads).
+// ================================================================================================================
+namespace {
+
+constexpr int FF_XS_ROWS = 1824;                  // 14 tiles x 128 + 27 halo rows, padded
+constexpr int FS_XS = 0;                          // 29184 -> 29696
+constexpr int FS_P1 = 29696;                      // 528 rows x 128 B (rows >= 429 stay zero)   67584
+constexpr int FS_W2 = FS_P1 + 67584;              // [4 t][32 oc][64 k] bf16 SW128              16384
+constexpr int FS_W1 = FS_W2 + 16384;              // [2 ty][16 oc][16 k] bf16 SW32              1024
+constexpr int FS_X = FS_W1 + 1024;                // staged u8 input                            12800
+constexpr int FS_TOTAL = FS_X + 12800;            // 127488
+constexpr uint32_t TF_C1 = 0, TF_C2 = 256;        // TMEM: conv1 14 x 16 columns, conv2 4 x 32 columns
+
+struct FusedFwdArgs {
+    const void* x; int x_f32;
+    const float* b1; const float* b2; const float* wfcp; const float* bfc;
+    __nv_bfloat16* xs; __nv_bfloat16* a2; float* logits;
+    int B;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                                                                       const __grid_constant__ CUtensorMap map_p1a, const __grid_constant__ CUtensorMap map_p1b,
+                                                                       const FusedFwdArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t x_full, x_empty, xs_ready, c1_done, p1_ready, c2_done, wbar;
+    __shared__ uint32_t tmem_s;
+    __shared__ float logit_s;
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = a.B > (int)blockIdx.x ? (a.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&x_full, 1); tc::mbar_init(&wbar, 1); tc::mbar_init(&c1_done, 1); tc::mbar_init(&c2_done, 1);
+        tc::mbar_init(&x_empty, FB_WORKERS); tc::mbar_init(&xs_ready, FB_WORKERS); tc::mbar_init(&p1_ready, FB_WORKERS);
+        tc::fence_barrier_init();
+        logit_s = 0.f;
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
+    {   // XS halo rows and P1 pad cells / tail rows are never written: they must read as zeros
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < FS_W2 / 16; i += FB_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_s;
+
+    if (warp == 0) {
+        if (lane == 0 && n_my > 0) {
+            tc::mbar_expect_tx(&wbar, 16384 + 1024);
+            tc::tma_load_2d(smem + FS_W2, &map_w2, &wbar, 0, 0);
+            tc::tma_load_2d(smem + FS_W1, &map_w1, &wbar, 0, 0);
+            if (!a.x_f32) {
+                for (int it = 0; it < n_my; ++it) {
+                    const int b = blockIdx.x + it * gridDim.x;
+                    if (it > 0) tc::mbar_wait(&x_empty, (uint32_t)((it - 1) & 1));
+                    tc::mbar_expect_tx(&x_full, 12800);
+                    bulk_load_1d(smem + FS_X, (const unsigned char*)a.x + (size_t)b * 12800, 12800, &x_full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (n_my > 0 && tc::elect_one()) {
+            constexpr uint64_t XS_K = tc::smem_desc_base(16, 128, tc::SW_NONE);      // conv1 A: K chunk 1 = the next 16-byte row
+            constexpr uint64_t W1_K = tc::smem_desc_base(0, 256, tc::SW_32B);
+            constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);     // conv2 A (P1 rows) and B (W2p)
+            constexpr uint32_t ID_C1 = tc::idesc_bf16(128, 16), ID_C2 = tc::idesc_bf16(128, 32);
+            const uint32_t xs = tc::smem_u32(smem + FS_XS), p1 = tc::smem_u32(smem + FS_P1), w1 = tc::smem_u32(smem + FS_W1), w2 = tc::smem_u32(smem + FS_W2);
+            tc::mbar_wait(&wbar, 0);
+            for (int it = 0; it < n_my; ++it) {
+                const uint32_t ph = (uint32_t)(it & 1);
+                tc::mbar_wait(&xs_ready, ph);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int tile = 0; tile < 14; ++tile)
+#pragma unroll
+                    for (int ty = 0; ty < 2; ++ty)
+                        tc::mma_f16_ss(tmem + TF_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512), ID_C1, ty != 0);
+                tc::mma_commit(&c1_done);
+                tc::mbar_wait(&p1_ready, ph);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int tile = 0; tile < 4; ++tile)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc::mma_f16_ss(tmem + TF_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
+                                           tc::smem_desc(KM128, w2 + t * 4096 + k * 32), ID_C2, (t | k) != 0);
+                tc::mma_commit(&c2_done);
+            }
+        }
+    } else {
+        const int q = warp & 3, h = (warp - 2) >> 2, tl = q * 32 + lane, w = threadIdx.x - 64;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const uint32_t xs_s = tc::smem_u32(smem + FS_XS), p1_s = tc::smem_u32(smem + FS_P1), x_s = tc::smem_u32(smem + FS_X);
+        float b1r[16], b2r[16], wreg[4][16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { b1r[c] = a.b1[c]; b2r[c] = a.b2[h * 16 + c]; }
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) {                        // fc.weight slice of this thread's rows (junk rows carry 0)
+            const int R = tile * 128 + tl;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 v = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32 + h * 16)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                wreg[tile][4 * c4] = v.x; wreg[tile][4 * c4 + 1] = v.y; wreg[tile][4 * c4 + 2] = v.z; wreg[tile][4 * c4 + 3] = v.w;
+            }
+        }
+        const float bfc = a.bfc[0];
+        // ---- S1: XS rows (8 values = (dy,dx,ch) of super pixel (sy,sx) of the zero-padded input), to shared memory and to global
+        auto build_xs = [&](int it) {
+            const int b = blockIdx.x + it * gridDim.x;
+            if (!a.x_f32) tc::mbar_wait(&x_full, (uint32_t)(it & 1));
+            for (int rr = w; rr < XS_ROWS; rr += FB_WORKERS) {
+                const int sy = rr / XS_W, sx = rr - sy * XS_W;
+                const int iy0 = 2 * sy - 1, ix0 = 2 * sx - 1, off0 = iy0 * 50 + ix0;      // element (dy,dx,ch) sits at off0 + dy*50 + dx + ch*6400
+                const bool y0 = iy0 >= 0, y1 = iy0 + 1 < 128, x0 = ix0 >= 0, x1 = ix0 + 1 < 50;
+                uint32_t u[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int dy = e >> 2, dx = (e >> 1) & 1, ch = e & 1;
+                    const bool in = (dy ? y1 : y0) && (dx ? x1 : x0);
+                    const int off = off0 + dy * 50 + dx + ch * 6400;
+                    float v;
+                    if (a.x_f32) v = in ? reinterpret_cast<const float*>(a.x)[(size_t)b * 12800 + off] : 0.f;
+                    else v = (float)(in ? tc::lds_u8(x_s + off) : 0u);
+                    u[e] = __float_as_uint(v);
+                }
+                uint4 pk;
+                if (a.x_f32) pk = make_uint4(pack_bf16x2(__uint_as_float(u[0]), __uint_as_float(u[1])), pack_bf16x2(__uint_as_float(u[2]), __uint_as_float(u[3])),
+                                             pack_bf16x2(__uint_as_float(u[4]), __uint_as_float(u[5])), pack_bf16x2(__uint_as_float(u[6]), __uint_as_float(u[7])));
+                else         // integers 0..255 are exact in bf16: the packed pair is just the two high halves
+                    pk = make_uint4(__byte_perm(u[0], u[1], 0x7632), __byte_perm(u[2], u[3], 0x7632), __byte_perm(u[4], u[5], 0x7632), __byte_perm(u[6], u[7], 0x7632));
+                tc::sts128(xs_s + rr * 16, pk);
+                *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&xs_ready);
+            tc::mbar_arrive(&x_empty);
+        };
+        if (n_my > 0) build_xs(0);
+        for (int it = 0; it < n_my; ++it) {
+            const int b = blockIdx.x + it * gridDim.x;
+            const uint32_t ph = (uint32_t)(it & 1);
+            // ---- S3: conv1 epilogue -> P1 (rows = super pixels, 64 values = (dy,dx,c16)); even tiles for h = 0, odd tiles for h = 1
+            tc::mbar_wait(&c1_done, ph);
+            tc::tc_fence_after();
+            if (w == 0) tc::bulk_wait_group_read<0>();                // the previous sample's P1 store has finished reading shared memory
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int tt = 0; tt < 7; ++tt) {
+                const int tile = 2 * tt + h;
+                uint32_t r[16];
+                tc::tmem_ld_32x16(tmem + tlane + TF_C1 + tile * 16, r);
+                tc::tmem_ld_wait();
+                const int m = tile * 128 + tl, oy = m / XS_W, ox = m - oy * XS_W;
+                if (m < XS_ROWS && oy < 64 && ox < 25) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float z0 = __uint_as_float(r[2 * c]) + b1r[2 * c], z1 = __uint_as_float(r[2 * c + 1]) + b1r[2 * c + 1];
+                        o[c] = pack_bf16x2(z0 > 0.f ? z0 : 0.2f * z0, z1 > 0.f ? z1 : 0.2f * z1);
+                    }
+                    const int yp = oy + 1, xp = ox + 1, R = (yp >> 1) * P1_W + (xp >> 1), cell = (yp & 1) * 2 + (xp & 1);
+                    const uint32_t rowp = p1_s + R * 128;
+                    tc::sts128(rowp + (((2 * cell) ^ (R & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                    tc::sts128(rowp + (((2 * cell + 1) ^ (R & 7)) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                }
+            }
+            tc::tc_fence_before();
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&p1_ready);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (w == 0) {                                             // P1 -> global for the backward (rows b*429 .. +429, two boxes)
+                tc::tma_store_2d(&map_p1a, smem + FS_P1, 0, b * P1_ROWS);
+                tc::tma_store_2d(&map_p1b, smem + FS_P1 + 224 * 128, 0, b * P1_ROWS + 224);
+                tc::bulk_commit_group();
+            }
+            if (it + 1 < n_my) build_xs(it + 1);                      // conv1 of this sample is done with XS: the next sample's rows are built under conv2's MMAs
+            // ---- S5: conv2 epilogue -> A2 rows (global), fc partial dot
+            tc::mbar_wait(&c2_done, ph);
+            tc::tc_fence_after();
+            float dot = 0.f;
+#pragma unroll
+            for (int tile = 0; tile < 4; ++tile) {
+                const int R = tile * 128 + tl;
+                uint32_t r[16];
+                tc::tmem_ld_32x16(tmem + tlane + TF_C2 + tile * 32 + h * 16, r);
+                tc::tmem_ld_wait();
+                if (R >= P1_ROWS) continue;
+                const int oy = R / P1_W, ox = R - oy * P1_W;
+                const bool real = oy < 32 && ox < 12;                 // junk rows of the row space are stored as zeros
+                uint32_t o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float z0 = __uint_as_float(r[2 * c]) + b2r[2 * c], z1 = __uint_as_float(r[2 * c + 1]) + b2r[2 * c + 1];
+                    z0 = z0 > 0.f ? z0 : 0.2f * z0; z1 = z1 > 0.f ? z1 : 0.2f * z1;
+                    o[c] = real ? pack_bf16x2(z0, z1) : 0u;
+                    dot = fmaf(bf_lo(o[c]), wreg[tile][2 * c], dot);                      // the bf16 values the backward will read
+                    dot = fmaf(bf_hi(o[c]), wreg[tile][2 * c + 1], dot);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(a.a2 + ((size_t)b * P1_ROWS + R) * 32 + h * 16);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            dot = warp_sum(dot);
+            if (lane == 0) atomicAdd(&logit_s, dot);
+            tc::tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (w == 0) { a.logits[b] = logit_s + bfc; logit_s = 0.f; }
+            // (the next use of logit_s comes after the next sample's two bar.sync: ordered)
+        }
+        if (w == 0) tc::bulk_wait_group_read<0>();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" {
+
+// x (B,2,128,50) uint8 (x_dtype 2) or float32 (x_dtype 0) -> xs (B*1690,8), p1 (B*429,64), a2 (B*429,32) bf16 and logits (B,) fp32
+// (fc bias included; nothing needs to be pre-initialised).
+int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b, void* xs, void* p1,
+                       void* a2, float* logits, int64_t B, void* stream) {
+    MMG_REQUIRE(x && packed && conv1_b && conv2_b && fc_b && xs && p1 && a2 && logits && B >= 0, MMG_EINVAL, "disc_fwd_fused: bad arguments");
+    MMG_REQUIRE(x_dtype == 0 || x_dtype == 2, MMG_EINVAL, "disc_fwd_fused: x_dtype must be 0 (f32) or 2 (u8)");
+    if (B == 0) return MMG_OK;
+    MMG_REQUIRE(B * XS_ROWS < (1LL << 31) - 4096, MMG_EUNSUPPORTED, "disc_fwd_fused: batch too large");
+    MMG_REQUIRE(x_dtype != 2 || ((uintptr_t)x & 15) == 0, MMG_EINVAL, "disc_fwd_fused: x must be 16-byte aligned");
+    const unsigned char* pk = (const unsigned char*)packed;
+    CUtensorMap map_w1, map_w2, map_p1a, map_p1b;
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_w1, pk, 16, 32, 32, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (w1b)");
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_w2, pk + 2048, 64, 128, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (w2p)");
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_p1a, p1, 64, (uint64_t)(B * P1_ROWS), 128, 64, 224, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (p1 a)");
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_p1b, p1, 64, (uint64_t)(B * P1_ROWS), 128, 64, 205, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (p1 b)");
+    FusedFwdArgs a;
+    a.x = x; a.x_f32 = x_dtype == 0; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
+    a.xs = (__nv_bfloat16*)xs; a.a2 = (__nv_bfloat16*)a2; a.logits = logits; a.B = (int)B;
+    const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
+    MMG_CUDA(cudaFuncSetAttribute(disc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_TOTAL + 1024));
+    disc_fwd_fused_kernel<<<grid, FB_THREADS, FS_TOTAL + 1024, (cudaStream_t)stream>>>(map_w1, map_w2, map_p1a, map_p1b, a);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+}  // extern "C"

@@ -15,8 +15,8 @@ _XD = {torch.float32: 0, torch.uint8: 2}
 
 
 class DiscTC:
-    def __init__(self, disc, max_batch, roll_size=(2, 128, 50), fused_backward=True):
-        self.fused_backward = fused_backward
+    def __init__(self, disc, max_batch, roll_size=(2, 128, 50), fused_backward=True, fused_forward=True):
+        self.fused_backward, self.fused_forward = fused_backward, fused_forward
         if tuple(roll_size) != (2, 128, 50) or disc.conv1.weight.shape != (16, 2, 4, 4) or disc.conv2.weight.shape != (32, 16, 4, 4):
             raise ValueError("the tensor-core discriminator path is specialised to roll_size (2,128,50), hidden_dim 16")
         self.d = disc
@@ -48,6 +48,11 @@ class DiscTC:
         x = x.contiguous()
         d, s = self.d, N.stream()
         logits = self.logits[:B]
+        if self.fused_forward:       # one persistent kernel: P1 stays in shared memory between conv1 and conv2 (csrc/disc_tc_fused.cu)
+            N.call("mmg_disc_fwd_fused", N.ptr(x), _XD[x.dtype], N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data),
+                   N.ptr(d.fc.bias.data), N.ptr(self.xs), N.ptr(self.p1), N.ptr(self.a2), N.ptr(logits), B, s)
+            self.x, self.B = x, B
+            return logits
         N.call("mmg_fill_scalar_f32", N.ptr(logits), N.ptr(d.fc.bias.data), B, s)
         N.call("mmg_disc_xs_pack", N.ptr(x), _XD[x.dtype], N.ptr(self.xs), B, s)
         N.call("mmg_disc_conv1_fwd", N.ptr(self.xs), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(self.p1), B, s)

@@ -117,6 +117,11 @@ int mmg_disc_conv1_wgrad(const void* xs, const void* dz1c, float* dconv1_w, int6
 int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const float* dlogit, const void* packed, float* dconv1_w,
                        float* dconv1_b, float* dconv2_w, float* dconv2_b, float* dfc_w, float* dfc_b, int64_t B, void* stream);
 
+/* The whole forward of one pass in ONE persistent kernel (csrc/disc_tc_fused.cu): xs_pack + conv1_fwd + conv2_fwd with P1 kept in
+ * shared memory between the two convolutions; writes xs / p1 / a2 for the backward and logits (fc bias included). */
+int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
+                       void* xs, void* p1, void* a2, float* logits, int64_t B, void* stream);
+
 /* ---- bf16 tensor-core generator blocks ([Linear -> BatchNorm1d -> Sigmoid], network_tests.py:75-80, as used by Generator
  * :58-90 and BeatGenerator :93-123) ----
  * One call = one Linear layer as a tcgen05 GEMM (bf16 operands, fp32 accumulate) with the neighbouring BatchNorm + sigmoid

@@ -37,7 +37,7 @@ def test_disc_tc_stages(B, dtype, fused):
     sd = mo.synth_state(mo.mmgan_shapes(), seed=31, d_scale=0.25)
     D = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
     D.load_state_dict({k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")})
-    tc = DiscTC(D, max_batch=B + 2, fused_backward=fused)
+    tc = DiscTC(D, max_batch=B + 2, fused_backward=fused, fused_forward=fused)
     x8 = torch.from_numpy(mo.synth_rolls(B, 50, seed=32, p=0.05)).to(DEV)
     x = x8 if dtype == torch.uint8 else x8.float()
     logits = tc.forward(x).clone()
