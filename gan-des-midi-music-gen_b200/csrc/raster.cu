@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const doubl
     }
     double t = 0.0;
     int st = 0, count = 0;
+    unsigned bigvel = 0;                                           // any kept note with velocity > 127 (does not fit K2's packed shared-memory record)
     for (int64_t i0 = 0; i0 < n; i0 += K1_CH) {
         uint32_t cm[K1_CJ];
 #pragma unroll
@@ -256,13 +257,14 @@ __global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const doubl
             const bool k = ((keep >> j) & 1u) && (lane + 32 * j < lim);
             const unsigned km = __ballot_sync(0xffffffffu, k);
             if (k) nout[count + __popc(km & lt_mask)] = rec[j];
+            bigvel |= __ballot_sync(0xffffffffu, k && (rec[j] >> 31));
             count += __popc(km);
         }
         if (first_halt < K1_CH) break;
         __syncwarp();
     }
     if (lane == 0) {
-        note_count[song] = count;
+        note_count[song] = count | (bigvel ? 0x40000000 : 0);
         if (status) status[song] = st;
     }
 }
@@ -279,8 +281,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const doubl
 // Every cell is therefore written at most once after the CTA's zero fill (which stays in L2 for the few microseconds in
 // between: HBM sees each output line once).
 // ------------------------------------------------------------------------------------------------
-constexpr int K2_THREADS = 256;
+constexpr int K2_THREADS = 128;
 constexpr int K2_WARPS = K2_THREADS / 32;
+constexpr int K2_CAP = 6656;                  // notes whose sorted copy fits shared memory (3 bytes each: 19.5 KB -> 9+ CTAs per SM, every song of a
+                                              // MAESTRO-scale batch resident at once); longer songs sort through the global workspace instead
 
 template <typename OutT>
 __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t* __restrict__ notes, uint32_t* __restrict__ sorted,
@@ -289,36 +293,58 @@ __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t*
     __shared__ int hist[K2_WARPS][128];          // per-warp-segment pitch histogram, then running scatter base
     __shared__ int pstart[129];
     __shared__ int wsum[4];
+    __shared__ uint16_t s_step[K2_CAP];          // sorted notes, shared-memory form: step | (off | velocity << 1)
+    __shared__ uint8_t s_ov[K2_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~lt_mask & ~(1u << lane);
     const int64_t song = blockIdx.x;
     const uint32_t* nin = notes + offsets[song];
     uint32_t* srt = sorted + offsets[song];
-    const int n = note_count[song];
+    const int nc = note_count[song];
+    const int n = nc & 0x3fffffff;
+    const bool in_smem = n <= K2_CAP && !(nc & 0x40000000);
+    auto put = [&](int pos, uint32_t r) {
+        if (in_smem) { s_step[pos] = (uint16_t)r; s_ov[pos] = (uint8_t)(((r >> 16) & 1u) | ((r >> 24) << 1)); }
+        else srt[pos] = r;
+    };
+    auto get = [&](int pos) -> uint32_t {
+        if (in_smem) { const uint32_t ov = s_ov[pos]; return (uint32_t)s_step[pos] | ((ov & 1u) << 16) | ((ov >> 1) << 24); }
+        return srt[pos];
+    };
     const int Wo = hi - lo;
     OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
     OutT* __restrict__ odur = oroll + (size_t)128 * Wo;
-    {   // zero fill (2*128*Wo*sizeof(OutT) bytes, a multiple of 16; 16-byte aligned)
+    // Zero fill.  When 8 rows are a multiple of 16 bytes the fill is done LATER, 8 pitch rows at a time by the warp that replays those
+    // pitches right afterwards, so the few cells the notes overwrite are still in L2 (a whole-song fill up front is evicted before the
+    // replay gets to it: every touched line then costs a DRAM read-modify-write).
+    const bool late_fill = ((size_t)8 * Wo * sizeof(OutT)) % 16 == 0;
+    if (!late_fill) {   // 2*128*Wo*sizeof(OutT) bytes, a multiple of 16; 16-byte aligned
         uint4* z = reinterpret_cast<uint4*>(oroll);
         const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);
         for (int i = tid; i < cnt; i += K2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     for (int i = tid; i < K2_WARPS * 128; i += K2_THREADS) (&hist[0][0])[i] = 0;
     __syncthreads();
-    // 1. histogram of this warp's contiguous segment (multiple of 32 notes)
+    // 1. histogram of this warp's contiguous segment (multiple of 32 notes); 4 groups of loads in flight
     const int seg = ((n + K2_WARPS * 32 - 1) / (K2_WARPS * 32)) * 32;
     const int s_lo = warp * seg, s_hi = min(n, s_lo + seg);
-    for (int i0 = s_lo; i0 < s_hi; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < s_hi;
-        const int p = valid ? (int)((nin[i] >> 17) & 0x7Fu) : 128 + lane;
-        const unsigned grp = __match_any_sync(0xffffffffu, p);
-        if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
-        __syncwarp();
+    for (int i0 = s_lo; i0 < s_hi; i0 += 128) {
+        uint32_t rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u + lane; rr[u] = i < s_hi ? nin[i] : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= s_hi) break;
+            const bool valid = i0 + 32 * u + lane < s_hi;
+            const int p = valid ? (int)((rr[u] >> 17) & 0x7Fu) : 128 + lane;
+            const unsigned grp = __match_any_sync(0xffffffffu, p);
+            if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
+            __syncwarp();
+        }
     }
     __syncthreads();
     // 2. pitch offsets (exclusive scan over 128 pitches) and per-segment bases
-    if (tid < 128) {
+    {
         int tot = 0;
 #pragma unroll
         for (int w = 0; w < K2_WARPS; ++w) tot += hist[w][tid];
@@ -326,8 +352,7 @@ __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t*
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
         if (lane == 31) wsum[warp] = inc;
-        __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __syncthreads();
         int base = inc - tot;
         for (int w = 0; w < warp; ++w) base += wsum[w];
         pstart[tid] = base;
@@ -337,23 +362,34 @@ __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t*
     }
     __syncthreads();
     // 3. stable scatter (each warp in message order over its own segment)
-    for (int i0 = s_lo; i0 < s_hi; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < s_hi;
-        const uint32_t r = valid ? nin[i] : 0u;
-        const int p = valid ? (int)((r >> 17) & 0x7Fu) : 128 + lane;
-        const unsigned grp = __match_any_sync(0xffffffffu, p);
-        if (valid) {
-            const int b = hist[warp][p];
-            srt[b + __popc(grp & lt_mask)] = r;
+    for (int i0 = s_lo; i0 < s_hi; i0 += 128) {
+        uint32_t rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u + lane; rr[u] = i < s_hi ? nin[i] : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= s_hi) break;
+            const bool valid = i0 + 32 * u + lane < s_hi;
+            const uint32_t r = rr[u];
+            const int p = valid ? (int)((r >> 17) & 0x7Fu) : 128 + lane;
+            const unsigned grp = __match_any_sync(0xffffffffu, p);
+            if (valid) put(hist[warp][p] + __popc(grp & lt_mask), r);
+            __syncwarp();
+            if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
+            __syncwarp();
         }
-        __syncwarp();
-        if (valid && !(grp & lt_mask)) hist[warp][p] += __popc(grp);
-        __syncwarp();
     }
-    __syncthreads();            // zero fill and sorted[] are visible to the whole CTA
+    __syncthreads();            // zero fill and the sorted notes are visible to the whole CTA
     // 4. per-pitch replay, one warp per pitch, 32 notes at a time with the unresolved last on / off carried forward
-    for (int p = warp; p < 128; p += K2_WARPS) {
+    for (int pi = 0; pi < 128 / K2_WARPS; ++pi) {
+        const int p = ((pi >> 3) * K2_WARPS + warp) * 8 + (pi & 7);     // blocks of 8 consecutive pitches, dealt round-robin to the warps
+        if (late_fill && (pi & 7) == 0) {
+            const int cnt = (int)((size_t)8 * Wo * sizeof(OutT) / 16);
+            uint4* z0 = reinterpret_cast<uint4*>(oroll + (size_t)p * Wo);
+            uint4* z1 = reinterpret_cast<uint4*>(odur + (size_t)p * Wo);
+            for (int i = lane; i < cnt; i += 32) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+            __syncwarp();
+        }
         const int b0 = pstart[p], b1 = pstart[p + 1];
         if (b0 == b1) continue;
         OutT* rrow = oroll + (size_t)p * Wo - lo;
@@ -364,7 +400,7 @@ __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t*
         for (int i0 = b0; i0 < b1; i0 += 32) {
             const int i = i0 + lane;
             const bool valid = i < b1;
-            const uint32_t r = valid ? srt[i] : 0u;
+            const uint32_t r = valid ? get(i) : 0u;
             const int s = (int)(r & 0xFFFFu);
             const bool is_off = valid && ((r >> 16) & 1u), is_on = valid && !((r >> 16) & 1u);
             const unsigned onm = __ballot_sync(0xffffffffu, is_on), offm = __ballot_sync(0xffffffffu, is_off);
