@@ -24,6 +24,18 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+// contiguous shared -> global copy in the async proxy (bulk group of the issuing thread)
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t saddr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
