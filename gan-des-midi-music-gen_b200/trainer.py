@@ -244,28 +244,50 @@ class HostBatchPipeline:
     ``MMGANTrainer.step`` with the H2D copies of batch i+1 running on a copy stream underneath the compute of
     batch i (double-buffered device staging; SURVEY 8f-1: network_tests.py:192-193 does B small blocking copies).
     Every batch is copied exactly once; the two losses are read back (blocking, like the ``.item()`` calls at
-    network_tests.py:320-321) after every step."""
+    network_tests.py:320-321) after every step.
+
+    ``dataset=(rolls, beats)``: the training set resident in HBM -- ``rolls`` (N,2,128,W) uint8/float32 and ``beats`` (N,50)
+    CUDA tensors (the reference's ``MaestroDatasetPickle(..., device=device)`` also keeps its items on the device,
+    datasets.py:73-87; 5.4 k MAESTRO slices are 69 MB).  A batch then carries ``real_idx`` (host int64 indices, what a
+    sampler yields) instead of ``real`` / ``beats``; the gather runs on the copy stream.  The fake rolls always come from the host."""
 
     KEYS = ("beats", "real", "fake_d", "fake_g")
 
-    def __init__(self, trainer, example):
+    def __init__(self, trainer, example, dataset=None):
         self.t = trainer
         dev = trainer.flat_grad.device
-        self.stage = [{k: torch.empty_like(example[k], device=dev) for k in self.KEYS} for _ in range(2)]
-        B = example["real"].shape[0]
+        self.dataset = dataset
+        B = example["fake_d"].shape[0]
+        if dataset is not None:
+            rolls, beats = dataset
+            N.require_cuda(rolls, beats)
+            self.copy_keys = ("fake_d", "fake_g")
+            self.stage = [{"fake_d": torch.empty_like(example["fake_d"], device=dev), "fake_g": torch.empty_like(example["fake_g"], device=dev),
+                           "real": torch.empty((B,) + tuple(rolls.shape[1:]), dtype=rolls.dtype, device=dev),
+                           "beats": torch.empty((B,) + tuple(beats.shape[1:]), dtype=beats.dtype, device=dev),
+                           "idx": torch.empty(B, dtype=torch.int64, device=dev)} for _ in range(2)]
+            self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.copy_keys) + B * 8
+        else:
+            self.copy_keys = self.KEYS
+            self.stage = [{k: torch.empty_like(example[k], device=dev) for k in self.KEYS} for _ in range(2)]
+            self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.KEYS)
         self.noise = [[torch.empty(B, trainer.m.z_dim, device=dev) for _ in range(2)] for _ in range(2)]     # static: graph replay
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         self.losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
-        self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.KEYS)
 
     def _issue(self, slot, batch, first_use):
         with torch.cuda.stream(self.copy_stream):
             if not first_use:
                 self.copy_stream.wait_event(self.free[slot])
-            for k in self.KEYS:
-                self.stage[slot][k].copy_(batch[k], non_blocking=True)
+            st = self.stage[slot]
+            for k in self.copy_keys:
+                st[k].copy_(batch[k], non_blocking=True)
+            if self.dataset is not None:
+                st["idx"].copy_(batch["real_idx"], non_blocking=True)
+                torch.index_select(self.dataset[0], 0, st["idx"], out=st["real"])
+                torch.index_select(self.dataset[1], 0, st["idx"], out=st["beats"])
             self.ready[slot].record(self.copy_stream)
 
     def run(self, batches):

@@ -153,3 +153,46 @@ def test_graph_replay_matches_eager():
     for a, b in zip(p0, p1):       # atomics reorder fp32 sums; Adam amplifies sign flips of ~0 gradients by lr per step
         assert (a - b).abs().max() <= 6 * 0.01 + 1e-6
         assert _rel_l2(a, b.cpu().numpy()) < 0.05
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_host_batch_pipeline_matches_direct_steps(resident):
+    """HostBatchPipeline (double-buffered H2D, optional HBM-resident training set gathered by index) must feed the iteration exactly
+    what a direct ``step`` on device copies of the same host data gets."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import HostBatchPipeline, MMGANTrainer
+    B, NDS = 32, 100
+    g = torch.Generator().manual_seed(11)
+    mk = lambda n: ((torch.rand(n, 2, 128, 50, generator=g) < 0.03) * torch.randint(1, 128, (n, 2, 128, 50), generator=g)).to(torch.uint8)
+    ds_rolls, ds_beats = mk(NDS), 25 * torch.rand(NDS, 50, generator=g)
+    batches = []
+    for _ in range(5):
+        idx = torch.randint(0, NDS, (B,), generator=g)
+        hb = dict(fake_d=mk(B).pin_memory(), fake_g=mk(B).pin_memory())
+        if resident:
+            hb["real_idx"] = idx.pin_memory()
+        else:
+            hb["real"], hb["beats"] = ds_rolls[idx].pin_memory(), ds_beats[idx].pin_memory()
+        hb["_idx"] = idx
+        batches.append(hb)
+    res = {}
+    for mode in ("pipeline", "direct"):
+        torch.manual_seed(21)
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150,
+                             device=DEV).train()
+        tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=B, inner_rng="device")
+        torch.manual_seed(22)
+        losses = []
+        if mode == "pipeline":
+            ex = dict(fake_d=batches[0]["fake_d"], fake_g=batches[0]["fake_g"], real=ds_rolls[:B], beats=ds_beats[:B])
+            pipe = HostBatchPipeline(tr, ex, dataset=(ds_rolls.to(DEV), ds_beats.to(DEV)) if resident else None)
+            for l in pipe.run(batches):
+                losses.append(l.clone())
+        else:
+            for hb in batches:
+                n1, n2 = torch.empty(B, 50, device=DEV).normal_(), torch.empty(B, 50, device=DEV).normal_()
+                dl, gl = tr.step(n1, n2, ds_beats[hb["_idx"]].to(DEV), ds_rolls[hb["_idx"]].to(DEV), hb["fake_d"].to(DEV), hb["fake_g"].to(DEV))
+                losses.append(torch.stack([dl, gl]).cpu())
+        res[mode] = torch.stack(losses)
+    assert torch.isfinite(res["pipeline"]).all()
+    assert torch.allclose(res["pipeline"], res["direct"], rtol=5e-3, atol=1e-4), (res["pipeline"], res["direct"])
