@@ -21,7 +21,8 @@
 
 namespace {
 
-constexpr int GT_THREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2-5 builders + epilogue
+constexpr int GT_WORKERS = 256;
+constexpr int GT_THREADS = 64 + GT_WORKERS;     // warp 0 TMA, warp 1 MMA, warps 2-9 builders + epilogue (two warps per TMEM lane quadrant)
 constexpr int GT_MAX_K = 256;
 constexpr int GT_A_CHUNK = 128 * 128;           // 128 rows x 64 bf16
 constexpr int GT_W_STAGES = 2;
@@ -87,20 +88,20 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
     __shared__ uint64_t wfull[GT_W_STAGES], wempty[GT_W_STAGES], aready, tfull[2], tempty[2];
     __shared__ uint32_t tmem_s;
     __shared__ float in_scale[GT_MAX_K], in_shift[GT_MAX_K];
-    __shared__ float ep_bias[256], ep_scale[256], ep_shift[256];
+    __shared__ __align__(16) float ep_bias[256], ep_scale[256], ep_shift[256];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int kchunks = a.Kp / 64;
     unsigned char* smem_a = smem;                                   // kchunks x 16 KB
     const int w_stage_bytes = kchunks * a.NG * 128;
     unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // GT_W_STAGES x w_stage_bytes
-    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // 2 x 16 KB output staging (only when y_out)
+    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // 2 warp groups x 2 x 16 KB output staging (only when y_out)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = a.row_tiles * a.n_groups;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < GT_W_STAGES; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&wempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
-        tc::mbar_init(&aready, 128);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], GT_WORKERS / 32); }
+        tc::mbar_init(&aready, GT_WORKERS);
         tc::fence_barrier_init();
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
@@ -167,38 +168,40 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             }
         }
     } else {
-        const int q = warp & 3, t = q * 32 + lane;               // t = row of the tile = TMEM lane
-        const int et = threadIdx.x - 64;                           // 0..127 over the builder/epilogue threads
-        // ---- A-tile builder: row t of row tile `rt`, all Kp features, swizzled 16-byte pieces
+        const int q = warp & 3, h = (warp - 2) >> 2, t = q * 32 + lane;     // t = row of the tile = TMEM lane; h = which half of the columns / features
+        const int et = threadIdx.x - 64;                                    // 0..255 over the builder/epilogue threads
+        const int eg = et & 127;                                            // index inside the warp group h
+        // ---- A-tile builder: row t of row tile `rt`, features [32h, 32h + 32) of every 64-feature chunk, swizzled 16-byte pieces
         auto build = [&](int rt) {
             const long long row = (long long)rt * 128 + t;
             const bool live = row < a.M;
             for (int c = 0; c < kchunks; ++c) {
                 const uint32_t dst = tc::smem_u32(smem_a) + c * GT_A_CHUNK + t * 128;
-                float v[64];                                       // all of the chunk's loads are issued before any is used
+                const int kb = c * 64 + 32 * h;
+                float v[32];                                       // all of the loads are issued before any is used
                 if (a.in_mode == 0) {
 #pragma unroll
-                    for (int e = 0; e < 64; ++e) {
-                        const int kk = c * 64 + e;
+                    for (int e = 0; e < 32; ++e) {
+                        const int kk = kb + e;
                         v[e] = !live ? 0.f : (kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < a.K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f));
                     }
                 } else {                                           // K is a multiple of 8 here (checked on the host)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int k = c * 64 + j * 4;
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kb + j * 4;
                         const float4 p = (live && k < a.K) ? *reinterpret_cast<const float4*>(a.x0 + row * a.K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                         v[4 * j] = p.x; v[4 * j + 1] = p.y; v[4 * j + 2] = p.z; v[4 * j + 3] = p.w;
                     }
 #pragma unroll
-                    for (int e = 0; e < 64; ++e) {
-                        const int k = c * 64 + e;
+                    for (int e = 0; e < 32; ++e) {
+                        const int k = kb + e;
                         v[e] = (live && k < a.K) ? fast_sigmoid_affine(v[e], in_scale[k], in_shift[k]) : 0.f;
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    tc::sts128(dst + ((j ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+                for (int j = 0; j < 4; ++j)
+                    tc::sts128(dst + (((4 * h + j) ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&aready);
@@ -210,8 +213,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
             const int rt = item / a.n_groups, grp = item % a.n_groups, n0 = grp * a.NG;
             // per-item column constants (bias; output-side BN folded to scale/shift)
-            asm volatile("bar.sync 1, 128;" ::: "memory");        // previous item's epilogue no longer reads ep_*
-            for (int c = et; c < a.NG; c += 128) {
+            asm volatile("bar.sync 3, 256;" ::: "memory");        // previous item's epilogue no longer reads ep_*
+            for (int c = et; c < a.NG; c += GT_WORKERS) {
                 const int n = n0 + c;
                 ep_bias[c] = (n < a.N && a.bias) ? a.bias[n] : 0.f;
                 if (a.y_out) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                     ep_shift[c] = (ep_bias[c] * sc + sh) * NEG_LOG2E;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 3, 256;" ::: "memory");
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
             // the MMAs of this item are complete: the A buffer is free, build the next item's tile so its MMAs overlap this epilogue
@@ -243,14 +246,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             if (next < items) build(next / a.n_groups);
             const long long row = (long long)rt * 128 + t;
             const bool live = row < a.M;
-            for (int c0 = 0; c0 < a.NG; c0 += 32) {
+            for (int c0 = 32 * h; c0 < a.NG; c0 += 64) {              // the two warps of a lane quadrant take alternate 32-column chunks
                 uint32_t r[32];
                 tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, r);
                 tc::tmem_ld_wait();
                 float z[32];
                 if (a.z_out || a.out_sums) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) z[e] = __uint_as_float(r[e]) + ep_bias[c0 + e];
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 bb = reinterpret_cast<const float4*>(ep_bias + c0)[e4];
+                        z[4 * e4] = __uint_as_float(r[4 * e4]) + bb.x; z[4 * e4 + 1] = __uint_as_float(r[4 * e4 + 1]) + bb.y;
+                        z[4 * e4 + 2] = __uint_as_float(r[4 * e4 + 2]) + bb.z; z[4 * e4 + 3] = __uint_as_float(r[4 * e4 + 3]) + bb.w;
+                    }
                 }
                 const int ncols = a.N - (n0 + c0);                  // columns of this chunk that exist (>= 32: all)
                 if (a.z_out && live) {
@@ -265,19 +272,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                 }
                 if (a.y_out) {
                     // y tile (128 rows x 32 fp32) -> 128-byte-swizzled staging buffer -> one TMA store (rows >= M and columns >= N are clipped)
-                    unsigned char* stg = smem_y + (ychunk & 1) * GT_Y_STAGE;
-                    if (et == 0) tc::bulk_wait_group_read<1>();        // the store issued from this buffer two chunks ago has read it
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    unsigned char* stg = smem_y + (2 * h + (ychunk & 1)) * GT_Y_STAGE;
+                    if (eg == 0) tc::bulk_wait_group_read<1>();        // the store this warp group issued from this buffer two chunks ago has read it
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
                     float y[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) y[e] = fast_sigmoid_affine(__uint_as_float(r[e]), ep_scale[c0 + e], ep_shift[c0 + e]);
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 sc = reinterpret_cast<const float4*>(ep_scale + c0)[e4], sh = reinterpret_cast<const float4*>(ep_shift + c0)[e4];
+                        y[4 * e4] = fast_sigmoid_affine(__uint_as_float(r[4 * e4]), sc.x, sh.x);
+                        y[4 * e4 + 1] = fast_sigmoid_affine(__uint_as_float(r[4 * e4 + 1]), sc.y, sh.y);
+                        y[4 * e4 + 2] = fast_sigmoid_affine(__uint_as_float(r[4 * e4 + 2]), sc.z, sh.z);
+                        y[4 * e4 + 3] = fast_sigmoid_affine(__uint_as_float(r[4 * e4 + 3]), sc.w, sh.w);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         tc::sts128(tc::smem_u32(stg) + t * 128 + ((j ^ (t & 7)) << 4), make_uint4(__float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
                                                                                                __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3])));
                     tc::fence_proxy_async_smem();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et == 0) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+                    if (eg == 0) {
                         tc::tma_store_2d(&map_y, stg, n0 + c0, rt * 128);
                         tc::bulk_commit_group();
                     }
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
         }
-        if (et == 0) tc::bulk_wait_group_read<0>();                // staging buffers must outlive the last TMA store's reads
+        if (eg == 0) tc::bulk_wait_group_read<0>();                // staging buffers must outlive the last TMA store's reads
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -368,7 +381,7 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w, p->w_packed, (uint64_t)a.Kp, (uint64_t)Np, (uint64_t)a.Kp * 2, 64, (uint32_t)a.NG, CU_TENSOR_MAP_SWIZZLE_128B) == 0,
                 MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(w) failed");
     const int kchunks = a.Kp / 64;
-    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 2 * GT_Y_STAGE : 0);
+    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 4 * GT_Y_STAGE : 0);
     CUtensorMap map_y = map_w;
     if (p->y_out) {
         MMG_REQUIRE(((uintptr_t)p->y_out & 15) == 0 && (p->N & 3) == 0, MMG_EUNSUPPORTED, "gen_layer_fwd: y_out must be 16-byte aligned with N % 4 == 0");
