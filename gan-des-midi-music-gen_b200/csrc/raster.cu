@@ -175,11 +175,11 @@ constexpr int K1_WARPS = 4;
 constexpr int K1_CH = 512;            // messages per chain chunk
 constexpr int K1_CJ = K1_CH / 32;
 
-__global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
+__global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
                                                                       const int64_t* __restrict__ offsets, int64_t n_songs, int S, int W,
                                                                       uint32_t* __restrict__ notes, int32_t* __restrict__ note_count,
                                                                       int32_t* __restrict__ status) {
-    __shared__ double tbuf[K1_WARPS][K1_CH];
+    __shared__ __align__(16) double tbuf[K1_WARPS][K1_CH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t song = (int64_t)blockIdx.x * K1_WARPS + warp;
     if (song >= n_songs) return;
@@ -212,19 +212,26 @@ __global__ void __launch_bounds__(K1_WARPS * 32) raster_steps_kernel(const doubl
         __syncwarp();
         const int cnt = (int)((n - i0) < K1_CH ? (n - i0) : K1_CH);
         if (lane == 0) {                                           // sequential float64 running sum (datasets.py:35)
+            // 8 elements per trip: 4 LDS.128 for the next trip are in flight behind the 8 dependent adds, 4 STS.128 write the prefix sums
+            // back (about 2 instructions per element: with 3 chains per scheduler the loop is bound by the DADD latency, not by issue slots)
             const int lim8 = (cnt + 7) & ~7;                       // padding holds 0.0: t + 0.0 == t
-            double v[8], w[8];
+            double2* tb2 = reinterpret_cast<double2*>(tb);
+            double2 v[4], w[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = tb[u];
+            for (int u = 0; u < 4; ++u) v[u] = tb2[u];
             for (int k = 0; k < lim8; k += 8) {
                 if (k + 8 < lim8) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) w[u] = tb[k + 8 + u];      // next 8 loaded behind the dependent adds
+                    for (int u = 0; u < 4; ++u) w[u] = tb2[(k >> 1) + 4 + u];
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { t = __dadd_rn(t, v[u]); tb[k + u] = t; }
+                for (int u = 0; u < 4; ++u) {
+                    t = __dadd_rn(t, v[u].x); v[u].x = t;
+                    t = __dadd_rn(t, v[u].y); v[u].y = t;
+                    tb2[(k >> 1) + u] = v[u];
+                }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = w[u];
+                for (int u = 0; u < 4; ++u) v[u] = w[u];
             }
         }
         __syncwarp();
