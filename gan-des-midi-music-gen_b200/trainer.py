@@ -14,14 +14,14 @@ precision='fp32' : the drop-in nn.Modules + autograd over the fp32 SIMT kernels 
 precision='bf16' : discriminator on the tcgen05 tensor-core kernels (disc_tc.DiscTC): bf16 operands,
                    fp32 accumulation, fp32 master weights / Adam state; fused BCE and multi-tensor Adam.
 CUDA graphs (``use_graph=True``, default for bf16): after one eager iteration on the same input buffers the iteration
-is captured (one graph, or two around the NCCL all-reduce when sharded) and later calls with the same buffers replay
+is captured (one graph, or three around the asynchronous NCCL all-reduce when sharded) and later calls with the same buffers replay
 it: one launch per iteration instead of ~100.  Adam's step count and learning rate live in device memory for that
 (``mmg_adam_multi_tensor_dev_f32``), so ``StepLR`` keeps working.
 ``inner_rng``: the reference's Generator draws its second input with ``torch.randn`` on the CPU generator inside forward
 (network_tests.py:83-84); 'reference' reproduces that draw (same global RNG consumption), 'device' draws on the GPU.
 Data parallel: with torch.distributed initialised (NCCL) the batch is sharded by rank, the D gradients
-live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step (the 1/world factor is
-folded into the Adam kernel), and the G-step D grads are not reduced (the reference discards them).
+live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step, asynchronously, overlapped with the G step's
+generator forwards (the 1/world factor is folded into the Adam kernel); the G-step D grads are not reduced (the reference discards them).
 """
 import ctypes
 
@@ -99,9 +99,10 @@ class MMGANTrainer:
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
 
-    def _allreduce_d_grads(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)       # sum; 1/world is applied inside the Adam kernel
+    def _allreduce_d_grads(self, async_op=False):
+        if self.world > 1:                 # sum; 1/world is applied inside the Adam kernel
+            return torch.distributed.all_reduce(self.flat_grad, group=self.pg, async_op=async_op)
+        return None
 
     def _disc_adam(self):
         """Adam on the six discriminator tensors, one launch, hyper-parameters and step count read from device memory."""
@@ -185,12 +186,16 @@ class MMGANTrainer:
         if self.tc is not None:
             self.logit_real = self.logit_real.clone()
 
+    def _seg_g_gen(self, noise1, noise2, beats, fake_g, inner_g):
+        """The G step's generator forwards (:312 -> :177-178).  They depend on nothing the D step produces (generator weights never change, SURVEY
+        3.1), so when sharded they run while the D-gradient all-reduce is in flight."""
+        self._generators(noise1, noise2, beats, inner_g)
+
     def _seg_g(self, noise1, noise2, beats, fake_g, inner_g):
-        """Adam on D (:308), then the G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them"""
+        """Adam on D (:308), then the rest of the G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them"""
         self._disc_adam()
         if self.tc is not None:
             self.tc.pack()
-        self._generators(noise1, noise2, beats, inner_g)
         self.logit_fake_g = self._d_pass(fake_g, 1.0, self.loss_g, False)
 
     def _capture(self, fn, *args):
@@ -219,23 +224,28 @@ class MMGANTrainer:
                     torch.cuda.synchronize()
                     self.graph_launches = 0
                     if self.world == 1:
-                        graphs = (self._capture(lambda: (self._seg_d(*a_d), self._seg_g(*a_g))),)
+                        graphs = (self._capture(lambda: (self._seg_d(*a_d), self._seg_g_gen(*a_g), self._seg_g(*a_g))),)
                     else:
-                        graphs = (self._capture(self._seg_d, *a_d), self._capture(self._seg_g, *a_g))
+                        graphs = (self._capture(self._seg_d, *a_d), self._capture(self._seg_g_gen, *a_g), self._capture(self._seg_g, *a_g))
                     self._graphs[key] = graphs       # capture does not execute: fall through to the replay below
         self._sync_hyper()
         if graphs is None:
             self._seg_d(*a_d)
-            self._allreduce_d_grads()
+            work = self._allreduce_d_grads(async_op=True)       # 84 KB over NVLink, hidden behind the G step's generator forwards
+            self._seg_g_gen(*a_g)
+            if work is not None:
+                work.wait()
             if self.on_d_grads is not None:
                 self.on_d_grads(self)              # observer hook: flat_grad holds the (summed) D-step gradients Adam is about to consume
             self._seg_g(*a_g)
         else:
             self.replayed_launches += self.graph_launches
             graphs[0].replay()
-            if len(graphs) == 2:
-                self._allreduce_d_grads()
+            if len(graphs) == 3:
+                work = self._allreduce_d_grads(async_op=True)
                 graphs[1].replay()
+                work.wait()
+                graphs[2].replay()
         self.gen_opt.step()          # no-op: generator grads are None
         return self.loss_d[0], self.loss_g[0]
 
