@@ -85,6 +85,77 @@ def _raster_leg(device, peaks, quick):
             "checksum": float(out.double().sum().item())}
 
 
+def _gandes_leg(device):
+    """BASELINE config 2: GAN-DES (GAN_DES/SIMNN.py:275-334) G+D training iteration on one synthetic song matrix (B = 30 spectrograms of
+    128 x 216), fp32 kernels of this library, fused BCE / multi-tensor Adam; DES + FluidSynth bridge excluded (the fake spectrograms are inputs)."""
+    import mmgan_oracle as mo               # cpu_baseline sample only
+    from .GAN_DES import SIMNN
+    from . import optim as fo
+    B = 30
+    gshapes, dshapes = mo.gandes_shapes()
+    gsd, dsd = mo.synth_state(gshapes, seed=11), mo.synth_state(dshapes, seed=12)
+    gen, disc = SIMNN.Generator().to(device), SIMNN.Discriminator().to(device)
+    gen.load_state_dict(gsd); disc.load_state_dict(dsd)
+    crit = fo.BCEWithLogitsLoss()
+    gen_opt = fo.FusedAdam(gen.parameters(), lr=2e-5, betas=(0.5, 0.999))
+    disc_opt = fo.FusedAdam(disc.parameters(), lr=2e-5, betas=(0.5, 0.999))
+    g = torch.Generator().manual_seed(3)
+    noise_h, real_h, fake_h = torch.randn(B, 100, 1, 1, generator=g), torch.randn(B, 128, 216, generator=g), torch.randn(B, 128, 216, generator=g)
+    noise, real, fake = noise_h.to(device), real_h.to(device), fake_h.to(device)
+    t09, t01, t1 = torch.full((B,), 0.9, device=device), torch.full((B,), 0.1, device=device), torch.ones(B, device=device)
+
+    def it(i):
+        disc_opt.zero_grad()
+        l_real = crit(disc(real).reshape(-1), t09)
+        with torch.no_grad():
+            gen(noise)
+        l_fake = crit(disc(fake.detach()).reshape(-1), t01)
+        (l_fake + l_real).backward()
+        disc_opt.step()
+        gen_opt.zero_grad()
+        crit(disc(fake).squeeze(), t1).backward()
+        gen_opt.step()
+
+    for _ in range(3):
+        it(0)
+    sec = _timed(it, 10, torch.cuda.synchronize) / 10
+    adam = {}
+    mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 5.0 and n < 20:
+        mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
+        n += 1
+    cs = (time.perf_counter() - t0) / n
+    return {"spectrograms_per_sec": B / sec, "ms_per_step": sec * 1e3, "batch": B, "dtype": "f32",
+            "cpu_baseline": {"value": B / cs, "unit": "spectrograms/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": f"{n} iterations of batch {B} through oracle/mmgan_oracle.gandes_iteration"}}
+
+
+def _inference_leg(mmgan, device):
+    """BASELINE config 5: eval-mode G1 + G2 (running-stat BatchNorm folded into the tcgen05 prologue / epilogue) for B = 1 .. 16384, outputs
+    (B,1,64,64) + (B,20) fp32 delivered to pinned host memory -- what matrix_to_midi consumes (matrix_sim_process.py:28-29)."""
+    from .gen_tc import GenTC
+    out = {}
+    for B in (1, 16, 256, 4096, 16384):
+        g1, g2 = GenTC(mmgan.generator1, B), GenTC(mmgan.generator2, B)
+        n = [torch.randn(B, 50, device=device) for _ in range(4)]
+        o1, o2 = torch.empty(B, 4096, device=device), torch.empty(B, 20, device=device)
+        h1, h2 = torch.empty(B, 4096).pin_memory(), torch.empty(B, 20).pin_memory()
+
+        def it(i):
+            g1.forward(n[0], n[1], training=False, out=o1)
+            g2.forward(n[2], n[3], training=False, out=o2)
+            h1.copy_(o1, non_blocking=True)
+            h2.copy_(o2, non_blocking=True)
+
+        for _ in range(3):
+            it(0)
+        sec = _timed(it, 10, torch.cuda.synchronize) / 10
+        out[str(B)] = {"samples_per_sec": B / sec, "us": sec * 1e6}
+    return out
+
+
 def run(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,6 +301,9 @@ def run(args):
                                     "sample": f"{n_it} iterations of batch {Bc} through oracle/mmgan_oracle.py (fp32, DES excluded)"}
         if not args.no_raster:
             line["raster"] = _raster_leg(device, peaks, quick=False)
+            mmgan.eval()
+            line["inference_sweep"] = _inference_leg(mmgan, device)
+            line["gandes"] = _gandes_leg(device)
     if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()
