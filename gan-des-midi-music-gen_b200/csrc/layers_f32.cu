@@ -75,12 +75,27 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     }
 }
 
+// y[i][j] = act(y[i][j] + bias[j])  (epilogue of a split-K product whose partial sums were accumulated with atomics)
+__global__ void bias_act_inplace_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int N, int act) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        y[i] = mmg_act(y[i] + (bias ? bias[i % N] : 0.f), act);
+}
+
 int launch_sgemm(const float* A, long long sa_i, long long sa_k, const float* B, long long sb_k, long long sb_j, float* C, int M, int N,
                  int K, const float* bias, int act, int accumulate, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return MMG_OK;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
     int splits = 1;
     const long long tiles = (long long)grid.x * grid.y;
+    if (act != MMG_ACT_NONE && !accumulate && K >= 8192 && tiles < MMG_NUM_SMS / 4) {
+        // a handful of output tiles over a very long K (GAN-DES fc1: 30 x 128 over 55 296): split K, then bias + activation in place
+        int rc = launch_sgemm(A, sa_i, sa_k, B, sb_k, sb_j, C, M, N, K, nullptr, MMG_ACT_NONE, 0, stream);
+        if (rc) return rc;
+        const long long total = (long long)M * N;
+        bias_act_inplace_kernel<<<mmg_grid(total, 256), 256, 0, stream>>>(C, bias, total, N, act);
+        MMG_LAUNCH_CHECK();
+        return MMG_OK;
+    }
     if (act == MMG_ACT_NONE && K >= 2048 && tiles < 2 * MMG_NUM_SMS) {        // split-K for skinny outputs (weight grads)
         splits = (int)((4LL * MMG_NUM_SMS + tiles - 1) / tiles);
         const int max_splits = (K + 255) / 256;
