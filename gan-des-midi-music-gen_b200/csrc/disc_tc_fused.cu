@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float z0 = __uint_as_float(r[2 * c]) + b1r[2 * c], z1 = __uint_as_float(r[2 * c + 1]) + b1r[2 * c + 1];
-                        o[c] = pack_bf16x2(z0 > 0.f ? z0 : 0.2f * z0, z1 > 0.f ? z1 : 0.2f * z1);
+                        o[c] = pack_bf16x2(fmaxf(z0, 0.2f * z0), fmaxf(z1, 0.2f * z1));       // LeakyReLU(0.2) = max(z, 0.2 z)
                     }
                     const int yp = oy + 1, xp = ox + 1, R = (yp >> 1) * P1_W + (xp >> 1), cell = (yp & 1) * 2 + (xp & 1);
                     const uint32_t rowp = p1_s + R * 128;
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float z0 = __uint_as_float(r[2 * c]) + b2r[2 * c], z1 = __uint_as_float(r[2 * c + 1]) + b2r[2 * c + 1];
-                    z0 = z0 > 0.f ? z0 : 0.2f * z0; z1 = z1 > 0.f ? z1 : 0.2f * z1;
+                    z0 = fmaxf(z0, 0.2f * z0); z1 = fmaxf(z1, 0.2f * z1);
                     o[c] = real ? pack_bf16x2(z0, z1) : 0u;
                     dot = fmaf(bf_lo(o[c]), wreg[tile][2 * c], dot);                      // the bf16 values the backward will read
                     dot = fmaf(bf_hi(o[c]), wreg[tile][2 * c + 1], dot);
