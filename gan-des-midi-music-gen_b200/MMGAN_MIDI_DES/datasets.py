@@ -244,6 +244,49 @@ def generate_piano_roll(midi_input, sequence_length=100, beats_length=50, start=
 
 
 # ----------------------------------------------------------------------------------------------
+# MAESTRO preprocessing (data_viewing_and_processing.ipynb cells 10-11 -> data/preprocessed_data_50.pkl)
+# ----------------------------------------------------------------------------------------------
+def total_time_steps(stream, sample_size):
+    """``total_time`` of the notebook's generate_piano_roll (cell 10): the time step of the last message the loop visited, i.e. of the
+    first message whose step reaches ``sample_size`` (the loop assigns it before it breaks) or of the last message.  The float64 running
+    sum is sequential (np.cumsum) and the rounding is half-to-even (np.rint), like ``int(round(my_time))``."""
+    if len(stream) == 0:
+        return 0
+    steps = np.rint(np.cumsum(stream.dt)).astype(np.int64)
+    over = np.nonzero(steps >= sample_size)[0]
+    return int(steps[over[0]] if len(over) else steps[-1])
+
+
+def preprocess_maestro(inputs, sample_size=300, sequence_length=50, beats_length=50, device="cuda"):
+    """The MAESTRO pickling pipeline of the reference (notebook cells 10-11) with ONE batched rasterisation on the device: every file
+    (path or :class:`EventStream`) is rasterised over a ``sample_size``-step window, cut into ``sequence_length``-step slices, slice 0 is
+    skipped, and each kept slice becomes a ``(piano_roll (128,L), durations (128,L), beats (beats_length,))`` triple of float32 CPU
+    tensors -- the list ``MaestroDatasetPickle`` unpickles (datasets.py:73-87)."""
+    streams = [_as_stream(x) for x in inputs]
+    if not streams:
+        return []
+    rolls = rasterize_batch(streams, sample_size, 0, sample_size, device=device).cpu()       # (S, 2, 128, sample_size), bit-exact
+    out = []
+    for s, r in zip(streams, rolls):
+        beats = np.asarray(s.beats, dtype=np.float64)
+        beats = np.pad(beats, (0, beats_length - len(beats))) if len(beats) < beats_length else beats[:beats_length]
+        beats_t = torch.from_numpy(beats).float()
+        n = int(np.floor(total_time_steps(s, sample_size) / sequence_length))
+        for i in range(1, n):                                # slice 0 is skipped (cell 11: `and i != 0`)
+            a = i * sequence_length
+            if a + sequence_length > sample_size:            # the reference's shape check drops slices past the window
+                break
+            out.append((r[0, :, a:a + sequence_length].clone(), r[1, :, a:a + sequence_length].clone(), beats_t))
+    return out
+
+
+def save_preprocessed(triples, path):
+    """Writes the list the way cell 11 does (pickle), readable by ``MaestroDatasetPickle``."""
+    with open(path, "wb") as f:
+        pickle.dump(triples, f)
+
+
+# ----------------------------------------------------------------------------------------------
 # Dataset classes (datasets.py:73-123)
 # ----------------------------------------------------------------------------------------------
 def _data_path(*parts):

@@ -173,3 +173,35 @@ def raster_batch_c(dt, meta, offsets, sequence_length, start, end, n_threads=1):
     with ThreadPoolExecutor(n_threads) as ex:
         notes = sum(ex.map(lambda ab: run(int(ab[0]), int(ab[1])), zip(bounds[:-1], bounds[1:])))
     return out, notes
+
+
+def preprocess_reference(streams, sample_size=300, sequence_length=50, beats_length=50):
+    """ORACLE restatement of the MAESTRO pickling loop, /root/reference/MMGAN_MIDI_DES/data_viewing_and_processing.ipynb cells 10-11, on
+    post-mido streams given as (dt, meta, beats) tuples: plain Python message loop (cell 10, which returns ``total_time`` = the step of the
+    last message visited), then the slicing of cell 11 (50-step slices, slice 0 skipped, wrong-shaped slices dropped).
+    Returns a list of (roll (128,L) f32, dur (128,L) f32, beats (beats_length,) f32) numpy triples."""
+    out = []
+    for dt, meta, beats in streams:
+        kind, pitch, vel = unpack_meta(meta)
+        roll = np.zeros((128, sample_size)); dur = np.zeros((128, sample_size))
+        on = np.zeros(128)
+        t, total = 0.0, 0
+        for i in range(len(dt)):
+            t += float(dt[i])
+            step = int(round(t))
+            total = step
+            if step >= sample_size:
+                break
+            if kind[i] == KIND_ON:
+                roll[pitch[i], step] = vel[i]
+                on[pitch[i]] = step
+            elif kind[i] == KIND_OFF:
+                a = int(round(on[pitch[i]]))
+                dur[pitch[i], a:step] = step - a
+        b = np.asarray(beats, dtype=np.float64)
+        b = np.pad(b, (0, beats_length - len(b))) if len(b) < beats_length else b[:beats_length]
+        for j in range(int(np.floor(total / sequence_length))):
+            rs, ds = roll[:, j * sequence_length:(j + 1) * sequence_length], dur[:, j * sequence_length:(j + 1) * sequence_length]
+            if rs.shape[1] == sequence_length and ds.shape[1] == sequence_length and j != 0:
+                out.append((rs.astype(np.float32), ds.astype(np.float32), b.astype(np.float32)))
+    return out

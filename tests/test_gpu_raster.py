@@ -98,3 +98,29 @@ def test_generate_piano_roll_api(golden_dir):
     assert np.array_equal(roll4, c["K4.roll"])
     item = ds.MaestroDatasetMidi([s], 100, 50, device="cuda")[0]
     assert item[0].shape == (128, 50) and item[0].dtype == torch.float32 and item[0].is_cuda
+
+
+def test_preprocess_maestro_matches_notebook_loop(tmp_path):
+    """the MAESTRO pickling pipeline (notebook cells 10-11) with one batched device rasterisation, against the plain-Python
+    restatement; includes a song shorter than one slice, one shorter than the window and ones that overrun it."""
+    import pickle
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    rng = np.random.default_rng(5)
+    streams, ref_in = [], []
+    for n_msg, total in ((0, 0.0), (40, 30.0), (900, 170.0), (3000, 420.0), (5000, 299.6), (2500, 1000.0)):
+        dt = rng.exponential(total / max(n_msg, 1), size=n_msg)
+        dt[rng.random(n_msg) < 0.1] = 0.5
+        meta = ro.pack_meta(rng.integers(0, 3, n_msg), rng.integers(21, 109, n_msg), rng.integers(0, 128, n_msg))
+        beats = np.sort(rng.random(rng.integers(0, 80))) * 60
+        streams.append(ds.EventStream(dt, meta, beats))
+        ref_in.append((dt, meta, beats))
+    got = ds.preprocess_maestro(streams)
+    want = ro.preprocess_reference(ref_in)
+    assert len(got) == len(want) and len(got) >= 8
+    for (gr, gd, gb), (wr, wd, wb) in zip(got, want):
+        assert gr.dtype == torch.float32 and tuple(gr.shape) == (128, 50) and tuple(gb.shape) == (50,)
+        assert np.array_equal(gr.numpy(), wr) and np.array_equal(gd.numpy(), wd) and np.array_equal(gb.numpy(), wb)
+    p = tmp_path / "preprocessed_data_50.pkl"
+    ds.save_preprocessed(got, p)
+    back = pickle.load(open(p, "rb"))
+    assert len(back) == len(got) and torch.equal(back[3][1], got[3][1])

@@ -72,3 +72,21 @@ def test_pickle_dataset(tmp_path, monkeypatch):
     d = ds.MaestroDatasetPickle("p.pkl")
     assert len(d) == 3 and d[1][2][7] == 7.0
     assert len(ds.MaestroDatasetMidi("nowhere")) == 0
+
+
+def test_total_time_steps_matches_sequential_loop():
+    """total_time of the notebook's preprocessing loop (cell 10): sequential float64 sum, round-half-even, the breaking message included."""
+    import numpy as np
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    rng = np.random.default_rng(2)
+    for n, scale in ((0, 1.0), (7, 0.5), (400, 0.9), (400, 0.3), (50, 10.0)):
+        dt = rng.exponential(scale, size=n)
+        dt[rng.random(n) < 0.3] = 0.5
+        s = ds.EventStream(dt, np.zeros(n, dtype=np.uint32))
+        t, total = 0.0, 0
+        for d in dt:
+            t += float(d)
+            total = int(round(t))
+            if total >= 300:
+                break
+        assert ds.total_time_steps(s, 300) == total
