@@ -196,3 +196,38 @@ def test_host_batch_pipeline_matches_direct_steps(resident):
         res[mode] = torch.stack(losses)
     assert torch.isfinite(res["pipeline"]).all()
     assert torch.allclose(res["pipeline"], res["direct"], rtol=5e-3, atol=1e-4), (res["pipeline"], res["direct"])
+
+
+@pytest.mark.parametrize("B", [2, 7, 149])
+def test_bf16_iteration_matches_fp32_iteration_on_small_and_odd_batches(B):
+    """Odd batch sizes (fewer samples than SMs, one more than the SM count) through the fused tcgen05 kernels vs the fp32 kernels of the same
+    library (themselves pinned to the reference): first-iteration losses within the bf16 tolerance."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    sd = mo.synth_state(mo.mmgan_shapes(), seed=4, d_scale=0.25)
+    inp = {k: v.to(DEV) for k, v in mo.synth_inputs(B, seed=77).items()}
+    out = {}
+    for precision in ("fp32", "bf16"):
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device=DEV)
+        m.load_state_dict(sd)
+        m.train()
+        tr = MMGANTrainer(m, lr=0.01, precision=precision, max_batch=B, use_graph=False)
+        dl, gl = tr.step(inp["noise1"], inp["noise2"], inp["beats"], inp["real"], inp["fake_d"], inp["fake_g"], inp["inner_d"], inp["inner_g"])
+        out[precision] = (dl.item(), gl.item(), tr.logit_real.clone(), tr.g2_out.clone())
+    a, b = out["fp32"], out["bf16"]
+    assert abs(a[0] - b[0]) <= 2e-3 * max(1.0, abs(a[0])), (a[0], b[0])
+    assert (a[2] - b[2]).abs().max().item() <= 5e-3 * a[2].abs().max().item() + 1e-3
+    if B >= 64:        # batch-statistics BatchNorm over a handful of samples is ill-conditioned (at B = 2 every output is sigmoid(+-gamma)): sign flips are not errors
+        assert (a[3] - b[3]).abs().max().item() < 2e-2
+
+
+def test_single_sample_training_batch_raises_like_torch():
+    """train-mode BatchNorm over one sample: torch raises ValueError('Expected more than 1 value per channel ...'); so do both precisions."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    inp = {k: v.to(DEV) for k, v in mo.synth_inputs(1, seed=5).items()}
+    for precision in ("fp32", "bf16"):
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device=DEV).train()
+        tr = MMGANTrainer(m, lr=0.01, precision=precision, max_batch=1, use_graph=False)
+        with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+            tr.step(inp["noise1"], inp["noise2"], inp["beats"], inp["real"], inp["fake_d"], inp["fake_g"], inp["inner_d"], inp["inner_g"])
