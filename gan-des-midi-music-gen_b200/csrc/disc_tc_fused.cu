@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_w,
                                                                        const FusedBwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t full_p1[2], full_a2, full_xs, dz2_ready, dz1_ready, mma1_done, mma2_done, wbar;
+    __shared__ uint64_t full_p1[2], full_a2, full_xs, dz2_ready[4], dz1_ready, dg_done[4], mma2_done, wbar;    // [4]: one per 128-row tile
     __shared__ uint32_t tmem_s;
     __shared__ float red_s[48];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&full_p1[0], 1); tc::mbar_init(&full_p1[1], 1); tc::mbar_init(&full_a2, 1); tc::mbar_init(&full_xs, 1); tc::mbar_init(&wbar, 1);
-        tc::mbar_init(&dz2_ready, FB_WORKERS); tc::mbar_init(&dz1_ready, FB_WORKERS);
-        tc::mbar_init(&mma1_done, 1); tc::mbar_init(&mma2_done, 1);
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&dz2_ready[i], FB_WORKERS); tc::mbar_init(&dg_done[i], 1); }
+        tc::mbar_init(&dz1_ready, FB_WORKERS); tc::mbar_init(&mma2_done, 1);
         tc::fence_barrier_init();
     }
     if (threadIdx.x < 48) red_s[threadIdx.x] = 0.f;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
             for (int it = 0; it < n_my; ++it) {
                 const int b = blockIdx.x + it * gridDim.x;
                 const uint32_t prev = (uint32_t)((it - 1) & 1);
-                if (it > 0) tc::mbar_wait(&mma1_done, prev);                      // conv2 wgrad / dgrad MMAs of the previous sample have read DZ2
+                if (it > 0) tc::mbar_wait(&dg_done[3], prev);                     // conv2 wgrad / dgrad MMAs of the previous sample have read DZ2
                 tc::mbar_expect_tx(&full_a2, A2_LOAD_ROWS * 64);
                 tc::tma_load_2d(smem + SM_DZ2 + 1024, &map_a2, &full_a2, 0, b * P1_ROWS);
                 tc::tma_load_2d(smem + SM_DZ2 + 1024 + 216 * 64, &map_a2, &full_a2, 0, b * P1_ROWS + 216);
@@ -138,24 +138,32 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
             for (int it = 0; it < n_my; ++it) {
                 const uint32_t ph = (uint32_t)(it & 1);
                 const uint32_t p1 = p1_base + (it & 1) * P1_BUF;
-                tc::mbar_wait(&dz2_ready, ph);
                 tc::mbar_wait(&full_p1[it & 1], (uint32_t)((it >> 1) & 1));
-                tc::tc_fence_after();
+                // tile by tile behind the workers' DZ2 pass: as soon as rows [128 t, 128 t + 128) of DZ2 exist, their conv2 wgrad K steps and
+                // dgrad tile t are issued, and the commit of tile t lets the dgrad epilogue of that tile start while later tiles still run
 #pragma unroll
-                for (int ty = 0; ty < 2 && !(a.dbg_skip & 1); ++ty)
-#pragma unroll 9
-                    for (int k = 0; k < K2_STEPS; ++k)
-                        tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
-                                       ID_WG2, (it | k) != 0, leader);
+                for (int tile = 0; tile < 4; ++tile) {
+                    tc::mbar_wait(&dz2_ready[tile], ph);
+                    tc::tc_fence_after();
+                    const int k_lo = tile * 8, k_hi = tile == 3 ? K2_STEPS : tile * 8 + 8;
+                    if (!(a.dbg_skip & 1)) {
 #pragma unroll
-                for (int tile = 0; tile < 4 && !(a.dbg_skip & 2); ++tile)
+                        for (int ty = 0; ty < 2; ++ty)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
+                            for (int k = k_lo; k < k_hi; ++k)
+                                tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128),
+                                                    tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64), ID_WG2, (it | k) != 0, leader);
+                    }
+                    if (!(a.dbg_skip & 2)) {
 #pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            tc::mma_f16_ss_pred(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
-                                           tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0, leader);
-                tc::mma_commit_pred(&mma1_done, leader);
+                        for (int t = 0; t < 4; ++t)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                tc::mma_f16_ss_pred(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
+                                                    tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0, leader);
+                    }
+                    tc::mma_commit_pred(&dg_done[tile], leader);
+                }
                 tc::mbar_wait(&dz1_ready, ph);
                 tc::mbar_wait(&full_xs, ph);
                 tc::tc_fence_after();
@@ -207,7 +215,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
                 const int R = tile * 128 + tl;
-                if (tile * 128 + q * 32 >= A2_LOAD_ROWS) continue;    // warp-uniform: this warp's 32 rows are all beyond the loaded rows
+                if (tile * 128 + q * 32 >= A2_LOAD_ROWS) {            // warp-uniform: this warp's 32 rows are all beyond the loaded rows
+                    tc::mbar_arrive(&dz2_ready[tile]);
+                    continue;
+                }
                 const bool loaded = R < A2_LOAD_ROWS;                 // rows 429..431 (the next sample's A2) have w = 0 -> they are zeroed
                 const uint32_t rowp = dz2s + (loaded ? R : 0) * 64;
                 const int sw = (R >> 1) & 3;
@@ -232,16 +243,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_bwd_fused_kernel(const __g
                     tc::sts128(c0p, make_uint4(o[0], o[1], o[2], o[3]));
                     tc::sts128(c1p, make_uint4(o[4], o[5], o[6], o[7]));
                 }
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&dz2_ready[tile]);                    // the MMAs of this tile may start
             }
             tmem_st_wait();
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&dz2_ready);
-            // ---- W3: conv2 dgrad epilogue -> DZ1 in place over P1, conv1.bias gradient
-            tc::mbar_wait(&mma1_done, ph);
-            tc::tc_fence_after();
+            // ---- W3: conv2 dgrad epilogue -> DZ1 in place over P1, conv1.bias gradient (tile t as soon as its MMAs have committed)
             const uint32_t p1s = p1_base + (it & 1) * P1_BUF;
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
+                tc::mbar_wait(&dg_done[tile], ph);
+                tc::tc_fence_after();
                 const int R = tile * 128 + tl;
                 uint32_t r[32];
                 tc::tmem_ld_32x32(tmem + tlane + TM_DG + tile * 64 + h * 32, r);      // cells (dy = h, dx = 0 | 1) x 16 channels
