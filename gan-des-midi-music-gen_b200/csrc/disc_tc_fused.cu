@@ -403,7 +403,8 @@ constexpr int FS_P1 = 29696;                      // 528 rows x 128 B (rows >= 4
 constexpr int FS_W2 = FS_P1 + 67584;              // [4 t][32 oc][64 k] bf16 SW128              16384
 constexpr int FS_W1 = FS_W2 + 16384;              // [2 ty][16 oc][16 k] bf16 SW32              1024
 constexpr int FS_X = FS_W1 + 1024;                // staged u8 input                            12800
-constexpr int FS_TOTAL = FS_X + 12800;            // 127488
+constexpr int FS_WF = FS_X + 12800;               // fc.weight slices, fp32, [8 (h, c4)][432 rows][4]: conflict-free LDS.128   55296
+constexpr int FS_TOTAL = FS_WF + 8 * 432 * 16;    // 182784
 constexpr uint32_t TF_C1 = 0, TF_C2 = 256;        // TMEM: conv1 14 x 16 columns, conv2 4 x 32 columns
 
 struct FusedFwdArgs {
@@ -495,45 +496,62 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
         const int q = warp & 3, h = (warp - 2) >> 2, tl = q * 32 + lane, w = threadIdx.x - 64;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const uint32_t xs_s = tc::smem_u32(smem + FS_XS), p1_s = tc::smem_u32(smem + FS_P1), x_s = tc::smem_u32(smem + FS_X);
-        float b1r[16], b2r[16], wreg[4][16];
+        float b1r[16], b2r[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) { b1r[c] = a.b1[c]; b2r[c] = a.b2[h * 16 + c]; }
-#pragma unroll
-        for (int tile = 0; tile < 4; ++tile) {                        // fc.weight slice of this thread's rows (junk rows carry 0)
-            const int R = tile * 128 + tl;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 v = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32 + h * 16)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                wreg[tile][4 * c4] = v.x; wreg[tile][4 * c4 + 1] = v.y; wreg[tile][4 * c4 + 2] = v.z; wreg[tile][4 * c4 + 3] = v.w;
-            }
+        const uint32_t wf_s = tc::smem_u32(smem + FS_WF);
+        for (int idx = w; idx < 8 * 432; idx += FB_WORKERS) {         // fc.weight (junk rows carry 0) -> shared memory, once per CTA
+            const int g = idx / 432, R = idx - g * 432;
+            const float4 v = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+            tc::sts128(wf_s + idx * 16, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const float bfc = a.bfc[0];
         // ---- S1: XS rows (8 values = (dy,dx,ch) of super pixel (sy,sx) of the zero-padded input), to shared memory and to global
         auto build_xs = [&](int it) {
             const int b = blockIdx.x + it * gridDim.x;
             if (!a.x_f32) tc::mbar_wait(&x_full, (uint32_t)(it & 1));
-            for (int rr = w; rr < XS_ROWS; rr += FB_WORKERS) {
-                const int sy = rr / XS_W, sx = rr - sy * XS_W;
-                const int iy0 = 2 * sy - 1, ix0 = 2 * sx - 1, off0 = iy0 * 50 + ix0;      // element (dy,dx,ch) sits at off0 + dy*50 + dx + ch*6400
-                const bool y0 = iy0 >= 0, y1 = iy0 + 1 < 128, x0 = ix0 >= 0, x1 = ix0 + 1 < 50;
-                uint32_t u[8];
+            if (!a.x_f32) {
+                // all of this thread's byte loads (7 rows x 8) are issued before any is used: one shared-memory latency instead of seven
+                constexpr int NR = (XS_ROWS + FB_WORKERS - 1) / FB_WORKERS;
+                uint32_t u[NR][8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int dy = e >> 2, dx = (e >> 1) & 1, ch = e & 1;
-                    const bool in = (dy ? y1 : y0) && (dx ? x1 : x0);
-                    const int off = off0 + dy * 50 + dx + ch * 6400;
-                    float v;
-                    if (a.x_f32) v = in ? reinterpret_cast<const float*>(a.x)[(size_t)b * 12800 + off] : 0.f;
-                    else v = (float)(in ? tc::lds_u8(x_s + off) : 0u);
-                    u[e] = __float_as_uint(v);
+                for (int i = 0; i < NR; ++i) {
+                    const int rr = w + i * FB_WORKERS;
+                    const int sy = rr / XS_W, sx = rr - sy * XS_W;
+                    const int iy0 = 2 * sy - 1, ix0 = 2 * sx - 1, off0 = iy0 * 50 + ix0;      // element (dy,dx,ch) sits at off0 + dy*50 + dx + ch*6400
+                    const bool row = rr < XS_ROWS, y0 = iy0 >= 0, y1 = iy0 + 1 < 128, x0 = ix0 >= 0, x1 = ix0 + 1 < 50;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int dy = e >> 2, dx = (e >> 1) & 1, ch = e & 1;
+                        const bool in = row && (dy ? y1 : y0) && (dx ? x1 : x0);
+                        u[i][e] = in ? tc::lds_u8(x_s + off0 + dy * 50 + dx + ch * 6400) : 0u;
+                    }
                 }
-                uint4 pk;
-                if (a.x_f32) pk = make_uint4(pack_bf16x2(__uint_as_float(u[0]), __uint_as_float(u[1])), pack_bf16x2(__uint_as_float(u[2]), __uint_as_float(u[3])),
-                                             pack_bf16x2(__uint_as_float(u[4]), __uint_as_float(u[5])), pack_bf16x2(__uint_as_float(u[6]), __uint_as_float(u[7])));
-                else         // integers 0..255 are exact in bf16: the packed pair is just the two high halves
-                    pk = make_uint4(__byte_perm(u[0], u[1], 0x7632), __byte_perm(u[2], u[3], 0x7632), __byte_perm(u[4], u[5], 0x7632), __byte_perm(u[6], u[7], 0x7632));
-                tc::sts128(xs_s + rr * 16, pk);
-                *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int rr = w + i * FB_WORKERS;
+                    if (rr >= XS_ROWS) break;
+                    uint32_t f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __float_as_uint((float)u[i][e]);      // integers 0..255 are exact in bf16 = the high half of the float
+                    const uint4 pk = make_uint4(__byte_perm(f[0], f[1], 0x7632), __byte_perm(f[2], f[3], 0x7632), __byte_perm(f[4], f[5], 0x7632), __byte_perm(f[6], f[7], 0x7632));
+                    tc::sts128(xs_s + rr * 16, pk);
+                    *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+                }
+            } else {
+                for (int rr = w; rr < XS_ROWS; rr += FB_WORKERS) {
+                    const int sy = rr / XS_W, sx = rr - sy * XS_W;
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int iy = 2 * sy + (e >> 2) - 1, ix = 2 * sx + ((e >> 1) & 1) - 1, ch = e & 1;
+                        v[e] = (iy >= 0 && iy < 128 && ix >= 0 && ix < 50) ? reinterpret_cast<const float*>(a.x)[(size_t)b * 12800 + (ch * 128 + iy) * 50 + ix] : 0.f;
+                    }
+                    const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    tc::sts128(xs_s + rr * 16, pk);
+                    *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+                }
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&xs_ready);
@@ -592,13 +610,19 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                 const int oy = R / P1_W, ox = R - oy * P1_W;
                 const bool real = oy < 32 && ox < 12;                 // junk rows of the row space are stored as zeros
                 uint32_t o[8];
+                float wv[16];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const uint4 q4 = tc::lds128(wf_s + ((h * 4 + c4) * 432 + R) * 16);
+                    wv[4 * c4] = __uint_as_float(q4.x); wv[4 * c4 + 1] = __uint_as_float(q4.y); wv[4 * c4 + 2] = __uint_as_float(q4.z); wv[4 * c4 + 3] = __uint_as_float(q4.w);
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float z0 = __uint_as_float(r[2 * c]) + b2r[2 * c], z1 = __uint_as_float(r[2 * c + 1]) + b2r[2 * c + 1];
                     z0 = fmaxf(z0, 0.2f * z0); z1 = fmaxf(z1, 0.2f * z1);
                     o[c] = real ? pack_bf16x2(z0, z1) : 0u;
-                    dot = fmaf(bf_lo(o[c]), wreg[tile][2 * c], dot);                      // the bf16 values the backward will read
-                    dot = fmaf(bf_hi(o[c]), wreg[tile][2 * c + 1], dot);
+                    dot = fmaf(bf_lo(o[c]), wv[2 * c], dot);                              // the bf16 values the backward will read
+                    dot = fmaf(bf_hi(o[c]), wv[2 * c + 1], dot);
                 }
                 uint4* dst = reinterpret_cast<uint4*>(a.a2 + ((size_t)b * P1_ROWS + R) * 32 + h * 16);
                 dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
