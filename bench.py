@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="N > 1: generator BatchNorm over the global batch (statistics all-reduced between the layer kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -176,21 +176,40 @@ def out_width(start, end):
     return N.lib().mmg_raster_out_width(int(start), int(end))
 
 
-def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, out_dtype=torch.float32, status=False):
+def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, out_dtype=torch.float32, status=False, out=None, workspace=None):
     """Device-resident batch rasterisation: ``dt`` (E,) float64, ``meta`` (E,) int32-typed packed u32,
-    ``offsets`` (S+1,) int64, all CUDA tensors -> (S, 2, 128, Wout) tensor of ``out_dtype``."""
+    ``offsets`` (S+1,) int64, all CUDA tensors -> (S, 2, 128, Wout) tensor of ``out_dtype``.
+    ``out`` (a contiguous (S,2,128,Wout) CUDA tensor, its dtype wins) and ``workspace`` (uint8, at least
+    ``raster_workspace_bytes(S, E)``) let a caller that rasterises every step reuse its buffers (no allocation on the stream)."""
     N.require_cuda(dt, meta, offsets)
     if end - start < 0:
         raise ValueError("end-start must be >= 0")
     S, E = offsets.numel() - 1, dt.numel()
     Wo = out_width(start, end)
-    out = torch.empty(S, 2, 128, Wo, device=dt.device, dtype=out_dtype)      # the kernel writes every cell
+    if out is None:
+        out = torch.empty(S, 2, 128, Wo, device=dt.device, dtype=out_dtype)      # the kernel writes every cell
+    else:
+        N.require_cuda(out)
+        if tuple(out.shape) != (S, 2, 128, Wo) or not out.is_contiguous() or out.dtype not in _TORCH_OUT:
+            raise ValueError(f"out must be a contiguous {(S, 2, 128, Wo)} float32 / bfloat16 / uint8 tensor")
+        out_dtype = out.dtype
     st = torch.zeros(S, device=dt.device, dtype=torch.int32) if status else None
-    ws_bytes = N.lib().mmg_raster_workspace_bytes(S, E)
-    ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8) if ws_bytes else None
+    ws_bytes = raster_workspace_bytes(S, E)
+    if workspace is None:
+        ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8) if ws_bytes else None
+    else:
+        N.require_cuda(workspace)
+        if workspace.dtype != torch.uint8 or workspace.numel() < ws_bytes:
+            raise ValueError(f"workspace must be a uint8 tensor of at least {ws_bytes} bytes")
+        ws = workspace
     N.call("mmg_raster_piano_roll", N.ptr(dt), N.ptr(meta), N.ptr(offsets), S, E, -1 if sequence_length is None else int(sequence_length),
            int(start), int(end), _TORCH_OUT[out_dtype], N.ptr(out), N.ptr(st), N.ptr(ws), ws_bytes, N.stream())
     return (out, st) if status else out
+
+
+def raster_workspace_bytes(n_songs, n_events):
+    """Scratch bytes the fast path of ``mmg_raster_piano_roll`` wants for a batch of this size."""
+    return int(N.lib().mmg_raster_workspace_bytes(int(n_songs), int(n_events)))
 
 
 def pack_streams(streams, device="cuda"):

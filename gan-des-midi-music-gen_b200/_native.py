@@ -59,7 +59,7 @@ class GenLayerArgs(ctypes.Structure):
                 ("w_packed", _P), ("bias", _P), ("N", _I),
                 ("z_out", _P), ("out_sums", _P), ("y_out", _P),
                 ("out_mode", _I), ("y_sums", _P), ("out_gamma", _P), ("out_beta", _P), ("out_run_mean", _P), ("out_run_var", _P),
-                ("momentum", _F), ("eps", _F), ("update_running", _I), ("M", _L)]
+                ("momentum", _F), ("eps", _F), ("update_running", _I), ("M", _L), ("stat_count", _L)]
 
 
 SIGNATURES.update({

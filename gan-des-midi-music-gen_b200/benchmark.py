@@ -40,6 +40,22 @@ def _synth_rolls_u8(B, W, seed, device):
     return out
 
 
+def _synth_fake_events(B, seed, E=320, T=60.0):
+    """Post-mido message streams of B simulated songs, the form in which the host DES bridge hands its output to ``generate_piano_roll``
+    (sim_log_to_midi.py:277): E messages per song, dt ~ Exp(mean T/E) float64 seconds, 40 % note_on / 40 % note_off / 20 % other, pitch
+    21..108, velocity 0..127.  With the reference's call shape (sequence_length 100, window 50) about 2 % of the roll plane is non-zero,
+    like the synthetic uint8 rolls.  Returns pinned (dt, meta as int32, offsets) host tensors."""
+    rng = np.random.default_rng(seed)
+    n = B * E
+    dt = rng.exponential(T / E, size=n)
+    u = rng.random(n, dtype=np.float32)
+    kind = np.where(u < 0.4, 1, np.where(u < 0.8, 2, 0)).astype(np.uint32)
+    meta = kind | (rng.integers(21, 109, size=n, dtype=np.uint32) << 8) | (rng.integers(0, 128, size=n, dtype=np.uint32) << 16)
+    meta[kind == 0] = 0
+    off = np.arange(B + 1, dtype=np.int64) * E
+    return tuple(torch.from_numpy(a).pin_memory() for a in (dt, meta.view(np.int32), off))
+
+
 def _timed(fn, steps, sync):
     """CUDA-event timing of `steps` calls of fn on the current stream; returns seconds."""
     sync()
@@ -174,7 +190,7 @@ def run(args):
     mmgan = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, W), input_dim=50, output_dim=20, instrument=0, start=100,
                              end=150, device=device)
     mmgan.train()
-    trainer = MMGANTrainer(mmgan, lr=0.01, precision=precision, max_batch=B, inner_rng="device")
+    trainer = MMGANTrainer(mmgan, lr=0.01, precision=precision, max_batch=B, inner_rng="device", sync_bn=getattr(args, "sync_bn", False))
 
     # ---- host (pinned) and device copies of one step's inputs
     h = {k: _synth_rolls_u8(B, W, 100 * rank + i, "cpu").pin_memory() for i, k in enumerate(("real", "fake_d", "fake_g"))}
@@ -185,12 +201,16 @@ def run(args):
     def step_resident(i):
         return trainer.step(noise[0], noise[1], d["beats"], d["real"], d["fake_d"], d["fake_g"], noise[2], noise[3])
 
-    # end-to-end arm: the real rolls / beats are gathered from a training set resident in HBM (indices come from the host sampler),
-    # the fake rolls -- what the host DES bridge returns for the two generator forwards -- are copied H2D every step
+    # end-to-end arm: the real rolls / beats are gathered from a training set resident in HBM (indices come from the host sampler);
+    # the fake songs -- what the host DES bridge produces for the two generator forwards -- arrive from the HOST every step, as note-event
+    # streams rasterised on the device (primary: generate_piano_roll is part of this path) or as ready-made uint8 rolls (secondary)
     ds_n = 2 * B
     dataset = (_synth_rolls_u8(ds_n, W, 7777 + rank, "cpu").to(device), (25.0 * torch.rand(ds_n, 50)).to(device))
-    pipe = HostBatchPipeline(trainer, h, dataset=dataset)
-    hb = [dict(fake_d=h["fake_d"], fake_g=h["fake_g"], real_idx=torch.randint(0, ds_n, (B,)).pin_memory()) for _ in range(4)]
+    pipe_rolls = HostBatchPipeline(trainer, h, dataset=dataset)
+    hb_rolls = [dict(fake_d=h["fake_d"], fake_g=h["fake_g"], real_idx=torch.randint(0, ds_n, (B,)).pin_memory()) for _ in range(4)]
+    ev = [_synth_fake_events(B, 31 * rank + i) for i in range(4)]
+    hb_ev = [dict(fake_d_events=ev[i], fake_g_events=ev[(i + 1) % 4], real_idx=hb_rolls[i]["real_idx"]) for i in range(4)]
+    pipe_ev = HostBatchPipeline(trainer, hb_ev[0], dataset=dataset, raster=(100, 0, W))
 
     def barrier():
         if world > 1:
@@ -214,25 +234,30 @@ def run(args):
     clocks = _b.ClockSampler(local)
     clocks.__enter__()                                   # sampled over the resident and the end-to-end timed regions
     sec, launches = measure(step_resident)
-    # ---- end to end: HOST (pinned) rolls / beats every step through the public API, H2D inside the timed region
-    for _ in pipe.run([hb[i % 4] for i in range(max(args.warmup, 4))]):       # both staging slots reach graph replay before the timed region
-        pass
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in pipe.run([hb[i % 4] for i in range(args.steps)]):
-        pass
-    e1.record()
-    barrier()
-    sec_e2e = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([sec_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec_e2e = t.item()
+    # ---- end to end: HOST (pinned) inputs every step through the public API, H2D inside the timed region
+    def measure_e2e(pipe, hb):
+        for _ in pipe.run([hb[i % 4] for i in range(max(args.warmup, 4))]):      # both staging slots reach graph replay before the timed region
+            pass
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in pipe.run([hb[i % 4] for i in range(args.steps)]):
+            pass
+        e1.record()
+        barrier()
+        s_ = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([s_], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ = t.item()
+        return s_
+
+    sec_e2e = measure_e2e(pipe_ev, hb_ev)
+    sec_e2e_rolls = measure_e2e(pipe_rolls, hb_rolls)
     clocks.__exit__(None, None, None)
     rolls = B * world * args.steps
     value, e2e = rolls / sec, rolls / sec_e2e
-    h2d = pipe.h2d_bytes
+    h2d = pipe_ev.h2d_bytes
 
     # ---- roofline of the dominant kernel, timed alone on this stream with CUDA events (after the step measurements: it touches D's grads)
     MAC_FWD, MAC_BWD = 3977216, 7135232                      # per roll and D pass
@@ -276,11 +301,16 @@ def run(args):
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": "MM-GAN G+D training iteration (network_tests.py:292-315), DES excluded", "batch_per_gpu": B, "global_batch": B * world,
-                       "roll_size": [2, 128, W], "adj_size": [64, 64], "z_dim": 50, "parallelism": f"dp{world}", "precision": precision, "cuda_graph": bool(trainer.use_graph),
+                       "roll_size": [2, 128, W], "adj_size": [64, 64], "z_dim": 50, "parallelism": f"dp{world}", "precision": precision, "cuda_graph": bool(trainer.use_graph), "generator_bn": "sync (global batch)" if trainer.sync_bn else "per-replica",
                        "l2": "inputs larger than L2 (per-step working set > 126 MB)" if B * 3 * 12800 > 126e6 else "working set may fit L2"},
             "e2e": {"value": e2e, "unit": "rolls/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": sec_e2e / args.steps * 1e3,
-                    "api": "trainer.HostBatchPipeline.run: pinned host batches (fake rolls u8 from the DES bridge + sampler indices), real rolls / beats gathered from the "
-                           "HBM-resident training set, H2D of batch i+1 overlapped with the iteration of batch i"},
+                    "api": "trainer.HostBatchPipeline.run: pinned host batches = the note-event streams of the simulated songs (what the DES bridge hands to "
+                           "generate_piano_roll: 320 messages per song, 12 B per message) + sampler indices; events copied H2D and rasterised on the device "
+                           "(mmg_raster_piano_roll, bit-exact) into the uint8 fake rolls, real rolls / beats gathered from the HBM-resident training set, "
+                           "copies + rasterisation of batch i+1 overlapped with the iteration of batch i; losses read back every step",
+                    "rolls_u8_variant": {"value": rolls / sec_e2e_rolls, "unit": "rolls/s", "h2d_bytes_per_step": pipe_rolls.h2d_bytes,
+                                         "ms_per_step": sec_e2e_rolls / args.steps * 1e3,
+                                         "api": "same pipeline fed with ready-made uint8 fake rolls (12.8 KB per roll over PCIe)"}},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline}
 
     if rank == 0 and world == 1:

@@ -39,6 +39,7 @@ struct GenDev {
     const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
     float momentum, eps; int update_running;
     long long M; int row_tiles;
+    double cnt;                                 // rows behind the batch sums (= M, or the global batch under SyncBN)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -111,9 +112,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             float sc, sh;
             if (a.in_mode == 1) {
                 float mu, var;
-                bn_scale_shift(a.in_sums[k], a.in_sums[a.K + k], (double)a.M, a.in_gamma[k], a.in_beta[k], a.eps, sc, sh, mu, var);
+                bn_scale_shift(a.in_sums[k], a.in_sums[a.K + k], a.cnt, a.in_gamma[k], a.in_beta[k], a.eps, sc, sh, mu, var);
                 if (a.update_running && blockIdx.x == 0 && a.in_run_mean) {
-                    const float unb = var * (float)((double)a.M / ((double)a.M - 1.0));
+                    const float unb = var * (float)(a.cnt / (a.cnt - 1.0));
                     a.in_run_mean[k] = (1.f - a.momentum) * a.in_run_mean[k] + a.momentum * mu;
                     a.in_run_var[k] = (1.f - a.momentum) * a.in_run_var[k] + a.momentum * unb;
                 }
@@ -222,9 +223,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                     if (n < a.N) {
                         if (a.out_mode == 1) {
                             float mu, var;
-                            bn_scale_shift(a.y_sums[n], a.y_sums[a.N + n], (double)a.M, a.out_gamma[n], a.out_beta[n], a.eps, sc, sh, mu, var);
+                            bn_scale_shift(a.y_sums[n], a.y_sums[a.N + n], a.cnt, a.out_gamma[n], a.out_beta[n], a.eps, sc, sh, mu, var);
                             if (a.update_running && rt == 0 && a.out_run_mean) {       // exactly one item owns (row tile 0, column n)
-                                const float unb = var * (float)((double)a.M / ((double)a.M - 1.0));
+                                const float unb = var * (float)(a.cnt / (a.cnt - 1.0));
                                 a.out_run_mean[n] = (1.f - a.momentum) * a.out_run_mean[n] + a.momentum * mu;
                                 a.out_run_var[n] = (1.f - a.momentum) * a.out_run_var[n] + a.momentum * unb;
                             }
@@ -355,14 +356,14 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
         MMG_REQUIRE(p->k1 == 0 && (K & 7) == 0 && ((uintptr_t)p->x0 & 15) == 0, MMG_EUNSUPPORTED, "gen_layer_fwd: BN prologue needs one 16-byte-aligned input with K % 8 == 0");
         MMG_REQUIRE(p->in_gamma && p->in_beta, MMG_EINVAL, "gen_layer_fwd: missing input BN affine");
         MMG_REQUIRE(p->in_mode == 1 ? p->in_sums != nullptr : (p->in_run_mean && p->in_run_var), MMG_EINVAL, "gen_layer_fwd: missing input BN statistics");
-        MMG_REQUIRE(p->in_mode != 1 || p->M > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, K);
+        MMG_REQUIRE(p->in_mode != 1 || (p->stat_count > 0 ? p->stat_count : p->M) > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, K);
     } else {
         MMG_REQUIRE(p->k1 == 0 || p->x1, MMG_EINVAL, "gen_layer_fwd: missing second input");
     }
     if (p->y_out) {
         MMG_REQUIRE(p->out_gamma && p->out_beta && (p->out_mode == 1 ? p->y_sums != nullptr : (p->out_mode == 2 && p->out_run_mean && p->out_run_var)), MMG_EINVAL,
                     "gen_layer_fwd: missing output BN parameters");
-        MMG_REQUIRE(p->out_mode != 1 || p->M > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, p->N);
+        MMG_REQUIRE(p->out_mode != 1 || (p->stat_count > 0 ? p->stat_count : p->M) > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)p->M, p->N);
     }
     GenDev a;
     a.x0 = p->x0; a.x1 = p->x1; a.k0 = p->k0; a.k1 = p->k1; a.in_mode = p->in_mode;
@@ -373,6 +374,7 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     a.z_out = p->z_out; a.out_sums = p->out_sums; a.y_out = p->y_out; a.out_mode = p->out_mode; a.y_sums = p->y_sums;
     a.out_gamma = p->out_gamma; a.out_beta = p->out_beta; a.out_run_mean = p->out_run_mean; a.out_run_var = p->out_run_var;
     a.momentum = p->momentum; a.eps = p->eps; a.update_running = p->update_running; a.M = p->M;
+    a.cnt = (double)(p->stat_count > 0 ? p->stat_count : p->M);
     const long long row_tiles = (p->M + 127) / 128;
     MMG_REQUIRE(row_tiles * a.n_groups < (1LL << 30), MMG_EUNSUPPORTED, "gen_layer_fwd: batch too large");
     a.row_tiles = (int)row_tiles;

@@ -5,6 +5,9 @@ network_tests.py:58-123): it owns the packed bf16 weights, the fp32 pre-activati
 fp64 batch-sum buffers, and runs the 4-block stack as 5 launches of ``mmg_gen_layer_fwd`` (csrc/gen_tc.cu): one per
 layer, the last layer twice (batch sums, then normalise + sigmoid + the single write of the output).  Training mode
 updates ``running_mean`` / ``running_var`` / ``num_batches_tracked`` in place like ``nn.BatchNorm1d``.
+Data parallel: ``sync_bn=True`` with an initialised process group all-reduces every layer's fp64 column sums between the
+layer kernels (4 collectives of <= 64 KB per forward) and normalises with the GLOBAL batch count, so that the sharded run
+reproduces the single-process global-batch BatchNorm of the reference; default = per-replica statistics.
 Forward only: the reference never back-propagates into the generators; the fp32 modules keep the
 differentiable path.
 """
@@ -16,8 +19,12 @@ from . import _native as N
 
 
 class GenTC:
-    def __init__(self, gen, max_batch):
+    def __init__(self, gen, max_batch, process_group=None, sync_bn=False):
         self.g = gen
+        dist = torch.distributed
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (sync_bn and dist.is_available() and dist.is_initialized()) else 1
+        self.sync_bn = bool(sync_bn) and self.world > 1
         self.blocks = [(blk[0], blk[1]) for blk in gen.gen]            # (Linear, BatchNorm1d)
         dev = self.blocks[0][0].weight.device
         N.require_cuda(self.blocks[0][0].weight)
@@ -46,6 +53,11 @@ class GenTC:
             N.call("mmg_gen_pack_weight", N.ptr(lin.weight.data), lin.out_features, lin.in_features, N.ptr(pk), N.stream())
         self._versions = vers
 
+    def _sync(self, i):
+        """SyncBN: sum layer i's batch sums over the ranks (every rank holds an equal shard)."""
+        if self.sync_bn:
+            torch.distributed.all_reduce(self.sum_views[i], group=self.pg)
+
     def forward(self, noise, input_tensor, training=None, out=None):
         """noise (B,z) and input_tensor (B,input_dim) fp32 CUDA tensors -> (B, out_features) fp32 (caller reshapes)."""
         N.require_cuda(noise, input_tensor)
@@ -53,7 +65,7 @@ class GenTC:
         B = noise.shape[0]
         if B > self.cap:
             raise ValueError(f"batch {B} exceeds the preallocated capacity {self.cap}")
-        if training and B <= 1:
+        if training and B * self.world <= 1:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {(B, self.widths[0])}")
         noise, input_tensor = noise.float().contiguous(), input_tensor.float().contiguous()
         self.pack(force=False)
@@ -76,17 +88,21 @@ class GenTC:
             a.w_packed, a.bias, a.N = N.ptr(self.packed[i]), N.ptr(lin.bias.data), lin.out_features
             a.momentum = bn.momentum if bn.momentum is not None else 0.1
             a.eps, a.M = bn.eps, B
+            a.stat_count = B * self.world if training else 0
             a.update_running = int(training)
             if i < last:
                 a.z_out = N.ptr(self.z[i])
                 a.out_sums = N.ptr(self.sum_views[i]) if training else None
                 N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
+                if training:
+                    self._sync(i)
             else:
                 a.out_gamma, a.out_beta = N.ptr(bn.weight.data), N.ptr(bn.bias.data)
                 a.out_run_mean, a.out_run_var = N.ptr(bn.running_mean), N.ptr(bn.running_var)
                 if training:                       # pass 1: batch sums only (also the one update of the previous layer's running stats)
                     a.out_sums = N.ptr(self.sum_views[i])
                     N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
+                    self._sync(i)
                     a.out_sums = None
                     a.in_run_mean = a.in_run_var = None      # already updated by pass 1
                 a.y_out, a.out_mode = N.ptr(y), mode

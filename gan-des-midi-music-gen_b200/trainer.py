@@ -14,7 +14,7 @@ precision='fp32' : the drop-in nn.Modules + autograd over the fp32 SIMT kernels 
 precision='bf16' : discriminator on the tcgen05 tensor-core kernels (disc_tc.DiscTC): bf16 operands,
                    fp32 accumulation, fp32 master weights / Adam state; fused BCE and multi-tensor Adam.
 CUDA graphs (``use_graph=True``, default for bf16): after one eager iteration on the same input buffers the iteration
-is captured (one graph, or three around the asynchronous NCCL all-reduce when sharded) and later calls with the same buffers replay
+is captured (one graph, or four around the asynchronous NCCL all-reduce when sharded) and later calls with the same buffers replay
 it: one launch per iteration instead of ~100.  Adam's step count and learning rate live in device memory for that
 (``mmg_adam_multi_tensor_dev_f32``), so ``StepLR`` keeps working.
 ``inner_rng``: the reference's Generator draws its second input with ``torch.randn`` on the CPU generator inside forward
@@ -22,6 +22,8 @@ it: one launch per iteration instead of ~100.  Adam's step count and learning ra
 Data parallel: with torch.distributed initialised (NCCL) the batch is sharded by rank, the D gradients
 live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step, asynchronously, overlapped with the G step's
 generator forwards (the 1/world factor is folded into the Adam kernel); the G-step D grads are not reduced (the reference discards them).
+``sync_bn=True`` (bf16 path): the generators' train-mode BatchNorm uses GLOBAL-batch statistics (fp64 column sums all-reduced between the
+layer kernels, gen_tc.GenTC), reproducing the reference's single-process batch; default False = per-replica statistics (torch-DDP semantics).
 """
 import ctypes
 
@@ -43,7 +45,7 @@ def shard_batch(t, rank, world):
 
 class MMGANTrainer:
     def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None, use_graph=None,
-                 inner_rng="reference"):
+                 inner_rng="reference", sync_bn=False):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.m = mmgan
@@ -64,6 +66,9 @@ class MMGANTrainer:
         dist = torch.distributed
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.on_d_grads = None
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        if self.sync_bn and precision != "bf16":
+            raise ValueError("sync_bn is implemented on the bf16 tensor-core generator path (precision='bf16')")
         self.tc = None
         self._g_out = None
         self._side = torch.cuda.Stream(device=self.d_params[0].device) if precision == "bf16" else None
@@ -73,8 +78,8 @@ class MMGANTrainer:
             from .disc_tc import DiscTC
             from .gen_tc import GenTC
             self.tc = DiscTC(D, max_batch)
-            self.gtc1 = GenTC(mmgan.generator1, max_batch)
-            self.gtc2 = GenTC(mmgan.generator2, max_batch)
+            self.gtc1 = GenTC(mmgan.generator1, max_batch, process_group, self.sync_bn)
+            self.gtc2 = GenTC(mmgan.generator2, max_batch, process_group, self.sync_bn)
         dev = self.flat_grad.device
         if inner_rng not in ("reference", "device"):
             raise ValueError("inner_rng must be 'reference' or 'device'")
@@ -144,13 +149,18 @@ class MMGANTrainer:
                 if self._g_out is None or self._g_out[0].shape[0] != B:
                     self._g_out = (torch.empty(B, self.gtc1.widths[-1], device=noise1.device), torch.empty(B, self.gtc2.widths[-1], device=noise1.device))
                 a = m.generator1.adj_size
-                # the two generators are independent: the beat generator runs on a side stream (fork / join, also under graph capture)
-                cur = torch.cuda.current_stream()
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
+                if self.sync_bn:
+                    # SyncBN: the statistics all-reduces sit between the layer kernels; both generators on this stream (one collective order)
                     self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
-                self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
-                cur.wait_stream(self._side)
+                    self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
+                else:
+                    # the two generators are independent: the beat generator runs on a side stream (fork / join, also under graph capture)
+                    cur = torch.cuda.current_stream()
+                    self._side.wait_stream(cur)
+                    with torch.cuda.stream(self._side):
+                        self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
+                    self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
+                    cur.wait_stream(self._side)
             else:
                 self.g1_out = m.generator1(noise1, inner)
                 self.g2_out = m.generator2(noise2, beats)
@@ -175,16 +185,23 @@ class MMGANTrainer:
         return logits.detach()
 
     # ------------------------------------------------------------------ one iteration
-    def _seg_d(self, noise1, noise2, beats, real, fake_d, inner_d):
-        """D step up to the gradients (:293-307)"""
-        self._zero_d_grads()
+    def _seg_d_gen(self, noise1, noise2, beats, real, fake_d, inner_d):
+        """The D step's generator forwards (:294 -> :177-178)"""
         self._generators(noise1, noise2, beats, inner_d)
+
+    def _seg_d_disc(self, noise1, noise2, beats, real, fake_d, inner_d):
+        """D step up to the gradients (:293, :304-307)"""
+        self._zero_d_grads()
         self.logit_fake_d = self._d_pass(fake_d, 0.0, self.loss_d, False)
         if self.tc is not None:
             self.logit_fake_d = self.logit_fake_d.clone()
         self.logit_real = self._d_pass(real, 1.0, self.loss_d, True)
         if self.tc is not None:
             self.logit_real = self.logit_real.clone()
+
+    def _seg_d(self, *a):
+        self._seg_d_gen(*a)
+        self._seg_d_disc(*a)
 
     def _seg_g_gen(self, noise1, noise2, beats, fake_g, inner_g):
         """The G step's generator forwards (:312 -> :177-178).  They depend on nothing the D step produces (generator weights never change, SURVEY
@@ -225,8 +242,10 @@ class MMGANTrainer:
                     self.graph_launches = 0
                     if self.world == 1:
                         graphs = (self._capture(lambda: (self._seg_d(*a_d), self._seg_g_gen(*a_g), self._seg_g(*a_g))),)
-                    else:
-                        graphs = (self._capture(self._seg_d, *a_d), self._capture(self._seg_g_gen, *a_g), self._capture(self._seg_g, *a_g))
+                    else:       # sharded: graphs around the asynchronous D-gradient all-reduce; SyncBN generators (collectives between kernels) stay eager
+                        eager_gen = self.sync_bn
+                        graphs = (None if eager_gen else self._capture(self._seg_d_gen, *a_d), self._capture(self._seg_d_disc, *a_d),
+                                  None if eager_gen else self._capture(self._seg_g_gen, *a_g), self._capture(self._seg_g, *a_g))
                     self._graphs[key] = graphs       # capture does not execute: fall through to the replay below
         self._sync_hyper()
         if graphs is None:
@@ -240,12 +259,16 @@ class MMGANTrainer:
             self._seg_g(*a_g)
         else:
             self.replayed_launches += self.graph_launches
-            graphs[0].replay()
-            if len(graphs) == 3:
+            if len(graphs) == 1:
+                graphs[0].replay()
+            else:
+                gd_gen, gd, gg_gen, gg = graphs
+                gd_gen.replay() if gd_gen is not None else self._seg_d_gen(*a_d)
+                gd.replay()
                 work = self._allreduce_d_grads(async_op=True)
-                graphs[1].replay()
+                gg_gen.replay() if gg_gen is not None else self._seg_g_gen(*a_g)
                 work.wait()
-                graphs[2].replay()
+                gg.replay()
         self.gen_opt.step()          # no-op: generator grads are None
         return self.loss_d[0], self.loss_g[0]
 
@@ -259,33 +282,75 @@ class HostBatchPipeline:
     ``dataset=(rolls, beats)``: the training set resident in HBM -- ``rolls`` (N,2,128,W) uint8/float32 and ``beats`` (N,50)
     CUDA tensors (the reference's ``MaestroDatasetPickle(..., device=device)`` also keeps its items on the device,
     datasets.py:73-87; 5.4 k MAESTRO slices are 69 MB).  A batch then carries ``real_idx`` (host int64 indices, what a
-    sampler yields) instead of ``real`` / ``beats``; the gather runs on the copy stream.  The fake rolls always come from the host."""
+    sampler yields) instead of ``real`` / ``beats``; the gather runs on the copy stream.  The fake rolls always come from the host:
+
+    * as rolls: ``fake_d`` / ``fake_g`` (B,2,128,W) uint8 / float32 (what ``matrix_to_midi`` returns, matrix_sim_process.py:191-195), or
+    * as note events: ``fake_d_events`` / ``fake_g_events`` = ``(dt float64 (E,), meta int32 (E,), offsets int64 (B+1,))`` pinned tensors, the
+      post-mido message streams of the B simulated songs (what ``process_adjsim_log`` hands to ``generate_piano_roll``,
+      sim_log_to_midi.py:277).  They are copied H2D (12 bytes per message instead of 12.8 KB per roll) and rasterised on the device by
+      ``mmg_raster_piano_roll`` straight into the uint8 roll buffers the discriminator kernels read -- bit-exact with the host rasterisation
+      (SURVEY 8f-3).  ``raster=(sequence_length, start, end)`` are ``generate_piano_roll``'s arguments; ``max_events`` bounds E per pass."""
 
     KEYS = ("beats", "real", "fake_d", "fake_g")
 
-    def __init__(self, trainer, example, dataset=None):
+    def __init__(self, trainer, example, dataset=None, max_events=None, raster=(100, 0, 50)):
         self.t = trainer
         dev = trainer.flat_grad.device
         self.dataset = dataset
-        B = example["fake_d"].shape[0]
+        self.events = "fake_d_events" in example
+        self.raster = tuple(int(v) for v in raster)
+        if self.events:
+            from .MMGAN_MIDI_DES import datasets as ds
+            self._ds = ds
+            B = example["fake_d_events"][2].numel() - 1
+            W = ds.out_width(self.raster[1], self.raster[2])
+            cap = int(max_events if max_events is not None else max(example[k][0].numel() for k in ("fake_d_events", "fake_g_events")))
+            self.max_events = cap
+            roll = lambda: torch.empty(B, 2, 128, W, dtype=torch.uint8, device=dev)
+            ev = lambda: (torch.empty(cap, dtype=torch.float64, device=dev), torch.empty(cap, dtype=torch.int32, device=dev),
+                          torch.empty(B + 1, dtype=torch.int64, device=dev))
+            self.ws = [torch.empty(ds.raster_workspace_bytes(B, cap), dtype=torch.uint8, device=dev) for _ in range(2)]
+        else:
+            B = example["fake_d"].shape[0]
+            roll = None
+        fake = (lambda k: roll()) if self.events else (lambda k: torch.empty_like(example[k], device=dev))
         if dataset is not None:
             rolls, beats = dataset
             N.require_cuda(rolls, beats)
-            self.copy_keys = ("fake_d", "fake_g")
-            self.stage = [{"fake_d": torch.empty_like(example["fake_d"], device=dev), "fake_g": torch.empty_like(example["fake_g"], device=dev),
+            self.copy_keys = () if self.events else ("fake_d", "fake_g")
+            self.stage = [{"fake_d": fake("fake_d"), "fake_g": fake("fake_g"),
                            "real": torch.empty((B,) + tuple(rolls.shape[1:]), dtype=rolls.dtype, device=dev),
                            "beats": torch.empty((B,) + tuple(beats.shape[1:]), dtype=beats.dtype, device=dev),
                            "idx": torch.empty(B, dtype=torch.int64, device=dev)} for _ in range(2)]
             self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.copy_keys) + B * 8
         else:
-            self.copy_keys = self.KEYS
-            self.stage = [{k: torch.empty_like(example[k], device=dev) for k in self.KEYS} for _ in range(2)]
-            self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.KEYS)
+            self.copy_keys = ("beats", "real") if self.events else self.KEYS
+            self.stage = [{k: (fake(k) if k.startswith("fake") else torch.empty_like(example[k], device=dev)) for k in self.KEYS} for _ in range(2)]
+            self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.copy_keys)
+        if self.events:
+            for st in self.stage:
+                st["ev_d"], st["ev_g"] = ev(), ev()
+            self.h2d_bytes += sum(t.numel() * t.element_size() for k in ("fake_d_events", "fake_g_events") for t in example[k])
         self.noise = [[torch.empty(B, trainer.m.z_dim, device=dev) for _ in range(2)] for _ in range(2)]     # static: graph replay
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         self.losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def _raster(self, slot, dev_ev, host_ev, out):
+        """H2D of one pass's message streams + device rasterisation into the pass's uint8 roll buffer (on the copy stream)."""
+        dt, meta, off = host_ev
+        E = dt.numel()
+        if E > self.max_events:
+            raise ValueError(f"{E} messages exceed the pipeline's max_events = {self.max_events}")
+        if off.numel() != dev_ev[2].numel():
+            raise ValueError("offsets must have batch + 1 entries")
+        d_dt, d_meta = dev_ev[0][:E], dev_ev[1][:E]
+        d_dt.copy_(dt, non_blocking=True)
+        d_meta.copy_(meta, non_blocking=True)
+        dev_ev[2].copy_(off, non_blocking=True)
+        S, a, b = self.raster
+        self._ds.rasterize_events(d_dt, d_meta, dev_ev[2], S, a, b, out=out, workspace=self.ws[slot])
 
     def _issue(self, slot, batch, first_use):
         with torch.cuda.stream(self.copy_stream):
@@ -294,6 +359,9 @@ class HostBatchPipeline:
             st = self.stage[slot]
             for k in self.copy_keys:
                 st[k].copy_(batch[k], non_blocking=True)
+            if self.events:
+                self._raster(slot, st["ev_d"], batch["fake_d_events"], st["fake_d"])
+                self._raster(slot, st["ev_g"], batch["fake_g_events"], st["fake_g"])
             if self.dataset is not None:
                 st["idx"].copy_(batch["real_idx"], non_blocking=True)
                 torch.index_select(self.dataset[0], 0, st["idx"], out=st["real"])

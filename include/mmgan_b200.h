@@ -143,6 +143,7 @@ typedef struct mmg_gen_layer_args {
     float* z_out; double* out_sums; float* y_out;
     int out_mode; const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
     float momentum; float eps; int update_running; int64_t M;
+    int64_t stat_count;   /* rows behind in_sums / y_sums; 0 = M.  Data parallel SyncBN: the caller all-reduces the sums and passes the global batch */
 } mmg_gen_layer_args;
 size_t mmg_gen_packed_weight_bytes(int N, int K);
 int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream);

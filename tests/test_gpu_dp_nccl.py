@@ -1,0 +1,108 @@
+"""Two-GPU (NCCL) checks of the data-parallel path: the sharded run must reproduce the single-process global batch.
+
+* SyncBN generators (gen_tc.GenTC(sync_bn=True)): outputs and running statistics of a batch split over 2 ranks == one GenTC over the whole
+  batch (the fp64 column sums are all-reduced between the layer kernels; same bf16 operands, so the tolerance is fp32 summation order).
+* MMGANTrainer(sync_bn=True) over 2 ranks: summed D-step gradients / world, averaged losses and post-Adam discriminator weights == the
+  single-process iteration on the global batch (D has no BatchNorm, mean-loss gradients are the average of shard gradients).
+Skipped on a box with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mmgan_oracle as mo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mk(device, seed=4):
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device=device)
+    m.load_state_dict(mo.synth_state(mo.mmgan_shapes(), seed=seed, d_scale=0.25))
+    return m.train()
+
+
+def _worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gan_des_midi_music_gen_b200.gen_tc import GenTC
+        from gan_des_midi_music_gen_b200.trainer import MMGANTrainer, shard_batch
+        Bg = 512
+        inp = {k: v.to(dev) for k, v in mo.synth_inputs(Bg, seed=9).items()}
+        mine = {k: shard_batch(v, rank, world).contiguous() for k, v in inp.items()}
+        out = {}
+        # ---- SyncBN generator forward vs the global batch on one GPU
+        m_dp, m_one = _mk(dev), _mk(dev)
+        g_dp = GenTC(m_dp.generator1, Bg // world, sync_bn=True)
+        assert g_dp.sync_bn and g_dp.world == world
+        y_dp = g_dp.forward(mine["noise1"], mine["inner_d"], training=True).clone()
+        y_one = GenTC(m_one.generator1, Bg).forward(inp["noise1"], inp["inner_d"], training=True)
+        out["gen_out"] = (y_dp - shard_batch(y_one, rank, world)).abs().max().item()
+        out["gen_run"] = max((a.running_mean - b.running_mean).abs().max().item() + (a.running_var - b.running_var).abs().max().item()
+                             for (_, a), (_, b) in zip(g_dp.blocks, [(blk[0], blk[1]) for blk in m_one.generator1.gen]))
+        # per-replica statistics must differ from the global ones (the flag does something)
+        y_loc = GenTC(_mk(dev).generator1, Bg // world).forward(mine["noise1"], mine["inner_d"], training=True)
+        out["gen_local_diff"] = (y_loc - shard_batch(y_one, rank, world)).abs().max().item()
+        # ---- one training iteration, sharded with SyncBN (graph replay on the 3rd call) vs single process
+        res = {}
+        for mode in ("dp", "one"):
+            m = _mk(dev)
+            if mode == "dp":
+                tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=Bg // world, sync_bn=True)
+                d = mine
+            else:
+                tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=Bg, process_group=None, use_graph=False)
+                tr.world = 1                                     # the reference run: whole batch, no collectives
+                d = inp
+            losses = []
+            for it in range(3):
+                dl, gl = tr.step(d["noise1"], d["noise2"], d["beats"], d["real"], d["fake_d"], d["fake_g"], d["inner_d"], d["inner_g"])
+                losses.append(torch.stack([dl, gl]).clone())
+            torch.cuda.synchronize()
+            ls = torch.stack(losses)
+            if mode == "dp":
+                dist.all_reduce(ls)
+                ls /= world
+                assert any(len(g) == 4 for g in tr._graphs.values()), "sharded iteration was not captured"
+            res[mode] = (ls.cpu(), [p.detach().clone() for p in m.discriminator.parameters()], m.generator1.gen[3][1].running_var.clone(), tr.g2_out.clone())
+        out["loss"] = (res["dp"][0] - res["one"][0]).abs().max().item() / max(1.0, res["one"][0].abs().max().item())
+        out["loss0"] = (res["dp"][0][0] - res["one"][0][0]).abs().max().item() / max(1.0, res["one"][0][0].abs().max().item())
+        out["par"] = max((a - b).abs().max().item() for a, b in zip(res["dp"][1], res["one"][1]))
+        out["run_var"] = (res["dp"][2] - res["one"][2]).abs().max().item()
+        out["g2"] = (res["dp"][3] - shard_batch(res["one"][3], rank, world)).abs().max().item()
+        q.put((rank, out, None))
+    except Exception as e:       # pragma: no cover
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sync_bn_and_sharded_iteration_match_global_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, out, err in res:
+        assert err is None, err
+        assert out["gen_out"] < 2e-3, out                  # same bf16 operands; fp32/fp64 summation order only
+        assert out["gen_run"] < 1e-4, out
+        assert out["gen_local_diff"] > 10 * max(out["gen_out"], 1e-6), out
+        assert out["loss0"] < 2e-3, out                    # first iteration: identical weights on both sides
+        assert out["loss"] < 5e-2, out                     # later iterations pass through Adam's sign-sensitive first steps (see test_gpu_trainer)
+        assert out["par"] <= 3 * 0.01 * 2 + 1e-6, out
+        assert out["run_var"] < 1e-4 and out["g2"] < 5e-3, out

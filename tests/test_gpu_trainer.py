@@ -198,6 +198,58 @@ def test_host_batch_pipeline_matches_direct_steps(resident):
     assert torch.allclose(res["pipeline"], res["direct"], rtol=5e-3, atol=1e-4), (res["pipeline"], res["direct"])
 
 
+def test_host_batch_pipeline_event_streams_match_host_rasterised_rolls():
+    """the pipeline fed with the simulated songs' note-event streams (H2D of 12 B / message + device rasterisation into the
+    uint8 fake-roll buffers) must give the discriminator bit-identical rolls, and therefore the same losses, as the pipeline fed with rolls
+    rasterised on the host by the oracle (= the reference's generate_piano_roll, datasets.py:27-54)."""
+    import raster_oracle as ro
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import HostBatchPipeline, MMGANTrainer
+    B, NDS, E = 48, 100, 200
+    g = torch.Generator().manual_seed(5)
+    mk = lambda n: ((torch.rand(n, 2, 128, 50, generator=g) < 0.03) * torch.randint(1, 128, (n, 2, 128, 50), generator=g)).to(torch.uint8)
+    ds_rolls, ds_beats = mk(NDS), 25 * torch.rand(NDS, 50, generator=g)
+
+    def events(seed, n_events):
+        dt, meta, off = ro.synth_songs(B, n_events, 70.0, seed=seed, p_on=0.4, p_off=0.4)      # some songs run past the 50-step window / step 100
+        host_roll, _ = ro.raster_batch_c(dt, meta, off, 100, 0, 50)
+        assert host_roll.max() <= 255
+        ev = tuple(torch.from_numpy(a).pin_memory() for a in (dt, meta.view(np.int32), off))
+        return ev, torch.from_numpy(host_roll).to(torch.uint8).pin_memory()
+
+    batches = []
+    for i in range(5):
+        ev_d, roll_d = events(100 + i, E - 7 * i)               # E varies from batch to batch (ragged staging)
+        ev_g, roll_g = events(200 + i, E - 3 * i)
+        batches.append(dict(fake_d_events=ev_d, fake_g_events=ev_g, fake_d=roll_d, fake_g=roll_g,
+                            real_idx=torch.randint(0, NDS, (B,), generator=g).pin_memory()))
+    res, staged = {}, {}
+    for mode in ("events", "rolls"):
+        torch.manual_seed(21)
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150,
+                             device=DEV).train()
+        tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=B, inner_rng="device")
+        torch.manual_seed(22)
+        keys = ("fake_d_events", "fake_g_events") if mode == "events" else ("fake_d", "fake_g")
+        feed = [{k: b[k] for k in keys + ("real_idx",)} for b in batches]
+        pipe = HostBatchPipeline(tr, feed[0], dataset=(ds_rolls.to(DEV), ds_beats.to(DEV)), max_events=B * E, raster=(100, 0, 50))
+        res[mode] = torch.stack([l.clone() for l in pipe.run(feed)])
+        torch.cuda.synchronize()
+        staged[mode] = [(st["fake_d"].cpu(), st["fake_g"].cpu()) for st in pipe.stage]
+    # last two batches are still in the two staging slots: batch 4 in slot 0, batch 3 in slot 1
+    for slot, bi in ((0, 4), (1, 3)):
+        for j, k in enumerate(("fake_d", "fake_g")):
+            assert staged["events"][slot][j].dtype == torch.uint8
+            assert torch.equal(staged["events"][slot][j], batches[bi][k]), (slot, k)
+            assert torch.equal(staged["rolls"][slot][j], batches[bi][k])
+    assert torch.isfinite(res["events"]).all()
+    assert torch.allclose(res["events"], res["rolls"], rtol=5e-3, atol=1e-4), (res["events"], res["rolls"])
+    ev_feed = [{k: batches[0][k] for k in ("fake_d_events", "fake_g_events", "real_idx")}]
+    with pytest.raises(ValueError, match="max_events"):
+        small = HostBatchPipeline(tr, ev_feed[0], dataset=(ds_rolls.to(DEV), ds_beats.to(DEV)), max_events=16, raster=(100, 0, 50))
+        list(small.run(ev_feed))
+
+
 @pytest.mark.parametrize("B", [2, 7, 149])
 def test_bf16_iteration_matches_fp32_iteration_on_small_and_odd_batches(B):
     """Odd batch sizes (fewer samples than SMs, one more than the SM count) through the fused tcgen05 kernels vs the fp32 kernels of the same
