@@ -176,11 +176,20 @@ def out_width(start, end):
     return N.lib().mmg_raster_out_width(int(start), int(end))
 
 
-def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, out_dtype=torch.float32, status=False, out=None, workspace=None):
+RASTER_PATH = os.environ.get("MMG_RASTER_PATH", "sort")      # default kernel path of rasterize_events: "stream" or "sort" (csrc/raster.cu)
+
+
+def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, out_dtype=torch.float32, status=False, out=None, workspace=None,
+                     path=None):
     """Device-resident batch rasterisation: ``dt`` (E,) float64, ``meta`` (E,) int32-typed packed u32,
     ``offsets`` (S+1,) int64, all CUDA tensors -> (S, 2, 128, Wout) tensor of ``out_dtype``.
     ``out`` (a contiguous (S,2,128,Wout) CUDA tensor, its dtype wins) and ``workspace`` (uint8, at least
-    ``raster_workspace_bytes(S, E)``) let a caller that rasterises every step reuse its buffers (no allocation on the stream)."""
+    ``raster_workspace_bytes(S, E)``) let a caller that rasterises every step reuse its buffers (no allocation on the stream).
+    ``path``: "stream" (warp-specialised single kernel, no workspace) or "sort" (chain + compaction kernel, sort-by-pitch write-once kernel);
+    both are bit-exact, None = ``RASTER_PATH``."""
+    path = RASTER_PATH if path is None else path
+    if path not in ("stream", "sort"):
+        raise ValueError("path must be 'stream' or 'sort'")
     N.require_cuda(dt, meta, offsets)
     if end - start < 0:
         raise ValueError("end-start must be >= 0")
@@ -194,8 +203,10 @@ def rasterize_events(dt, meta, offsets, sequence_length=100, start=0, end=50, ou
             raise ValueError(f"out must be a contiguous {(S, 2, 128, Wo)} float32 / bfloat16 / uint8 tensor")
         out_dtype = out.dtype
     st = torch.zeros(S, device=dt.device, dtype=torch.int32) if status else None
-    ws_bytes = raster_workspace_bytes(S, E)
-    if workspace is None:
+    ws_bytes = raster_workspace_bytes(S, E) if path == "sort" else 0
+    if ws_bytes == 0:
+        ws = None
+    elif workspace is None:
         ws = torch.empty(ws_bytes, device=dt.device, dtype=torch.uint8) if ws_bytes else None
     else:
         N.require_cuda(workspace)

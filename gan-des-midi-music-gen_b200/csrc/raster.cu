@@ -5,34 +5,21 @@
 // Integer-only apart from the float64 running time sum, which stays SEQUENTIAL per song (a parallel
 // scan would not be bit-exact) and is rounded half-to-even exactly like Python's round().
 //
-// Two paths.  FAST (S <= 65535 and a workspace is supplied):
+// Two paths, both bit-exact.
+// STREAM (default; no workspace): raster_stream_kernel, one 64-thread CTA per song -- a chain warp runs the t += dt chain while a
+//   replay warp, one chunk behind, rounds / cuts off / scatters into a just-in-time zero-filled output (see the kernel's header).
+// SORT (a workspace is supplied and S <= 65535):
 //   K1 raster_steps_kernel  one WARP per song: 32 lanes stage dt through shared memory, lane 0 runs the dependent
 //      t += dt chain, all lanes round to steps, evaluate the cut-off rule with ballots and COMPACT the surviving
 //      note_on / note_off messages into 4-byte records (step | off<<16 | pitch<<17 | vel<<24) in the workspace.
-//      Latency-bound by the fp64 chain, so every song is in flight at once (tiny footprint per warp).
 //   K2 raster_rows_kernel   one CTA per song: zero-fills the song's planes, stable-counting-sorts the notes by pitch
 //      (per-warp segment histograms, no atomics), then one warp per pitch replays the pitch's list 32 notes at a time
 //      with a closed form of the sequential rules, writing every touched cell exactly once (see the kernel's header).
-// GENERIC (any S, W): one fused kernel, one WARP per song (all songs in flight at once; nothing but the output leaves
-// the SM):
-//   1. the warp zero-fills its song's output planes (coalesced 16-byte stores);
-//   2. per chunk of 256 messages: 32 lanes stage dt into shared memory (coalesced, next chunk
-//      prefetched into registers), lane 0 runs the dependent t += dt chain in place, then all lanes
-//      round to steps and evaluate the cut-off rule (first message with step >= S, first note_on with
-//      step >= W) with ballots;
-//   3. per 32 messages, in message order: lanes resolve same-pitch dependencies with match_any /
-//      ballot (which note_on arms a note_off, which note_on is the last writer of a cell) and scatter
-//      velocities / duration fills straight into the output (each note touches a few cells).
-//      __syncwarp() between sub-steps gives the last-writer-wins order of the reference loop.
-// HBM traffic = 12 B per message read once + every output cell written once (+ the touched cells; fast path: + 4 B
-// per surviving note written and read back through the workspace).
+// HBM traffic = 12 B per message read once + every output cell written once (SORT: + 4 B per surviving note written and
+// read back through the workspace).
 #include "common.cuh"
 
 namespace {
-
-constexpr int RW = 4;     // warps (= songs) per CTA
-constexpr int CH = 256;   // messages per chain chunk
-constexpr int CJ = CH / 32;
 
 template <typename OutT>
 __device__ __forceinline__ OutT to_out(unsigned v);
@@ -40,133 +27,204 @@ template <> __device__ __forceinline__ float to_out<float>(unsigned v) { return 
 template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(unsigned v) { return (uint8_t)(v > 255u ? 255u : v); }
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(unsigned v) { return __float2bfloat16((float)v); }
 
+// ------------------------------------------------------------------------------------------------
+// STREAM path: one 64-thread CTA per song, warp-specialised.
+//   warp 0 (chain)   stages 512 dt values into one half of a double buffer (next chunk prefetched into registers) and lane 0 runs the
+//                    dependent t += dt chain in place -- nothing else sits on the chain's critical path;
+//   warp 1 (replay)  works one chunk behind: rounds the prefix sums to steps, evaluates the cut-off rule with ballots, and replays the
+//                    chunk 32 messages at a time in message order (same-pitch dependencies inside a group resolved with match_any /
+//                    ballots, across groups through note_on_time[] in shared memory), scattering velocities and duration fills straight
+//                    into the output.  The output is zero-filled JUST IN TIME, one 128-byte column block of all 256 rows at a time, right
+//                    before the first message whose step reaches the block: steps never decrease, so the lines a chunk touches were
+//                    written a few microseconds earlier and are still in L2 -- DRAM sees every output line once, as a full line.
+//   One __syncthreads() per chunk hands chunk k to the replay warp and buffer (k+1)&1 back to the chain warp.
+// The whole batch is in flight at once (8.7 KB of shared memory per song); the kernel's floor is the fp64 add latency x messages per song.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_CH = 512;            // messages per chunk
+constexpr int SK_CJ = SK_CH / 32;
+
 template <typename OutT>
-__global__ void __launch_bounds__(RW * 32) raster_fused_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
-                                                                const int64_t* __restrict__ offsets, int64_t n_songs, int S, int W,
-                                                                int lo, int hi, OutT* __restrict__ out, int32_t* __restrict__ status) {
-    __shared__ double tbuf[RW][CH];
-    __shared__ int on_time[RW][128];
+__global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
+                                                            const int64_t* __restrict__ offsets, int S, int W, int lo, int hi,
+                                                            OutT* __restrict__ out, int32_t* __restrict__ status) {
+    __shared__ __align__(16) double tbuf[2][SK_CH];
+    __shared__ int on[128];
+    __shared__ int halt_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t song = (int64_t)blockIdx.x * RW + warp;
-    if (song >= n_songs) return;                       // warp-uniform; no block-level barrier is used below
-    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~lt_mask & ~(1u << lane);
+    const int64_t song = blockIdx.x;
     const int64_t a0 = offsets[song];
     const int64_t n = offsets[song + 1] - a0;
+    const int64_t nchunks = (n + SK_CH - 1) / SK_CH;
+    if (threadIdx.x == 0) halt_flag = 0;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- chain warp
+        double d[SK_CJ];
+#pragma unroll
+        for (int j = 0; j < SK_CJ; ++j) { const int64_t i = lane + 32 * j; d[j] = i < n ? dt[a0 + i] : 0.0; }
+        double t = 0.0;                                             // my_time (datasets.py:32), carried by lane 0
+        for (int64_t k = 0; k <= nchunks; ++k) {
+            if (k < nchunks) {
+                double* tb = tbuf[k & 1];
+#pragma unroll
+                for (int j = 0; j < SK_CJ; ++j) tb[lane + 32 * j] = d[j];
+#pragma unroll
+                for (int j = 0; j < SK_CJ; ++j) {                   // prefetch the next chunk behind the chain
+                    const int64_t i = (k + 1) * SK_CH + lane + 32 * j;
+                    d[j] = i < n ? dt[a0 + i] : 0.0;
+                }
+                __syncwarp();
+                if (lane == 0) {                                    // sequential float64 running sum (datasets.py:35); padding holds 0.0: t + 0.0 == t
+                    const int64_t rem = n - k * SK_CH;
+                    const int lim8 = rem >= SK_CH ? SK_CH : (((int)rem + 7) & ~7);
+                    double2* tb2 = reinterpret_cast<double2*>(tb);
+                    double2 v[4], w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = tb2[u];
+                    for (int q = 0; q < lim8; q += 8) {
+                        if (q + 8 < lim8) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) w[u] = tb2[(q >> 1) + 4 + u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            t = __dadd_rn(t, v[u].x); v[u].x = t;
+                            t = __dadd_rn(t, v[u].y); v[u].y = t;
+                            tb2[(q >> 1) + u] = v[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = w[u];
+                    }
+                }
+            }
+            __syncthreads();
+            if (halt_flag) break;
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- replay warp
+    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~lt_mask & ~(1u << lane);
     const int Wo = hi - lo;
     OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
     OutT* __restrict__ odur = oroll + (size_t)128 * Wo;
-    double* tb = tbuf[warp];
-    int* on = on_time[warp];
-
-    {   // 1. zero-fill (2*128*Wo*sizeof(OutT) bytes, a multiple of 16; the region is 16-byte aligned)
+    // zero fill: just in time by 128-byte column blocks when a row is a whole number of 16-byte words, else the whole song up front
+    const int row_bytes = Wo * (int)sizeof(OutT);
+    const bool jit = (row_bytes & 15) == 0;
+    const int rowq = row_bytes >> 4;                                // 16-byte words per row
+    const int nblk = jit ? (rowq + 7) >> 3 : 0;
+    constexpr int CPB = 128 / (int)sizeof(OutT);                    // output columns per fill block
+    int filled = 0;                                                 // fill blocks done
+    auto fill_block = [&](int b) {
         uint4* z = reinterpret_cast<uint4*>(oroll);
-        const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);
+#pragma unroll 4
+        for (int idx = lane; idx < 256 * 8; idx += 32) {
+            const int q = b * 8 + (idx & 7);
+            if (q < rowq) z[(size_t)(idx >> 3) * rowq + q] = make_uint4(0, 0, 0, 0);
+        }
+    };
+    if (!jit) {
+        uint4* z = reinterpret_cast<uint4*>(oroll);
+        const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);        // the song's planes are a multiple of 16 bytes, 16-byte aligned
         for (int i = lane; i < cnt; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-        for (int p = lane; p < 128; p += 32) on[p] = 0;            // note_on_time = zeros(128) (:33)
     }
+    for (int p = lane; p < 128; p += 32) on[p] = 0;                 // note_on_time = zeros(128) (:33)
     __syncwarp();
-
-    double d[CJ];
-    uint32_t m[CJ];
+    uint32_t m[SK_CJ];
 #pragma unroll
-    for (int j = 0; j < CJ; ++j) {
-        const int64_t i = lane + 32 * j;
-        d[j] = i < n ? dt[a0 + i] : 0.0;
-        m[j] = i < n ? meta[a0 + i] : 0u;
-    }
-    double t = 0.0;                                                 // my_time (:32), carried by lane 0
+    for (int j = 0; j < SK_CJ; ++j) { const int64_t i = lane + 32 * j; m[j] = i < n ? meta[a0 + i] : 0u; }
     int st = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += CH) {
-        uint32_t cm[CJ];
+    for (int64_t k = 0; k <= nchunks; ++k) {
+        if (k >= 1) {
+            const int64_t i0 = (k - 1) * SK_CH;
+            const double* tb = tbuf[(k - 1) & 1];
+            uint32_t cm[SK_CJ];
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) { tb[lane + 32 * j] = d[j]; cm[j] = m[j]; }
+            for (int j = 0; j < SK_CJ; ++j) cm[j] = m[j];
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) {                              // prefetch the next chunk behind the chain
-            const int64_t i = i0 + CH + lane + 32 * j;
-            d[j] = i < n ? dt[a0 + i] : 0.0;
-            m[j] = i < n ? meta[a0 + i] : 0u;
-        }
-        __syncwarp();
-        const int cnt = (int)((n - i0) < CH ? (n - i0) : CH);
-        if (lane == 0) {                                            // 2. sequential float64 running sum (:35)
-            const int lim8 = (cnt + 7) & ~7;                        // padding holds 0.0: t + 0.0 == t
-            for (int k = 0; k < lim8; k += 8) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = tb[k + u];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { t = __dadd_rn(t, v[u]); tb[k + u] = t; }
+            for (int j = 0; j < SK_CJ; ++j) {                       // prefetch the next chunk's meta
+                const int64_t i = i0 + SK_CH + lane + 32 * j;
+                m[j] = i < n ? meta[a0 + i] : 0u;
             }
-        }
-        __syncwarp();
-        int sj[CJ];
-        int first_halt = CH;
+            const int cnt = (int)((n - i0) < SK_CH ? (n - i0) : SK_CH);
+            int sj[SK_CJ];
+            int first_halt = SK_CH;
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) {
-            const int e = lane + 32 * j;
-            const long long step = __double2ll_rn(tb[e]);           // :36 round-half-even
-            const uint32_t kind = cm[j] & 0xFFu, pitch = (cm[j] >> 8) & 0xFFu;
-            const bool note = kind == 1u || kind == 2u;
-            bool halt = step >= S;                                  // :37-38, every message kind
-            halt |= step < 0;                                       // dt < 0: outside the contract (flagged)
-            halt |= note && pitch >= 128u;                          // IndexError in the reference
-            halt |= kind == 1u && step >= W;                        // IndexError -> bare except (:41,:46)
-            const unsigned hm = __ballot_sync(0xffffffffu, e < cnt && halt);
-            if (hm && first_halt == CH) {
-                const int src = __ffs(hm) - 1;
-                first_halt = 32 * j + src;
-                const int bits = (step < 0 ? 1 : 0) | ((note && pitch >= 128u) ? 2 : 0);
-                st = __shfl_sync(0xffffffffu, bits, src);
+            for (int j = 0; j < SK_CJ; ++j) {
+                const int e = lane + 32 * j;
+                const long long step = __double2ll_rn(tb[e]);       // :36 round-half-even
+                const uint32_t kind = cm[j] & 0xFFu, pitch = (cm[j] >> 8) & 0xFFu;
+                const bool note = kind == 1u || kind == 2u;
+                bool halt = step >= S;                              // :37-38, every message kind
+                halt |= step < 0;                                   // dt < 0: outside the contract (flagged)
+                halt |= note && pitch >= 128u;                      // IndexError in the reference
+                halt |= kind == 1u && step >= W;                    // IndexError -> bare except (:41,:46)
+                const unsigned hm = __ballot_sync(0xffffffffu, e < cnt && halt);
+                if (hm && first_halt == SK_CH) {
+                    const int src = __ffs(hm) - 1;
+                    first_halt = 32 * j + src;
+                    const int bits = (step < 0 ? 1 : 0) | ((note && pitch >= 128u) ? 2 : 0);
+                    st = __shfl_sync(0xffffffffu, bits, src);
+                }
+                sj[j] = (int)(step < 0 ? 0 : (step > 0x7fffffff ? 0x7fffffff : step));
             }
-            sj[j] = (int)(step < 0 ? 0 : (step > 0x7fffffff ? 0x7fffffff : step));
-        }
-        const int lim = cnt < first_halt ? cnt : first_halt;
-        __syncwarp();
-        // 3. replay, 32 messages at a time, in message order
+            const int lim = cnt < first_halt ? cnt : first_halt;
+            // replay, 32 messages at a time, in message order
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) {
-            if (32 * j >= lim) break;
-            const bool valid = lane + 32 * j < lim;
-            const uint32_t v = cm[j];
-            const uint32_t kind = valid ? (v & 0xFFu) : 0u;
-            const int p = (int)((v >> 8) & 0x7Fu);
-            const int s = sj[j];
-            const bool is_on = kind == 1u, is_off = kind == 2u;
-            const unsigned pg = __match_any_sync(0xffffffffu, (is_on || is_off) ? (unsigned)p : 128u + lane);
-            const unsigned onm = __ballot_sync(0xffffffffu, is_on), offm = __ballot_sync(0xffffffffu, is_off);
-            // the note_on that arms this message: latest earlier note_on of the same pitch in this group, else carried state
-            const unsigned lower_on = pg & onm & lt_mask;
-            const int s_prev = __shfl_sync(0xffffffffu, s, lower_on ? 31 - __clz(lower_on) : lane);
-            const int a = lower_on ? s_prev : on[p];
-            // a note_on is overwritten if the next note_on of its pitch lands on the same step (steps never decrease)
-            const unsigned higher_on = pg & onm & gt_mask;
-            const int s_next = __shfl_sync(0xffffffffu, s, higher_on ? __ffs(higher_on) - 1 : lane);
-            __syncwarp();
-            if (is_on) {                                            // :39-42
-                if (!(higher_on && s_next == s) && s >= lo && s < hi) oroll[(size_t)p * Wo + (s - lo)] = to_out<OutT>((v >> 16) & 0xFFu);
-                if (!higher_on) on[p] = s;
-            }
-            // :43-45  durations[p, a:s] = s - a.  One note_off at a time, in message order (later fills overwrite
-            // earlier ones); the whole warp writes each range, so the stores are coalesced along the row.
-            unsigned rem = offm;
-            while (rem) {
-                const int src = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int pp = __shfl_sync(0xffffffffu, p, src), aa = __shfl_sync(0xffffffffu, a, src), ss = __shfl_sync(0xffffffffu, s, src);
-                const int c0 = aa > lo ? aa : lo;
-                int c1 = ss < W ? ss : W;
-                c1 = c1 < hi ? c1 : hi;
-                const OutT val = to_out<OutT>((unsigned)(ss - aa));
-                OutT* row = odur + (size_t)pp * Wo - lo;
-                for (int c = c0 + lane; c < c1; c += 32) row[c] = val;
+            for (int j = 0; j < SK_CJ; ++j) {
+                if (32 * j >= lim) break;
+                const bool valid = lane + 32 * j < lim;
+                const uint32_t v = cm[j];
+                const uint32_t kind = valid ? (v & 0xFFu) : 0u;
+                const int p = (int)((v >> 8) & 0x7Fu);
+                const int s = sj[j];
+                const bool is_on = kind == 1u, is_off = kind == 2u;
+                if (jit) {                                          // zero the column blocks this group reaches (steps never decrease)
+                    int need = __reduce_max_sync(0xffffffffu, (is_on || is_off) ? s : 0);
+                    need = (need < hi ? need : hi - 1) - lo;
+                    if (need >= filled * CPB) {
+                        while (filled < nblk && filled * CPB <= need) fill_block(filled++);
+                        __syncwarp();
+                    }
+                }
+                const unsigned pg = __match_any_sync(0xffffffffu, (is_on || is_off) ? (unsigned)p : 128u + lane);
+                const unsigned onm = __ballot_sync(0xffffffffu, is_on), offm = __ballot_sync(0xffffffffu, is_off);
+                // the note_on that arms this message: latest earlier note_on of the same pitch in this group, else carried state
+                const unsigned lower_on = pg & onm & lt_mask;
+                const int s_prev = __shfl_sync(0xffffffffu, s, lower_on ? 31 - __clz(lower_on) : lane);
+                const int a = lower_on ? s_prev : on[p];
+                // a note_on is overwritten if the next note_on of its pitch lands on the same step (steps never decrease)
+                const unsigned higher_on = pg & onm & gt_mask;
+                const int s_next = __shfl_sync(0xffffffffu, s, higher_on ? __ffs(higher_on) - 1 : lane);
                 __syncwarp();
+                if (is_on) {                                        // :39-42
+                    if (!(higher_on && s_next == s) && s >= lo && s < hi) oroll[(size_t)p * Wo + (s - lo)] = to_out<OutT>((v >> 16) & 0xFFu);
+                    if (!higher_on) on[p] = s;
+                }
+                // :43-45  durations[p, a:s] = s - a.  One note_off at a time, in message order (later fills overwrite earlier ones); the
+                // whole warp writes each range, so the stores are coalesced along the row.
+                unsigned rem = offm;
+                while (rem) {
+                    const int src = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const int pp = __shfl_sync(0xffffffffu, p, src), aa = __shfl_sync(0xffffffffu, a, src), ss = __shfl_sync(0xffffffffu, s, src);
+                    const int c0 = aa > lo ? aa : lo;
+                    int c1 = ss < W ? ss : W;
+                    c1 = c1 < hi ? c1 : hi;
+                    const OutT val = to_out<OutT>((unsigned)(ss - aa));
+                    OutT* row = odur + (size_t)pp * Wo - lo;
+                    for (int c = c0 + lane; c < c1; c += 32) row[c] = val;
+                    __syncwarp();
+                }
             }
+            if (first_halt < SK_CH && lane == 0) halt_flag = 1;
         }
-        if (first_halt < CH) break;
+        __syncthreads();
+        if (halt_flag) break;
     }
+    while (filled < nblk) fill_block(filled++);                     // columns no message reached
     if (status && lane == 0) status[song] = st;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // fast path, K1: time chain + cut-off + note compaction (one warp per song)
@@ -512,8 +570,7 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
     long lo, hi;
     if (end < 128) clip_slice(start, end, W, &lo, &hi); else clip_slice(0, end, W, &lo, &hi);
     if (hi - lo == 0) return MMG_OK;                                    // nothing to write
-    const long long blocks = (n_songs + RW - 1) / RW;
-    MMG_REQUIRE(blocks <= 0x7fffffff && n_songs <= 0x7fffffff, MMG_EUNSUPPORTED, "raster: too many songs");
+    MMG_REQUIRE(n_songs <= 0x7fffffff, MMG_EUNSUPPORTED, "raster: too many songs");
     if (S <= 65535 && workspace && ws_bytes >= mmg_raster_workspace_bytes(n_songs, total_events) && ((uintptr_t)workspace & 3) == 0) {
         const size_t rec_bytes = ((size_t)total_events * 4 + 15) & ~(size_t)15;
         uint32_t* notes = (uint32_t*)workspace;
@@ -532,11 +589,11 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
         return MMG_OK;
     }
     if (out_dtype == 0)
-        raster_fused_kernel<float><<<(int)blocks, RW * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
+        raster_stream_kernel<float><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
     else if (out_dtype == 1)
-        raster_fused_kernel<__nv_bfloat16><<<(int)blocks, RW * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out, status);
+        raster_stream_kernel<__nv_bfloat16><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out, status);
     else
-        raster_fused_kernel<uint8_t><<<(int)blocks, RW * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, (int)lo, (int)hi, (uint8_t*)out, status);
+        raster_stream_kernel<uint8_t><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (uint8_t*)out, status);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
