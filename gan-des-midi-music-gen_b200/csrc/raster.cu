@@ -31,23 +31,29 @@ template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(unsig
 // STREAM path: one 64-thread CTA per song, warp-specialised.
 //   warp 0 (chain)   stages 512 dt values into one half of a double buffer (next chunk prefetched into registers) and lane 0 runs the
 //                    dependent t += dt chain in place -- nothing else sits on the chain's critical path;
-//   warp 1 (replay)  works one chunk behind: rounds the prefix sums to steps, evaluates the cut-off rule with ballots, and replays the
-//                    chunk 32 messages at a time in message order (same-pitch dependencies inside a group resolved with match_any /
-//                    ballots, across groups through note_on_time[] in shared memory), scattering velocities and duration fills straight
-//                    into the output.  The output is zero-filled JUST IN TIME, one 128-byte column block of all 256 rows at a time, right
-//                    before the first message whose step reaches the block: steps never decrease, so the lines a chunk touches were
-//                    written a few microseconds earlier and are still in L2 -- DRAM sees every output line once, as a full line.
+//   warp 1 (replay)  works one chunk behind: rounds the prefix sums to steps, evaluates the cut-off rule with ballots, and BINS the
+//                    chunk's notes by pitch in shared memory, 32 messages at a time in message order (match_any ranks; 8 slots per
+//                    pitch).  When a bin is full, and at the end of the song, the bins are DRAINED lane-per-pitch: every lane replays
+//                    its pitch's notes with the reference's own two rules (rows are independent, so per-pitch message order is all
+//                    that last-writer-wins needs), scattering velocities and duration fills straight into the output.
+//                    The output is zero-filled JUST IN TIME, one 128-byte column block of all 256 rows at a time, right before the
+//                    first note whose step reaches the block: steps never decrease, so the lines a drain touches were written a few
+//                    microseconds earlier and are still in L2 -- DRAM sees every output line once, as a full line.
 //   One __syncthreads() per chunk hands chunk k to the replay warp and buffer (k+1)&1 back to the chain warp.
-// The whole batch is in flight at once (8.7 KB of shared memory per song); the kernel's floor is the fp64 add latency x messages per song.
+// The whole batch is in flight at once (15 KB of shared memory per song); the kernel's floor is the fp64 add latency x messages per song.
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_CH = 512;            // messages per chunk
 constexpr int SK_CJ = SK_CH / 32;
+constexpr int SK_CAP = 8;             // bin capacity per pitch (a full bin triggers a drain)
 
 template <typename OutT>
 __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
                                                             const int64_t* __restrict__ offsets, int S, int W, int lo, int hi,
                                                             OutT* __restrict__ out, int32_t* __restrict__ status) {
     __shared__ __align__(16) double tbuf[2][SK_CH];
+    __shared__ int bin_s[SK_CAP][128];              // per-pitch bins of the replay warp: steps ...
+    __shared__ uint16_t bin_v[SK_CAP][128];         // ... and off | velocity << 1, in message order
+    __shared__ int bcnt[128];
     __shared__ int on[128];
     __shared__ int halt_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
     }
 
     // -------------------------------------------------------------------- replay warp
-    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~lt_mask & ~(1u << lane);
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int Wo = hi - lo;
     OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
     OutT* __restrict__ odur = oroll + (size_t)128 * Wo;
@@ -128,8 +134,38 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
         const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);        // the song's planes are a multiple of 16 bytes, 16-byte aligned
         for (int i = lane; i < cnt; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
-    for (int p = lane; p < 128; p += 32) on[p] = 0;                 // note_on_time = zeros(128) (:33)
+    for (int p = lane; p < 128; p += 32) { on[p] = 0; bcnt[p] = 0; }  // note_on_time = zeros(128) (:33); empty bins
     __syncwarp();
+    // Drain: lane-per-pitch replay of the binned notes, literally the reference loop (:39-45) restricted to one pitch row -- rows are
+    // independent, and a pitch's notes sit in its bin in message order, so last-writer-wins is preserved.
+    auto drain = [&]() {
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int p = lane + 32 * q;
+            const int c = bcnt[p];
+            if (c == 0) continue;
+            int on_t = on[p];
+            OutT* rrow = oroll + (size_t)p * Wo - lo;
+            OutT* drow = odur + (size_t)p * Wo - lo;
+#pragma unroll 1
+            for (int i = 0; i < c; ++i) {
+                const int s = bin_s[i][p];
+                const unsigned ov = bin_v[i][p];
+                if (!(ov & 1u)) {                                   // note_on (:39-42)
+                    if (s >= lo && s < hi) rrow[s] = to_out<OutT>(ov >> 1);
+                    on_t = s;
+                } else {                                            // note_off (:43-45): durations[p, on:s] = s - on
+                    int c1 = s < W ? s : W;
+                    c1 = c1 < hi ? c1 : hi;
+                    const OutT val = to_out<OutT>((unsigned)(s - on_t));
+                    for (int cc = on_t > lo ? on_t : lo; cc < c1; ++cc) drow[cc] = val;
+                }
+            }
+            on[p] = on_t;
+            bcnt[p] = 0;
+        }
+        __syncwarp();
+    };
     uint32_t m[SK_CJ];
 #pragma unroll
     for (int j = 0; j < SK_CJ; ++j) { const int64_t i = lane + 32 * j; m[j] = i < n ? meta[a0 + i] : 0u; }
@@ -137,23 +173,15 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
     for (int64_t k = 0; k <= nchunks; ++k) {
         if (k >= 1) {
             const int64_t i0 = (k - 1) * SK_CH;
-            const double* tb = tbuf[(k - 1) & 1];
-            uint32_t cm[SK_CJ];
-#pragma unroll
-            for (int j = 0; j < SK_CJ; ++j) cm[j] = m[j];
-#pragma unroll
-            for (int j = 0; j < SK_CJ; ++j) {                       // prefetch the next chunk's meta
-                const int64_t i = i0 + SK_CH + lane + 32 * j;
-                m[j] = i < n ? meta[a0 + i] : 0u;
-            }
+            double* tb = tbuf[(k - 1) & 1];
+            int2* sm = reinterpret_cast<int2*>(tb);                 // each slot is rewritten in place as (step, meta) once it is rounded
             const int cnt = (int)((n - i0) < SK_CH ? (n - i0) : SK_CH);
-            int sj[SK_CJ];
             int first_halt = SK_CH;
 #pragma unroll
             for (int j = 0; j < SK_CJ; ++j) {
                 const int e = lane + 32 * j;
                 const long long step = __double2ll_rn(tb[e]);       // :36 round-half-even
-                const uint32_t kind = cm[j] & 0xFFu, pitch = (cm[j] >> 8) & 0xFFu;
+                const uint32_t kind = m[j] & 0xFFu, pitch = (m[j] >> 8) & 0xFFu;
                 const bool note = kind == 1u || kind == 2u;
                 bool halt = step >= S;                              // :37-38, every message kind
                 halt |= step < 0;                                   // dt < 0: outside the contract (flagged)
@@ -166,55 +194,51 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
                     const int bits = (step < 0 ? 1 : 0) | ((note && pitch >= 128u) ? 2 : 0);
                     st = __shfl_sync(0xffffffffu, bits, src);
                 }
-                sj[j] = (int)(step < 0 ? 0 : (step > 0x7fffffff ? 0x7fffffff : step));
+                sm[e] = make_int2((int)(step < 0 ? 0 : (step > 0x7fffffff ? 0x7fffffff : step)), (int)m[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < SK_CJ; ++j) {                       // prefetch the next chunk's meta
+                const int64_t i = i0 + SK_CH + lane + 32 * j;
+                m[j] = i < n ? meta[a0 + i] : 0u;
             }
             const int lim = cnt < first_halt ? cnt : first_halt;
-            // replay, 32 messages at a time, in message order
-#pragma unroll
-            for (int j = 0; j < SK_CJ; ++j) {
-                if (32 * j >= lim) break;
-                const bool valid = lane + 32 * j < lim;
-                const uint32_t v = cm[j];
-                const uint32_t kind = valid ? (v & 0xFFu) : 0u;
+            // bin the chunk's notes by pitch, 32 messages at a time, in message order (rolled loop: the body must stay in the instruction cache)
+#pragma unroll 1
+            for (int e0 = 0; e0 < lim; e0 += 32) {
+                const int2 rec = sm[e0 + lane];                     // own slot, written by this lane above
+                const uint32_t v = (uint32_t)rec.y;
+                const uint32_t kind = (e0 + lane < lim) ? (v & 0xFFu) : 0u;
+                const bool note = kind == 1u || kind == 2u;
                 const int p = (int)((v >> 8) & 0x7Fu);
-                const int s = sj[j];
-                const bool is_on = kind == 1u, is_off = kind == 2u;
-                if (jit) {                                          // zero the column blocks this group reaches (steps never decrease)
-                    int need = __reduce_max_sync(0xffffffffu, (is_on || is_off) ? s : 0);
+                const int s = rec.x;
+                unsigned pend = __ballot_sync(0xffffffffu, note);
+                if (!pend) continue;
+                if (jit) {                                          // zero the column blocks this group reaches
+                    int need = __reduce_max_sync(0xffffffffu, note ? s : 0);
                     need = (need < hi ? need : hi - 1) - lo;
                     if (need >= filled * CPB) {
                         while (filled < nblk && filled * CPB <= need) fill_block(filled++);
                         __syncwarp();
                     }
                 }
-                const unsigned pg = __match_any_sync(0xffffffffu, (is_on || is_off) ? (unsigned)p : 128u + lane);
-                const unsigned onm = __ballot_sync(0xffffffffu, is_on), offm = __ballot_sync(0xffffffffu, is_off);
-                // the note_on that arms this message: latest earlier note_on of the same pitch in this group, else carried state
-                const unsigned lower_on = pg & onm & lt_mask;
-                const int s_prev = __shfl_sync(0xffffffffu, s, lower_on ? 31 - __clz(lower_on) : lane);
-                const int a = lower_on ? s_prev : on[p];
-                // a note_on is overwritten if the next note_on of its pitch lands on the same step (steps never decrease)
-                const unsigned higher_on = pg & onm & gt_mask;
-                const int s_next = __shfl_sync(0xffffffffu, s, higher_on ? __ffs(higher_on) - 1 : lane);
-                __syncwarp();
-                if (is_on) {                                        // :39-42
-                    if (!(higher_on && s_next == s) && s >= lo && s < hi) oroll[(size_t)p * Wo + (s - lo)] = to_out<OutT>((v >> 16) & 0xFFu);
-                    if (!higher_on) on[p] = s;
-                }
-                // :43-45  durations[p, a:s] = s - a.  One note_off at a time, in message order (later fills overwrite earlier ones); the
-                // whole warp writes each range, so the stores are coalesced along the row.
-                unsigned rem = offm;
-                while (rem) {
-                    const int src = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    const int pp = __shfl_sync(0xffffffffu, p, src), aa = __shfl_sync(0xffffffffu, a, src), ss = __shfl_sync(0xffffffffu, s, src);
-                    const int c0 = aa > lo ? aa : lo;
-                    int c1 = ss < W ? ss : W;
-                    c1 = c1 < hi ? c1 : hi;
-                    const OutT val = to_out<OutT>((unsigned)(ss - aa));
-                    OutT* row = odur + (size_t)pp * Wo - lo;
-                    for (int c = c0 + lane; c < c1; c += 32) row[c] = val;
+                const unsigned grp = __match_any_sync(0xffffffffu, note ? (unsigned)p : 128u + lane);
+                bool mine = note;
+                while (true) {
+                    const unsigned g = grp & pend;                  // still-unbinned notes of my pitch
+                    const int base = bcnt[p];
+                    const int r = __popc(g & lt_mask);
+                    const bool fits = mine && base + r < SK_CAP;
+                    if (fits) {
+                        bin_s[base + r][p] = s;
+                        bin_v[base + r][p] = (uint16_t)((kind == 2u ? 1u : 0u) | (((v >> 16) & 0xFFu) << 1));
+                    }
                     __syncwarp();
+                    if (mine && r == 0) { const int c = __popc(g); bcnt[p] = base + (c < SK_CAP - base ? c : SK_CAP - base); }
+                    __syncwarp();
+                    mine = mine && !fits;
+                    pend = __ballot_sync(0xffffffffu, mine);
+                    if (!pend) break;
+                    drain();                                        // a bin is full: replay everything binned so far, then go on
                 }
             }
             if (first_halt < SK_CH && lane == 0) halt_flag = 1;
@@ -222,9 +246,12 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
         __syncthreads();
         if (halt_flag) break;
     }
+    __syncwarp();
+    drain();
     while (filled < nblk) fill_block(filled++);                     // columns no message reached
     if (status && lane == 0) status[song] = st;
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // fast path, K1: time chain + cut-off + note compaction (one warp per song)
