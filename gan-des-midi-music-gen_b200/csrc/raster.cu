@@ -28,10 +28,10 @@ template <> __device__ __forceinline__ uint8_t to_out<uint8_t>(unsigned v) { ret
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(unsigned v) { return __float2bfloat16((float)v); }
 
 // ------------------------------------------------------------------------------------------------
-// STREAM path: one 64-thread CTA per song, warp-specialised.
+// STREAM path: one CTA per song (one chain warp + SK_R replay warps, each replay warp owning the pitches p % SK_R == w), warp-specialised.
 //   warp 0 (chain)   stages 512 dt values into one half of a double buffer (next chunk prefetched into registers) and lane 0 runs the
 //                    dependent t += dt chain in place -- nothing else sits on the chain's critical path;
-//   warp 1 (replay)  works one chunk behind: rounds the prefix sums to steps, evaluates the cut-off rule with ballots, and BINS the
+//   warps 1.. (replay) work one chunk behind; each rounds its share of the chunk, then all see the whole chunk: rounds the prefix sums to steps, evaluates the cut-off rule with ballots, and BINS the
 //                    chunk's notes by pitch in shared memory, 32 messages at a time in message order (match_any ranks; 8 slots per
 //                    pitch).  When a bin is full, and at the end of the song, the bins are DRAINED lane-per-pitch: every lane replays
 //                    its pitch's notes with the reference's own two rules (rows are independent, so per-pitch message order is all
@@ -44,17 +44,20 @@ template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(unsig
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_CH = 512;            // messages per chunk
 constexpr int SK_CJ = SK_CH / 32;
-constexpr int SK_CAP = 8;             // bin capacity per pitch (a full bin triggers a drain)
+constexpr int SK_CAP = 8;             // bin capacity per pitch (a full bin triggers a drain of the warp's bins)
+constexpr int SK_R = 2;               // replay warps per song; warp w owns the pitches p with p % SK_R == w (rows are independent)
 
-template <typename OutT>
-__global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
-                                                            const int64_t* __restrict__ offsets, int S, int W, int lo, int hi,
-                                                            OutT* __restrict__ out, int32_t* __restrict__ status) {
+template <typename OutT, int R>
+__global__ void __launch_bounds__(32 * (1 + R), R == 1 ? 12 : 9)
+raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta, const int64_t* __restrict__ offsets, int S, int W, int lo,
+                     int hi, OutT* __restrict__ out, int32_t* __restrict__ status) {
+    static_assert(SK_CJ % R == 0 && 128 % (32 * R) == 0, "replay warps must divide the chunk groups and the pitch range");
     __shared__ __align__(16) double tbuf[2][SK_CH];
-    __shared__ int bin_s[SK_CAP][128];              // per-pitch bins of the replay warp: steps ...
+    __shared__ int bin_s[SK_CAP][128];              // per-pitch bins: steps ...
     __shared__ uint16_t bin_v[SK_CAP][128];         // ... and off | velocity << 1, in message order
     __shared__ int bcnt[128];
     __shared__ int on[128];
+    __shared__ int fh[R], fst[R];                   // per replay warp: first halting message of its share of the chunk, its status bits
     __shared__ int halt_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t song = blockIdx.x;
@@ -109,7 +112,10 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
         return;
     }
 
-    // -------------------------------------------------------------------- replay warp
+    // -------------------------------------------------------------------- replay warps
+    constexpr int GJ = SK_CJ / R;                                   // groups of 32 messages this warp rounds per chunk
+    constexpr int NP = 128 / R;                                     // pitches this warp owns
+    const int rw = warp - 1;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int Wo = hi - lo;
     OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
@@ -120,28 +126,30 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
     const int rowq = row_bytes >> 4;                                // 16-byte words per row
     const int nblk = jit ? (rowq + 7) >> 3 : 0;
     constexpr int CPB = 128 / (int)sizeof(OutT);                    // output columns per fill block
-    int filled = 0;                                                 // fill blocks done
-    auto fill_block = [&](int b) {
+    int filled = 0;                                                 // fill blocks done (of this warp's rows)
+    auto fill_block = [&](int b) {                                  // this warp's 2 * NP rows (both planes of its pitches), 8 words each
         uint4* z = reinterpret_cast<uint4*>(oroll);
 #pragma unroll 4
-        for (int idx = lane; idx < 256 * 8; idx += 32) {
-            const int q = b * 8 + (idx & 7);
-            if (q < rowq) z[(size_t)(idx >> 3) * rowq + q] = make_uint4(0, 0, 0, 0);
+        for (int idx = lane; idx < 2 * NP * 8; idx += 32) {
+            const int q = b * 8 + (idx & 7), rr = idx >> 3;
+            const int row = (rr / NP) * 128 + rw + R * (rr % NP);
+            if (q < rowq) z[(size_t)row * rowq + q] = make_uint4(0, 0, 0, 0);
         }
     };
     if (!jit) {
         uint4* z = reinterpret_cast<uint4*>(oroll);
         const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);        // the song's planes are a multiple of 16 bytes, 16-byte aligned
-        for (int i = lane; i < cnt; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane + 32 * rw; i < cnt; i += 32 * R) z[i] = make_uint4(0, 0, 0, 0);
+        if (R > 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * R) : "memory");   // rows are shared between the replay warps in this mode
     }
-    for (int p = lane; p < 128; p += 32) { on[p] = 0; bcnt[p] = 0; }  // note_on_time = zeros(128) (:33); empty bins
+    for (int i = lane; i < NP; i += 32) { on[rw + R * i] = 0; bcnt[rw + R * i] = 0; }  // note_on_time = zeros(128) (:33); empty bins
     __syncwarp();
     // Drain: lane-per-pitch replay of the binned notes, literally the reference loop (:39-45) restricted to one pitch row -- rows are
     // independent, and a pitch's notes sit in its bin in message order, so last-writer-wins is preserved.
     auto drain = [&]() {
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int p = lane + 32 * q;
+        for (int q = 0; q < NP / 32; ++q) {
+            const int p = rw + R * (lane + 32 * q);
             const int c = bcnt[p];
             if (c == 0) continue;
             int on_t = on[p];
@@ -166,9 +174,9 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
         }
         __syncwarp();
     };
-    uint32_t m[SK_CJ];
+    uint32_t m[GJ];                                                 // meta of this warp's share of the next chunk
 #pragma unroll
-    for (int j = 0; j < SK_CJ; ++j) { const int64_t i = lane + 32 * j; m[j] = i < n ? meta[a0 + i] : 0u; }
+    for (int j = 0; j < GJ; ++j) { const int64_t i = lane + 32 * (rw * GJ + j); m[j] = i < n ? meta[a0 + i] : 0u; }
     int st = 0;
     for (int64_t k = 0; k <= nchunks; ++k) {
         if (k >= 1) {
@@ -176,10 +184,10 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
             double* tb = tbuf[(k - 1) & 1];
             int2* sm = reinterpret_cast<int2*>(tb);                 // each slot is rewritten in place as (step, meta) once it is rounded
             const int cnt = (int)((n - i0) < SK_CH ? (n - i0) : SK_CH);
-            int first_halt = SK_CH;
+            int first_halt = SK_CH, st_new = 0;
 #pragma unroll
-            for (int j = 0; j < SK_CJ; ++j) {
-                const int e = lane + 32 * j;
+            for (int j = 0; j < GJ; ++j) {
+                const int e = lane + 32 * (rw * GJ + j);
                 const long long step = __double2ll_rn(tb[e]);       // :36 round-half-even
                 const uint32_t kind = m[j] & 0xFFu, pitch = (m[j] >> 8) & 0xFFu;
                 const bool note = kind == 1u || kind == 2u;
@@ -190,27 +198,49 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
                 const unsigned hm = __ballot_sync(0xffffffffu, e < cnt && halt);
                 if (hm && first_halt == SK_CH) {
                     const int src = __ffs(hm) - 1;
-                    first_halt = 32 * j + src;
+                    first_halt = 32 * (rw * GJ + j) + src;
                     const int bits = (step < 0 ? 1 : 0) | ((note && pitch >= 128u) ? 2 : 0);
-                    st = __shfl_sync(0xffffffffu, bits, src);
+                    st_new = __shfl_sync(0xffffffffu, bits, src);
                 }
                 sm[e] = make_int2((int)(step < 0 ? 0 : (step > 0x7fffffff ? 0x7fffffff : step)), (int)m[j]);
             }
 #pragma unroll
-            for (int j = 0; j < SK_CJ; ++j) {                       // prefetch the next chunk's meta
-                const int64_t i = i0 + SK_CH + lane + 32 * j;
+            for (int j = 0; j < GJ; ++j) {                          // prefetch this warp's share of the next chunk's meta
+                const int64_t i = i0 + SK_CH + lane + 32 * (rw * GJ + j);
                 m[j] = i < n ? meta[a0 + i] : 0u;
             }
+            if (R > 1) {                                            // the earliest halt over all shares decides
+                if (lane == 0) { fh[rw] = first_halt; fst[rw] = st_new; }
+                asm volatile("bar.sync 1, %0;" ::"r"(32 * R) : "memory");
+                first_halt = SK_CH;
+#pragma unroll
+                for (int w = R - 1; w >= 0; --w)
+                    if (fh[w] < SK_CH) { first_halt = fh[w]; st_new = fst[w]; }
+            }
+            if (first_halt < SK_CH) st = st_new;
             const int lim = cnt < first_halt ? cnt : first_halt;
-            // bin the chunk's notes by pitch, 32 messages at a time, in message order (rolled loop: the body must stay in the instruction cache)
+            // bin this warp's pitches, 32 messages at a time, in message order (rolled loop: the body must stay in the instruction cache)
+            // (the match_any of group g + 1 is issued before group g is processed: its ~200-cycle latency hides behind the binning)
+            auto load_group = [&](int e0, uint32_t& v, int& s, bool& note, unsigned& grp) {
+                const int2 rec = sm[e0 + lane];
+                v = (uint32_t)rec.y;
+                s = rec.x;
+                const uint32_t kind = (e0 + lane < lim) ? (v & 0xFFu) : 0u;
+                const int p = (int)((v >> 8) & 0x7Fu);
+                note = (kind == 1u || kind == 2u) && (R == 1 || (p % R) == rw);
+                grp = __match_any_sync(0xffffffffu, note ? (unsigned)p : 128u + lane);
+            };
+            uint32_t v_n = 0; int s_n = 0; bool note_n = false; unsigned grp_n = 0;
+            if (lim > 0) load_group(0, v_n, s_n, note_n, grp_n);
 #pragma unroll 1
             for (int e0 = 0; e0 < lim; e0 += 32) {
-                const int2 rec = sm[e0 + lane];                     // own slot, written by this lane above
-                const uint32_t v = (uint32_t)rec.y;
-                const uint32_t kind = (e0 + lane < lim) ? (v & 0xFFu) : 0u;
-                const bool note = kind == 1u || kind == 2u;
+                const uint32_t v = v_n;
+                const int s = s_n;
+                const bool note = note_n;
+                const unsigned grp = grp_n;
+                if (e0 + 32 < lim) load_group(e0 + 32, v_n, s_n, note_n, grp_n);
+                const uint32_t kind = v & 0xFFu;
                 const int p = (int)((v >> 8) & 0x7Fu);
-                const int s = rec.x;
                 unsigned pend = __ballot_sync(0xffffffffu, note);
                 if (!pend) continue;
                 if (jit) {                                          // zero the column blocks this group reaches
@@ -221,7 +251,6 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
                         __syncwarp();
                     }
                 }
-                const unsigned grp = __match_any_sync(0xffffffffu, note ? (unsigned)p : 128u + lane);
                 bool mine = note;
                 while (true) {
                     const unsigned g = grp & pend;                  // still-unbinned notes of my pitch
@@ -241,17 +270,16 @@ __global__ void __launch_bounds__(64, 12) raster_stream_kernel(const double* __r
                     drain();                                        // a bin is full: replay everything binned so far, then go on
                 }
             }
-            if (first_halt < SK_CH && lane == 0) halt_flag = 1;
+            if (first_halt < SK_CH && rw == 0 && lane == 0) halt_flag = 1;
         }
         __syncthreads();
         if (halt_flag) break;
     }
     __syncwarp();
     drain();
-    while (filled < nblk) fill_block(filled++);                     // columns no message reached
-    if (status && lane == 0) status[song] = st;
+    while (filled < nblk) fill_block(filled++);                     // columns no note of this warp's pitches reached
+    if (status && rw == 0 && lane == 0) status[song] = st;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // fast path, K1: time chain + cut-off + note compaction (one warp per song)
@@ -616,11 +644,11 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
         return MMG_OK;
     }
     if (out_dtype == 0)
-        raster_stream_kernel<float><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
+        raster_stream_kernel<float, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
     else if (out_dtype == 1)
-        raster_stream_kernel<__nv_bfloat16><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out, status);
+        raster_stream_kernel<__nv_bfloat16, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out, status);
     else
-        raster_stream_kernel<uint8_t><<<(int)n_songs, 64, 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (uint8_t*)out, status);
+        raster_stream_kernel<uint8_t, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (uint8_t*)out, status);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

@@ -16,10 +16,23 @@ def _dev(a, dtype=None):
     return t.cuda()
 
 
+PATH = {"v": None}
+
+
+@pytest.fixture(autouse=True, params=["stream", "sort"])
+def raster_path(request):
+    """every test of this file runs through both kernel paths of csrc/raster.cu (warp-specialised stream kernel; chain + sort-by-pitch kernels)"""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    PATH["v"], old = request.param, ds.RASTER_PATH
+    ds.RASTER_PATH = request.param                 # the API-level tests (generate_piano_roll, preprocess_maestro) follow it too
+    yield request.param
+    PATH["v"], ds.RASTER_PATH = None, old
+
+
 def _run(dt, meta, off, sl, start, end, out_dtype=torch.float32, status=False):
     from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
     return ds.rasterize_events(_dev(dt.astype(np.float64)), _dev(meta.astype(np.uint32).view(np.int32)), _dev(off.astype(np.int64)),
-                               sl, start, end, out_dtype, status)
+                               sl, start, end, out_dtype, status, path=PATH["v"])
 
 
 def test_golden_cases(golden_dir):
