@@ -43,17 +43,84 @@ class ShimMessage:
         self.type, self.time, self.note, self.velocity = type, time, note, velocity
 
 
+class ShimBuildMessage:
+    """Stands in for mido.Message / mido.MetaMessage on the BUILD side (sim_log_to_midi.py:19-20,87-96,153-172): keyword attributes,
+    equality by value (mido compares ``vars``; ``list.remove`` in save_midi relies on it) and ``copy(time=...)``."""
+
+    def __init__(self, type, **kw):
+        self.type = type
+        self.time = kw.pop("time", 0)
+        self.__dict__.update(kw)
+
+    def copy(self, **kw):
+        m = ShimBuildMessage.__new__(ShimBuildMessage)
+        m.__dict__.update(self.__dict__)
+        m.__dict__.update(kw)
+        return m
+
+    def __eq__(self, other):
+        return isinstance(other, ShimBuildMessage) and vars(self) == vars(other)
+
+    __hash__ = None
+
+
+class ShimMidiTrack(list):
+    pass
+
+
+def _merge_tracks(tracks):
+    """mido 1.3.2 ``merge_tracks``: absolute ticks, stable sort by time, back to deltas, every end_of_track removed (its delta carried
+    to the next message) and one appended at the end (``fix_end_of_track``)."""
+    msgs = []
+    for tr in tracks:
+        now = 0
+        for m in tr:
+            now += m.time
+            msgs.append(m.copy(time=now))
+    msgs.sort(key=lambda m: m.time)
+    out, now, accum = [], 0, 0
+    for m in msgs:
+        delta = m.time - now
+        now = m.time
+        if m.type == "end_of_track":
+            accum += delta
+        else:
+            out.append(m.copy(time=delta + accum))
+            accum = 0
+    out.append(ShimBuildMessage("end_of_track", time=accum))
+    return out
+
+
 class ShimMidiFile:
-    """Stands in for mido.MidiFile: an iterable of ShimMessage with .filename."""
+    """Stands in for mido.MidiFile.  Read side: an iterable of ShimMessage with .filename (pre-parsed events).  Build side
+    (``mido.MidiFile()`` with no arguments): ``tracks`` / ``ticks_per_beat`` / ``save`` and iteration with mido 1.3.2's published
+    semantics -- merged tracks, delta ticks -> seconds with the running tempo (``tick * (tempo * 1e-6 / ticks_per_beat)``), the tempo
+    switching after the set_tempo message is yielded."""
     beats = ()
 
     def __init__(self, events=None, filename=None, beats=()):
-        self.events = list(events or [])
+        self.events = None if events is None else list(events)
         self.filename = filename if filename is not None else self
         self.beats = beats
+        self.tracks = []
+        self.ticks_per_beat = 480
+        self.type = 1
+
+    def save(self, filename=None):
+        self.saved_as = filename
 
     def __iter__(self):
-        return iter(self.events)
+        if self.events is not None:
+            return iter(self.events)
+        return self._play()
+
+    def _play(self):
+        tempo = 500000
+        for m in _merge_tracks(self.tracks):
+            delta = m.time * (tempo * 1e-6 / self.ticks_per_beat) if m.time > 0 else 0
+            yield m.copy(time=delta)
+            if m.type == "set_tempo":
+                tempo = m.tempo
 
 
 class ShimPrettyMIDI:
@@ -76,6 +143,9 @@ def _install_stubs():
             sys.modules[name] = _Stub(name)
     mido = _Stub("mido")
     mido.MidiFile = ShimMidiFile
+    mido.Message = ShimBuildMessage
+    mido.MetaMessage = ShimBuildMessage
+    mido.MidiTrack = ShimMidiTrack
     sys.modules["mido"] = mido
     pm = _Stub("pretty_midi")
     pm.PrettyMIDI = ShimPrettyMIDI
@@ -101,6 +171,19 @@ def import_mmgan():
     finally:
         os.chdir(cwd)
     return nt, ds
+
+
+def import_simlog():
+    """Returns the unmodified MMGAN_MIDI_DES/sim_log_to_midi.py module (MidiGenerator, LogLineProcessor, process_adjsim_log)."""
+    import_mmgan()
+    d = os.path.join(REF_ROOT, "MMGAN_MIDI_DES")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        m = importlib.import_module("sim_log_to_midi")
+    finally:
+        os.chdir(cwd)
+    return m
 
 
 def import_gandes():

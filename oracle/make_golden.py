@@ -8,12 +8,14 @@ only the committed .npz files.
     python oracle/make_golden.py raster     -> tests/golden/raster_cases.npz
     python oracle/make_golden.py mmgan      -> tests/golden/mmgan_b16.npz, mmgan_b4_small.npz
     python oracle/make_golden.py gandes     -> tests/golden/gandes_b3.npz   (separate process: module-name clash)
+    python oracle/make_golden.py simlog     -> tests/golden/simlog_cases.npz
 
 Reference entry points exercised:
   MMGAN_MIDI_DES/datasets.py:13-70      generate_piano_roll (via the mido / pretty_midi shim)
   MMGAN_MIDI_DES/network_tests.py:58-206 Generator, BeatGenerator, DiscriminatorCNN, MultiModalGAN
   MMGAN_MIDI_DES/network_tests.py:248-315 criterion, the two Adam optimisers and the loop body
   GAN_DES/SIMNN.py:62-142,256-331        Generator, Discriminator, loop body
+  MMGAN_MIDI_DES/sim_log_to_midi.py:13-277 MidiGenerator, LogLineProcessor, process_adjsim_log (mido build-side shim)
 """
 import os
 import sys
@@ -266,6 +268,80 @@ def make_gandes():
     print("gandes golden written")
 
 
+def synth_sim_log(rng, n_lines, t_max, n_servers=16, n_customers=40, junk=0.1):
+    """Log lines in the simulator's 'Music' logging format (simulation_v3.py:341,546,604,617): time - customer - server - event."""
+    t = np.sort(rng.random(n_lines) * t_max)
+    lines = []
+    for i in range(n_lines):
+        if rng.random() < junk:
+            lines.append("INFO:root:queue length 3\n")                      # lines the regex rejects
+            continue
+        ev = "arrival" if rng.random() < 0.55 else "departure"
+        tt = f"{t[i]:.4f}" if rng.random() < 0.8 else f"{int(t[i])}"
+        lines.append(f"INFO:root:{tt} - {int(rng.integers(0, n_customers))} - {int(rng.integers(0, n_servers))} - {ev}\n")
+    return lines
+
+
+def make_simlog():
+    import contextlib, io, tempfile
+    m = R.import_simlog()
+    rng = np.random.default_rng(2024)
+    out, names = {}, []
+    # (name, lines, t_max, gen2[0:6], generate, start, end)
+    specs = [("hundred", 200, 60.0, (0.2, 0.3, 0.5, 0.7, 0.5, 0.4), False, 0, 50),
+             ("not_multiple_of_100", 150, 60.0, (0.2, 0.3, 0.5, 0.7, 0.5, 0.4), False, 0, 50),
+             ("generate", 150, 60.0, (0.2, 0.3, 0.5, 0.7, 0.5, 0.4), True, 0, 50),
+             ("slow_tempo", 300, 40.0, (0.21, 0.35, 0.5, 0.9, 0.95, 0.9), False, 0, 50),
+             ("very_slow_tempo", 100, 20.0, (0.2, 0.3, 0.7, 0.3, 9.0, 0.05), False, 0, 50),
+             ("track_cap", 1500, 150.0, (0.2, 0.3, 0.5, 0.6, 0.3, 0.5), False, 0, 50),
+             ("late_times", 400, 320.0, (0.2, 0.2, 0.2, 0.6, 0.1, 0.5), False, 0, 50),
+             ("window", 200, 60.0, (0.2, 0.3, 0.5, 0.7, 0.9, 0.4), True, 100, 150),
+             ("sparse_skips", 300, 60.0, (0.7, 0.9, 1.1, 0.7, 0.6, 0.0), False, 0, 50),
+             ("zero_tempo", 100, 30.0, (0.2, 0.3, 0.5, 0.7, 0.0, 0.4), False, 0, 50),
+             ("too_long", 5100, 190.0, (0.2, 0.3, 0.5, 0.7, 0.5, 0.4), False, 0, 50)]
+    for name, n_lines, t_max, g6, generate, start, end in specs:
+        lines = synth_sim_log(rng, n_lines, t_max)
+        gen2 = np.concatenate([np.array(g6, dtype=np.float32), rng.random(4).astype(np.float32)])
+        instruments = rng.integers(0, 100, 16)
+        note_levels = rng.integers(30, 100, 16)
+        seen = {}
+        real_gpr = m.generate_piano_roll
+
+        def spy(midi, **kw):
+            seen["msgs"] = [(x.type, float(x.time), int(getattr(x, "note", 0)), int(getattr(x, "velocity", 0))) for x in midi]
+            return real_gpr(midi, **kw)
+
+        m.generate_piano_roll = spy
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as td:
+            os.makedirs(os.path.join(td, "logs"))
+            os.makedirs(os.path.join(td, "adj_sim_outputs", "midi"))
+            open(os.path.join(td, "logs", "simulation.log"), "w").writelines(lines)
+            os.chdir(td)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    roll, dur, _ = m.process_adjsim_log(instruments=instruments, note_levels=note_levels, gen2_output=gen2, count=0, start=start, end=end,
+                                                        generate=generate)
+            finally:
+                os.chdir(cwd)
+                m.generate_piano_roll = real_gpr
+        kinds = {"note_on": 1, "note_off": 2}
+        msgs = seen["msgs"]
+        names.append(name)
+        out[name + ".lines"] = np.array(lines)
+        out[name + ".gen2"] = gen2
+        out[name + ".instruments"] = instruments
+        out[name + ".note_levels"] = note_levels
+        out[name + ".args"] = np.array([int(generate), start, end])
+        out[name + ".dt"] = np.array([x[1] for x in msgs], dtype=np.float64)
+        out[name + ".meta"] = np.array([(kinds[x[0]] | (x[2] << 8) | (x[3] << 16)) if x[0] in kinds else 0 for x in msgs], dtype=np.uint32)
+        out[name + ".roll"] = np.asarray(roll)
+        out[name + ".dur"] = np.asarray(dur)
+        print(name, "messages", len(msgs), "notes", int((out[name + ".meta"] != 0).sum()), "roll nnz", int((roll != 0).sum()), "dur nnz", int((dur != 0).sum()))
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "simlog_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -275,6 +351,8 @@ if __name__ == "__main__":
         make_mmgan()
     if what == "gandes":
         make_gandes()
+    if what in ("simlog", "all"):
+        make_simlog()
     if what == "all":
         import subprocess
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "gandes"])
