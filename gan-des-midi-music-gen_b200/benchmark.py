@@ -92,9 +92,15 @@ def _raster_leg(device, peaks, quick):
     cpu_sec = time.perf_counter() - t0
     n_on = int((kinds == 1).sum())
     alg_bytes = 12.0 * S * E + 2 * 128 * 300 * 4.0 * S
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    if os.path.exists(tpath):                                # both kernels of the sort path, one call, from the committed ncu --set full capture
+        t = json.load(open(tpath)).get("raster_sort_path")
+        if t and t.get("songs") == S and t.get("messages_per_song") == E:
+            traffic = t["dram_bytes"]
     return {"notes_per_sec": n_on / sec, "messages_per_sec": S * E / sec, "ms": sec * 1e3, "songs": S, "messages_per_song": E, "window": 300,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                         "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_src": peaks["src"],
                          "algorithmic_bytes": alg_bytes},
             "cpu_baseline": {"value": (n_on * sample / S) / cpu_sec, "unit": "notes/s", "cores": 1, "kind": "port",
                              "sample": f"first {sample} songs through oracle/raster_oracle.c"},
@@ -286,9 +292,12 @@ def run(args):
     traffic = None
     tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     if os.path.exists(tpath):                                # dram__bytes_read+write of one launch from the committed ncu --set full capture
-        t = json.load(open(tpath)).get(kname.split(" ")[0])
+        tj = json.load(open(tpath))
+        t = tj.get(kname.split(" ")[0])
         if t and t.get("batch") == Bk:
             traffic = t["dram_bytes"]
+        elif str(Bk) in tj.get("by_batch", {}) and kname.split(" ")[0] in tj["by_batch"][str(Bk)]:
+            traffic = tj["by_batch"][str(Bk)][kname.split(" ")[0]]["dram_bytes"]
     roofline = {"bound": "tensor", "kernel": kname, "achieved": kflops / ksec / 1e12, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": kflops / ksec / 1e12 / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_src": peaks["src"],
                 "kernel_us": ksec * 1e6, "kernel_algorithmic_flops": kflops, "kernel_algorithmic_bytes": kbytes,

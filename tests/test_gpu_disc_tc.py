@@ -90,3 +90,46 @@ def test_disc_tc_matches_fp32_module():
         want = D(x8.float()).squeeze(1)
     got = DiscTC(D, max_batch=B).forward(x8)
     assert (got - want).abs().max().item() <= 5e-3 * want.abs().max().item() + 1e-4
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 3 at its full per-GPU batch (16 384 rolls) through the fused kernels, checked with size-independent properties:
+    samples are independent (the logits of the full batch equal the logits of its four quarters run separately, whatever CTA a sample lands
+    on, up to the order in which a sample's eight per-warp fp32 partial dots are added), and the mean-loss gradient is additive over shards (full-batch gradient = sum of the quarter gradients, fp32 summation
+    order only) -- the property the data-parallel all-reduce relies on."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.disc_tc import DiscTC
+    B, Q = 16384, 4096
+    sd = mo.synth_state(mo.mmgan_shapes(), seed=31, d_scale=0.25)
+    D = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
+    D.load_state_dict({k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")})
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = ((torch.rand(B, 2, 128, 50, device=DEV, generator=g) < 0.02) * torch.randint(1, 128, (B, 2, 128, 50), device=DEV, generator=g)).to(torch.uint8)
+    dl = torch.randn(B, device=DEV, generator=g) / B
+    names = [n for n, _ in D.named_parameters()]
+
+    def grads():
+        return {n: p.grad.clone() for n, p in D.named_parameters()}
+
+    tc = DiscTC(D, max_batch=B)
+    for p in D.parameters():
+        p.grad = None
+    full_logits = tc.forward(x).clone()
+    tc.backward(dl)
+    torch.cuda.synchronize()
+    full = grads()
+    assert torch.isfinite(full_logits).all()
+    scale = full_logits.abs().max().item()
+    tcq = DiscTC(D, max_batch=Q)
+    for p in D.parameters():
+        p.grad = None
+    for i in range(B // Q):
+        lq = tcq.forward(x[i * Q:(i + 1) * Q])
+        assert (lq - full_logits[i * Q:(i + 1) * Q]).abs().max().item() <= 1e-5 * scale + 1e-6, f"quarter {i}: logits depend on the batch"
+        tcq.backward(dl[i * Q:(i + 1) * Q].contiguous())            # accumulates
+    torch.cuda.synchronize()
+    parts = grads()
+    for n in names:
+        assert _rel_l2(parts[n], full[n]) < 5e-4, (n, _rel_l2(parts[n], full[n]))      # fp32 accumulation order under heavy cancellation (zero-mean dlogits)
+    # idempotence of the forward on the same buffers
+    assert (tc.forward(x) - full_logits).abs().max().item() <= 1e-5 * scale + 1e-6
