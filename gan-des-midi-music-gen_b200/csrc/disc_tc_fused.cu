@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap map_p1a, const __grid_constant__ CUtensorMap map_p1b,
                                                                        const FusedFwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t x_full, x_empty, xs_ready, c1_done, p1_ready, c2_done, wbar;
+    __shared__ uint64_t x_full, x_empty, xs_ready, c1_done, p1_ready[4], c2_done[4], wbar;     // [4]: one per 128-row conv2 tile
     __shared__ uint32_t tmem_s;
     __shared__ float logit_s;
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -431,8 +431,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
     const int n_my = a.B > (int)blockIdx.x ? (a.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&x_full, 1); tc::mbar_init(&wbar, 1); tc::mbar_init(&c1_done, 1); tc::mbar_init(&c2_done, 1);
-        tc::mbar_init(&x_empty, FB_WORKERS); tc::mbar_init(&xs_ready, FB_WORKERS); tc::mbar_init(&p1_ready, FB_WORKERS);
+        tc::mbar_init(&x_full, 1); tc::mbar_init(&wbar, 1); tc::mbar_init(&c1_done, 1);
+        tc::mbar_init(&x_empty, FB_WORKERS); tc::mbar_init(&xs_ready, FB_WORKERS);
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&p1_ready[i], FB_WORKERS); tc::mbar_init(&c2_done[i], 1); }
         tc::fence_barrier_init();
         logit_s = 0.f;
     }
@@ -479,17 +480,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     for (int ty = 0; ty < 2; ++ty)
                         tc::mma_f16_ss(tmem + TF_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512), ID_C1, ty != 0);
                 tc::mma_commit(&c1_done);
-                tc::mbar_wait(&p1_ready, ph);
-                tc::tc_fence_after();
+                // tile by tile behind the conv1 epilogue: conv2 tile t starts as soon as the P1 rows it reads (<= 128 t + 141) exist, and its
+                // commit lets the conv2 epilogue of that tile run while the later tiles are still in the tensor pipe
 #pragma unroll
-                for (int tile = 0; tile < 4; ++tile)
+                for (int tile = 0; tile < 4; ++tile) {
+                    tc::mbar_wait(&p1_ready[tile], ph);
+                    tc::tc_fence_after();
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             tc::mma_f16_ss(tmem + TF_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
                                            tc::smem_desc(KM128, w2 + t * 4096 + k * 32), ID_C2, (t | k) != 0);
-                tc::mma_commit(&c2_done);
+                    tc::mma_commit(&c2_done[tile]);
+                }
             }
         }
     } else {
@@ -585,10 +589,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     tc::sts128(rowp + (((2 * cell) ^ (R & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
                     tc::sts128(rowp + (((2 * cell + 1) ^ (R & 7)) << 4), make_uint4(o[4], o[5], o[6], o[7]));
                 }
+                // conv1 tiles <= 2 tt + 1 are in P1 once every worker is past this point: conv2 tile 0 reads P1 rows <= 141 (conv1 rows <= 544:
+                // tiles 0..4), tile 1 rows <= 269 (tiles 0..8), tiles 2 and 3 everything
+                if (tt == 2 || tt == 4 || tt == 6) {
+                    tc::tc_fence_before();
+                    tc::fence_proxy_async_smem();
+                    tc::mbar_arrive(&p1_ready[tt == 2 ? 0 : tt == 4 ? 1 : 2]);
+                    if (tt == 6) tc::mbar_arrive(&p1_ready[3]);
+                }
             }
-            tc::tc_fence_before();
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&p1_ready);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (w == 0) {                                             // P1 -> global for the backward (rows b*429 .. +429, two boxes)
                 tc::tma_store_2d(&map_p1a, smem + FS_P1, 0, b * P1_ROWS);
@@ -597,11 +606,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
             }
             if (it + 1 < n_my) build_xs(it + 1);                      // conv1 of this sample is done with XS: the next sample's rows are built under conv2's MMAs
             // ---- S5: conv2 epilogue -> A2 rows (global), fc partial dot
-            tc::mbar_wait(&c2_done, ph);
-            tc::tc_fence_after();
             float dot = 0.f;
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
+                tc::mbar_wait(&c2_done[tile], ph);
+                tc::tc_fence_after();
                 const int R = tile * 128 + tl;
                 uint32_t r[16];
                 tc::tmem_ld_32x16(tmem + tlane + TF_C2 + tile * 32 + h * 16, r);
