@@ -392,7 +392,8 @@ int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const flo
 //   S2  tcgen05   conv1: 14 row tiles x 2 taps (M128 x N16 x K16) -> 224 TMEM columns
 //   S3  workers   bias + LeakyReLU -> bf16 -> P1 super-pixel rows in shared memory (128-byte swizzle); one TMA store sends P1 to global
 //   S4  tcgen05   conv2: 4 row tiles x 4 taps x 4 K steps (M128 x N32 x K16), tap-shifted descriptors over the SAME P1 rows
-//   S5  workers   bias + LeakyReLU -> A2 rows to global; fc partial dots reduced per sample -> logits[b] (with the fc bias; no atomics)
+//   S5  workers   bias + LeakyReLU -> A2 rows in a shared-memory staging tile (one TMA store per sample); fc partial dots reduced per sample ->
+//                 logits[b] (with the fc bias; no global atomics)
 // P1 never makes the HBM round trip between conv1 and conv2.  HBM per sample: 12.8 KB read, 110 KB written (what the backward reads).
 // ================================================================================================================
 namespace {
@@ -404,14 +405,15 @@ constexpr int FS_W2 = FS_P1 + 67584;              // [4 t][32 oc][64 k] bf16 SW1
 constexpr int FS_W1 = FS_W2 + 16384;              // [2 ty][16 oc][16 k] bf16 SW32              1024
 constexpr int FS_X = FS_W1 + 1024;                // staged u8 input                            12800
 constexpr int FS_WF = FS_X + 12800;               // fc.weight slices, fp32, [8 (h, c4)][432 rows][4]: conflict-free LDS.128   55296
-constexpr int FS_TOTAL = FS_WF + 8 * 432 * 16;    // 182784
+constexpr int FS_A2 = ((FS_WF + 8 * 432 * 16 + 1023) / 1024) * 1024;      // A2 staging, 432 rows x 64 B, SW64 (TMA-stored once per sample)   27648
+constexpr int FS_TOTAL = FS_A2 + 432 * 64;        // 210944
 constexpr uint32_t TF_C1 = 0, TF_C2 = 256;        // TMEM: conv1 14 x 16 columns, conv2 4 x 32 columns
 
 struct FusedFwdArgs {
     const void* x; int x_f32;
     const float* b1; const float* b2; const float* wfcp; const float* bfc;
     __nv_bfloat16* xs; __nv_bfloat16* a2; float* logits;
-    int B;
+    int B; int dbg_skip;      // dbg_skip (env MMG_DBG_SKIP_FWD, timing experiments only): bit0 conv1, bit1 conv2 MMAs are not issued
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -421,6 +423,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                                                                        const __grid_constant__ CUtensorMap map_p1a, const __grid_constant__ CUtensorMap map_p1b,
+                                                                       const __grid_constant__ CUtensorMap map_a2a, const __grid_constant__ CUtensorMap map_a2b,
                                                                        const FusedFwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t x_full, x_empty, xs_ready, c1_done, p1_ready[4], c2_done[4], wbar;     // [4]: one per 128-row conv2 tile
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                 for (int tile = 0; tile < 14; ++tile)
 #pragma unroll
                     for (int ty = 0; ty < 2; ++ty)
-                        tc::mma_f16_ss(tmem + TF_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512), ID_C1, ty != 0);
+                        if (!(a.dbg_skip & 1)) tc::mma_f16_ss(tmem + TF_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512), ID_C1, ty != 0);
                 tc::mma_commit(&c1_done);
                 // tile by tile behind the conv1 epilogue: conv2 tile t starts as soon as the P1 rows it reads (<= 128 t + 141) exist, and its
                 // commit lets the conv2 epilogue of that tile run while the later tiles are still in the tensor pipe
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc::mma_f16_ss(tmem + TF_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
+                            if (!(a.dbg_skip & 2)) tc::mma_f16_ss(tmem + TF_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
                                            tc::smem_desc(KM128, w2 + t * 4096 + k * 32), ID_C2, (t | k) != 0);
                     tc::mma_commit(&c2_done[tile]);
                 }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
     } else {
         const int q = warp & 3, h = (warp - 2) >> 2, tl = q * 32 + lane, w = threadIdx.x - 64;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
-        const uint32_t xs_s = tc::smem_u32(smem + FS_XS), p1_s = tc::smem_u32(smem + FS_P1), x_s = tc::smem_u32(smem + FS_X);
+        const uint32_t xs_s = tc::smem_u32(smem + FS_XS), p1_s = tc::smem_u32(smem + FS_P1), x_s = tc::smem_u32(smem + FS_X), a2_s = tc::smem_u32(smem + FS_A2);
         float b1r[16], b2r[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) { b1r[c] = a.b1[c]; b2r[c] = a.b2[h * 16 + c]; }
@@ -512,6 +515,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float bfc = a.bfc[0];
         // ---- S1: XS rows (8 values = (dy,dx,ch) of super pixel (sy,sx) of the zero-padded input), to shared memory and to global
+        // Sample 0's rows also go to global memory row by row; later samples leave the SM as ONE bulk copy of the finished 27 KB (issued by
+        // thread 0 behind the barrier that ends the sample's conv2 epilogue), which keeps 1690 16-byte stores out of the workers' instruction stream.
         auto build_xs = [&](int it) {
             const int b = blockIdx.x + it * gridDim.x;
             if (!a.x_f32) tc::mbar_wait(&x_full, (uint32_t)(it & 1));
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     for (int e = 0; e < 8; ++e) f[e] = __float_as_uint((float)u[i][e]);      // integers 0..255 are exact in bf16 = the high half of the float
                     const uint4 pk = make_uint4(__byte_perm(f[0], f[1], 0x7632), __byte_perm(f[2], f[3], 0x7632), __byte_perm(f[4], f[5], 0x7632), __byte_perm(f[6], f[7], 0x7632));
                     tc::sts128(xs_s + rr * 16, pk);
-                    *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+                    if (it == 0) *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
                 }
             } else {
                 for (int rr = w; rr < XS_ROWS; rr += FB_WORKERS) {
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     }
                     const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     tc::sts128(xs_s + rr * 16, pk);
-                    *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
+                    if (it == 0) *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
                 }
             }
             tc::fence_proxy_async_smem();
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
             // ---- S3: conv1 epilogue -> P1 (rows = super pixels, 64 values = (dy,dx,c16)); even tiles for h = 0, odd tiles for h = 1
             tc::mbar_wait(&c1_done, ph);
             tc::tc_fence_after();
-            if (w == 0) tc::bulk_wait_group_read<0>();                // the previous sample's P1 store has finished reading shared memory
+            if (w == 0) tc::bulk_wait_group_read<1>();                // the previous sample's P1 store (every group but the newest) has finished reading shared memory
             asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
             for (int tt = 0; tt < 7; ++tt) {
@@ -598,7 +603,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     if (tt == 6) tc::mbar_arrive(&p1_ready[3]);
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (w == 0) tc::bulk_wait_group_read<0>();                // the previous sample's A2 store and this sample's XS store (issued one epilogue ago) are done
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // with shared memory: the A2 staging rows and the XS rows may be overwritten below
             if (w == 0) {                                             // P1 -> global for the backward (rows b*429 .. +429, two boxes)
                 tc::tma_store_2d(&map_p1a, smem + FS_P1, 0, b * P1_ROWS);
                 tc::tma_store_2d(&map_p1b, smem + FS_P1 + 224 * 128, 0, b * P1_ROWS + 224);
@@ -633,15 +639,24 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     dot = fmaf(bf_lo(o[c]), wv[2 * c], dot);                              // the bf16 values the backward will read
                     dot = fmaf(bf_hi(o[c]), wv[2 * c + 1], dot);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(a.a2 + ((size_t)b * P1_ROWS + R) * 32 + h * 16);
-                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                const uint32_t rowp = a2_s + R * 64;                  // A2 row -> staging (64-byte swizzle), stored by TMA below: full lines instead of half-sector stores
+                const int sw = (R >> 1) & 3;
+                tc::sts128(rowp + (((2 * h) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                tc::sts128(rowp + (((2 * h + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
             }
             dot = warp_sum(dot);
             if (lane == 0) atomicAdd(&logit_s, dot);
             tc::tc_fence_before();
+            tc::fence_proxy_async_smem();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (w == 0) { a.logits[b] = logit_s + bfc; logit_s = 0.f; }
+            if (w == 0) {
+                a.logits[b] = logit_s + bfc; logit_s = 0.f;
+                tc::tma_store_2d(&map_a2a, smem + FS_A2, 0, b * P1_ROWS);                 // A2 rows b*429 .. +429 (two boxes)
+                tc::tma_store_2d(&map_a2b, smem + FS_A2 + 216 * 64, 0, b * P1_ROWS + 216);
+                if (it + 1 < n_my)                                    // the next sample's XS rows (built above by all workers)
+                    tc::bulk_store_1d(a.xs + (size_t)(b + gridDim.x) * XS_ROWS * 8, xs_s, XS_ROWS * 16);
+                tc::bulk_commit_group();
+            }
             // (the next use of logit_s comes after the next sample's two bar.sync: ordered)
         }
         if (w == 0) tc::bulk_wait_group_read<0>();
@@ -665,17 +680,20 @@ int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const flo
     MMG_REQUIRE(B * XS_ROWS < (1LL << 31) - 4096, MMG_EUNSUPPORTED, "disc_fwd_fused: batch too large");
     MMG_REQUIRE(x_dtype != 2 || ((uintptr_t)x & 15) == 0, MMG_EINVAL, "disc_fwd_fused: x must be 16-byte aligned");
     const unsigned char* pk = (const unsigned char*)packed;
-    CUtensorMap map_w1, map_w2, map_p1a, map_p1b;
+    CUtensorMap map_w1, map_w2, map_p1a, map_p1b, map_a2a, map_a2b;
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w1, pk, 16, 32, 32, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (w1b)");
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w2, pk + 2048, 64, 128, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (w2p)");
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_p1a, p1, 64, (uint64_t)(B * P1_ROWS), 128, 64, 224, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (p1 a)");
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_p1b, p1, 64, (uint64_t)(B * P1_ROWS), 128, 64, 205, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (p1 b)");
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_a2a, a2, 32, (uint64_t)(B * P1_ROWS), 64, 32, 216, CU_TENSOR_MAP_SWIZZLE_64B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (a2 a)");
+    MMG_REQUIRE(tc::make_map_2d_bf16(&map_a2b, a2, 32, (uint64_t)(B * P1_ROWS), 64, 32, 213, CU_TENSOR_MAP_SWIZZLE_64B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (a2 b)");
     FusedFwdArgs a;
     a.x = x; a.x_f32 = x_dtype == 0; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
     a.xs = (__nv_bfloat16*)xs; a.a2 = (__nv_bfloat16*)a2; a.logits = logits; a.B = (int)B;
+    { const char* e = getenv("MMG_DBG_SKIP_FWD"); a.dbg_skip = e ? atoi(e) : 0; }
     const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
     MMG_CUDA(cudaFuncSetAttribute(disc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_TOTAL + 1024));
-    disc_fwd_fused_kernel<<<grid, FB_THREADS, FS_TOTAL + 1024, (cudaStream_t)stream>>>(map_w1, map_w2, map_p1a, map_p1b, a);
+    disc_fwd_fused_kernel<<<grid, FB_THREADS, FS_TOTAL + 1024, (cudaStream_t)stream>>>(map_w1, map_w2, map_p1a, map_p1b, map_a2a, map_a2b, a);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
