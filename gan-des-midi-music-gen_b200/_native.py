@@ -64,6 +64,7 @@ class GenLayerArgs(ctypes.Structure):
 
 SIGNATURES.update({
     "mmg_disc_fwd_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "mmg_disc_fwd_fused_gather": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mmg_disc_bwd_fused": (_I, [_P] * 11 + [_L, _P]),
     "mmg_gen_packed_weight_bytes": (_Z, [_I, _I]),
     "mmg_gen_pack_weight": (_I, [_P, _I, _I, _P, _P]),

@@ -410,7 +410,7 @@ constexpr int FS_TOTAL = FS_A2 + 432 * 64;        // 210944
 constexpr uint32_t TF_C1 = 0, TF_C2 = 256;        // TMEM: conv1 14 x 16 columns, conv2 4 x 32 columns
 
 struct FusedFwdArgs {
-    const void* x; int x_f32;
+    const void* x; int x_f32; const int64_t* x_index;       // x_index != NULL: sample b is row x_index[b] of x (the HBM-resident training set)
     const float* b1; const float* b2; const float* wfcp; const float* bfc;
     __nv_bfloat16* xs; __nv_bfloat16* a2; float* logits;
     int B; int dbg_skip;      // dbg_skip (env MMG_DBG_SKIP_FWD, timing experiments only): bit0 conv1, bit1 conv2 MMAs are not issued
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     const int b = blockIdx.x + it * gridDim.x;
                     if (it > 0) tc::mbar_wait(&x_empty, (uint32_t)((it - 1) & 1));
                     tc::mbar_expect_tx(&x_full, 12800);
-                    bulk_load_1d(smem + FS_X, (const unsigned char*)a.x + (size_t)b * 12800, 12800, &x_full);
+                    bulk_load_1d(smem + FS_X, (const unsigned char*)a.x + (size_t)(a.x_index ? a.x_index[b] : b) * 12800, 12800, &x_full);
                 }
             }
         }
@@ -549,13 +549,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) disc_fwd_fused_kernel(const __g
                     if (it == 0) *reinterpret_cast<uint4*>(a.xs + ((size_t)b * XS_ROWS + rr) * 8) = pk;
                 }
             } else {
+                const long long xb = a.x_index ? a.x_index[b] : b;
                 for (int rr = w; rr < XS_ROWS; rr += FB_WORKERS) {
                     const int sy = rr / XS_W, sx = rr - sy * XS_W;
                     float v[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int iy = 2 * sy + (e >> 2) - 1, ix = 2 * sx + ((e >> 1) & 1) - 1, ch = e & 1;
-                        v[e] = (iy >= 0 && iy < 128 && ix >= 0 && ix < 50) ? reinterpret_cast<const float*>(a.x)[(size_t)b * 12800 + (ch * 128 + iy) * 50 + ix] : 0.f;
+                        v[e] = (iy >= 0 && iy < 128 && ix >= 0 && ix < 50) ? reinterpret_cast<const float*>(a.x)[(size_t)xb * 12800 + (ch * 128 + iy) * 50 + ix] : 0.f;
                     }
                     const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     tc::sts128(xs_s + rr * 16, pk);
@@ -672,8 +673,18 @@ extern "C" {
 
 // x (B,2,128,50) uint8 (x_dtype 2) or float32 (x_dtype 0) -> xs (B*1690,8), p1 (B*429,64), a2 (B*429,32) bf16 and logits (B,) fp32
 // (fc bias included; nothing needs to be pre-initialised).
+int mmg_disc_fwd_fused_gather(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b,
+                              const float* fc_b, void* xs, void* p1, void* a2, float* logits, int64_t B, void* stream);
+
 int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b, void* xs, void* p1,
                        void* a2, float* logits, int64_t B, void* stream) {
+    return mmg_disc_fwd_fused_gather(x, x_dtype, nullptr, packed, conv1_b, conv2_b, fc_b, xs, p1, a2, logits, B, stream);
+}
+
+// The same with a gather: sample b of the pass is row x_index[b] (int64, device memory) of x -- the discriminator reads the real rolls
+// straight out of the HBM-resident training set by sampler index, no gathered copy of the batch is ever made.  x_index == NULL: rows 0..B-1.
+int mmg_disc_fwd_fused_gather(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b,
+                              const float* fc_b, void* xs, void* p1, void* a2, float* logits, int64_t B, void* stream) {
     MMG_REQUIRE(x && packed && conv1_b && conv2_b && fc_b && xs && p1 && a2 && logits && B >= 0, MMG_EINVAL, "disc_fwd_fused: bad arguments");
     MMG_REQUIRE(x_dtype == 0 || x_dtype == 2, MMG_EINVAL, "disc_fwd_fused: x_dtype must be 0 (f32) or 2 (u8)");
     if (B == 0) return MMG_OK;
@@ -688,7 +699,7 @@ int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const flo
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_a2a, a2, 32, (uint64_t)(B * P1_ROWS), 64, 32, 216, CU_TENSOR_MAP_SWIZZLE_64B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (a2 a)");
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_a2b, a2, 32, (uint64_t)(B * P1_ROWS), 64, 32, 213, CU_TENSOR_MAP_SWIZZLE_64B) == 0, MMG_EINVAL, "disc_fwd_fused: tensor map (a2 b)");
     FusedFwdArgs a;
-    a.x = x; a.x_f32 = x_dtype == 0; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
+    a.x = x; a.x_f32 = x_dtype == 0; a.x_index = x_index; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
     a.xs = (__nv_bfloat16*)xs; a.a2 = (__nv_bfloat16*)a2; a.logits = logits; a.B = (int)B;
     { const char* e = getenv("MMG_DBG_SKIP_FWD"); a.dbg_skip = e ? atoi(e) : 0; }
     const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);

@@ -39,17 +39,20 @@ class DiscTC:
         d = self.d
         N.call("mmg_disc_pack_weights", N.ptr(d.conv1.weight.data), N.ptr(d.conv2.weight.data), N.ptr(d.fc.weight.data), N.ptr(self.packed), N.stream())
 
-    def forward(self, x):
-        """x: (B,2,128,50) uint8 or float32 CUDA tensor -> logits (B,) fp32 (a view of an internal buffer)."""
-        N.require_cuda(x)
-        B = x.shape[0]
+    def forward(self, x, index=None):
+        """x: (B,2,128,50) uint8 or float32 CUDA tensor -> logits (B,) fp32 (a view of an internal buffer).
+        ``index`` (B,) int64 CUDA tensor: the pass runs on rows ``x[index]`` of a larger resident set, gathered inside the kernel."""
+        N.require_cuda(x, index)
+        B = x.shape[0] if index is None else index.numel()
         if B > self.cap or tuple(x.shape[1:]) != (2, 128, 50) or x.dtype not in _XD:
             raise ValueError(f"bad discriminator input {tuple(x.shape)} {x.dtype} (capacity {self.cap})")
+        if index is not None and (index.dtype != torch.int64 or not self.fused_forward):
+            raise ValueError("index must be an int64 tensor (fused forward only)")
         x = x.contiguous()
         d, s = self.d, N.stream()
         logits = self.logits[:B]
         if self.fused_forward:       # one persistent kernel: P1 stays in shared memory between conv1 and conv2 (csrc/disc_tc_fused.cu)
-            N.call("mmg_disc_fwd_fused", N.ptr(x), _XD[x.dtype], N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data),
+            N.call("mmg_disc_fwd_fused_gather", N.ptr(x), _XD[x.dtype], N.ptr(index), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data),
                    N.ptr(d.fc.bias.data), N.ptr(self.xs), N.ptr(self.p1), N.ptr(self.a2), N.ptr(logits), B, s)
             self.x, self.B = x, B
             return logits

@@ -165,15 +165,17 @@ class MMGANTrainer:
                 self.g1_out = m.generator1(noise1, inner)
                 self.g2_out = m.generator2(noise2, beats)
 
-    def _d_pass(self, x, target, loss, accumulate):
-        """forward + BCE + backward of the discriminator on one batch; grads accumulate into flat_grad"""
-        B = x.shape[0]
+    def _d_pass(self, x, target, loss, accumulate, index=None):
+        """forward + BCE + backward of the discriminator on one batch (rows ``x[index]`` when ``index`` is given); grads accumulate into flat_grad"""
+        B = x.shape[0] if index is None else index.numel()
         if self.tc is not None:
-            logits = self.tc.forward(x)
+            logits = self.tc.forward(x, index)
             dl = self.dlogit[:B]
             N.call("mmg_bce_logits_f32", N.ptr(logits), None, float(target), B, N.ptr(loss), int(accumulate), N.ptr(dl), 1.0 / B, None, N.stream())
             self.tc.backward(dl)
             return logits
+        if index is not None:
+            x = x.index_select(0, index)
         xf = x if x.dtype == torch.float32 else x.float()
         logits = self.m.discriminator(xf).squeeze(-1)
         lv = Fn.bce_with_logits(logits, float(target))
@@ -185,17 +187,17 @@ class MMGANTrainer:
         return logits.detach()
 
     # ------------------------------------------------------------------ one iteration
-    def _seg_d_gen(self, noise1, noise2, beats, real, fake_d, inner_d):
+    def _seg_d_gen(self, noise1, noise2, beats, real, fake_d, inner_d, real_index=None):
         """The D step's generator forwards (:294 -> :177-178)"""
         self._generators(noise1, noise2, beats, inner_d)
 
-    def _seg_d_disc(self, noise1, noise2, beats, real, fake_d, inner_d):
+    def _seg_d_disc(self, noise1, noise2, beats, real, fake_d, inner_d, real_index=None):
         """D step up to the gradients (:293, :304-307)"""
         self._zero_d_grads()
         self.logit_fake_d = self._d_pass(fake_d, 0.0, self.loss_d, False)
         if self.tc is not None:
             self.logit_fake_d = self.logit_fake_d.clone()
-        self.logit_real = self._d_pass(real, 1.0, self.loss_d, True)
+        self.logit_real = self._d_pass(real, 1.0, self.loss_d, True, real_index)
         if self.tc is not None:
             self.logit_real = self.logit_real.clone()
 
@@ -223,17 +225,19 @@ class MMGANTrainer:
         self.graph_launches += N.lib().mmg_launch_count() - l0
         return g
 
-    def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None):
-        B = real.shape[0]
+    def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None, real_index=None):
+        """``real_index`` (B,) int64 CUDA tensor: the real batch is ``real[real_index]`` -- ``real`` is then the whole HBM-resident training set and
+        the discriminator kernel gathers the rows itself (no gathered copy of the batch)."""
+        B = real.shape[0] if real_index is None else real_index.numel()
         if inner_d is None:
             inner_d = self._draw_inner(B, "d")
         if inner_g is None:
             inner_g = self._draw_inner(B, "g")
         self.gen_opt.zero_grad(set_to_none=True)
-        a_d, a_g = (noise1, noise2, beats, real, fake_d, inner_d), (noise1, noise2, beats, fake_g, inner_g)
+        a_d, a_g = (noise1, noise2, beats, real, fake_d, inner_d, real_index), (noise1, noise2, beats, fake_g, inner_g)
         graphs = None
         if self.use_graph and self.on_d_grads is None:
-            key = tuple(t.data_ptr() for t in (*a_d, fake_g, inner_g)) + (B, real.dtype, fake_d.dtype, fake_g.dtype)
+            key = tuple(t.data_ptr() for t in (*a_d, fake_g, inner_g) if t is not None) + (B, real.dtype, fake_d.dtype, fake_g.dtype, real_index is None)
             graphs = self._graphs.get(key)
             if graphs is None:
                 self._seen[key] = self._seen.get(key, 0) + 1
@@ -282,7 +286,8 @@ class HostBatchPipeline:
     ``dataset=(rolls, beats)``: the training set resident in HBM -- ``rolls`` (N,2,128,W) uint8/float32 and ``beats`` (N,50)
     CUDA tensors (the reference's ``MaestroDatasetPickle(..., device=device)`` also keeps its items on the device,
     datasets.py:73-87; 5.4 k MAESTRO slices are 69 MB).  A batch then carries ``real_idx`` (host int64 indices, what a
-    sampler yields) instead of ``real`` / ``beats``; the gather runs on the copy stream.  The fake rolls always come from the host:
+    sampler yields) instead of ``real`` / ``beats``; on the tensor-core path the discriminator kernel gathers the real rolls by index itself
+    (``mmg_disc_fwd_fused_gather``), otherwise the gather runs on the copy stream.  The fake rolls always come from the host:
 
     * as rolls: ``fake_d`` / ``fake_g`` (B,2,128,W) uint8 / float32 (what ``matrix_to_midi`` returns, matrix_sim_process.py:191-195), or
     * as note events: ``fake_d_events`` / ``fake_g_events`` = ``(dt float64 (E,), meta int32 (E,), offsets int64 (B+1,))`` pinned tensors, the
@@ -298,6 +303,7 @@ class HostBatchPipeline:
         dev = trainer.flat_grad.device
         self.dataset = dataset
         self.events = "fake_d_events" in example
+        self.gather_in_kernel = dataset is not None and trainer.tc is not None and getattr(trainer.tc, "fused_forward", False)
         self.raster = tuple(int(v) for v in raster)
         if self.events:
             from .MMGAN_MIDI_DES import datasets as ds
@@ -319,7 +325,7 @@ class HostBatchPipeline:
             N.require_cuda(rolls, beats)
             self.copy_keys = () if self.events else ("fake_d", "fake_g")
             self.stage = [{"fake_d": fake("fake_d"), "fake_g": fake("fake_g"),
-                           "real": torch.empty((B,) + tuple(rolls.shape[1:]), dtype=rolls.dtype, device=dev),
+                           "real": None if self.gather_in_kernel else torch.empty((B,) + tuple(rolls.shape[1:]), dtype=rolls.dtype, device=dev),
                            "beats": torch.empty((B,) + tuple(beats.shape[1:]), dtype=beats.dtype, device=dev),
                            "idx": torch.empty(B, dtype=torch.int64, device=dev)} for _ in range(2)]
             self.h2d_bytes = sum(example[k].numel() * example[k].element_size() for k in self.copy_keys) + B * 8
@@ -364,7 +370,8 @@ class HostBatchPipeline:
                 self._raster(slot, st["ev_g"], batch["fake_g_events"], st["fake_g"])
             if self.dataset is not None:
                 st["idx"].copy_(batch["real_idx"], non_blocking=True)
-                torch.index_select(self.dataset[0], 0, st["idx"], out=st["real"])
+                if not self.gather_in_kernel:
+                    torch.index_select(self.dataset[0], 0, st["idx"], out=st["real"])
                 torch.index_select(self.dataset[1], 0, st["idx"], out=st["beats"])
             self.ready[slot].record(self.copy_stream)
 
@@ -387,7 +394,10 @@ class HostBatchPipeline:
             n1, n2 = self.noise[slot]
             n1.normal_()                                                          # network_tests.py:284-285
             n2.normal_()
-            dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
+            if self.dataset is not None and self.gather_in_kernel:      # the discriminator kernel reads the real rolls by index out of the resident set
+                dl, gl = self.t.step(n1, n2, st["beats"], self.dataset[0], st["fake_d"], st["fake_g"], real_index=st["idx"])
+            else:
+                dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
             self.free[slot].record(main)
             self.losses_host.copy_(torch.stack([dl, gl]), non_blocking=False)
             yield self.losses_host

@@ -121,6 +121,11 @@ int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const flo
  * shared memory between the two convolutions; writes xs / p1 / a2 for the backward and logits (fc bias included). */
 int mmg_disc_fwd_fused(const void* x, int x_dtype, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
                        void* xs, void* p1, void* a2, float* logits, int64_t B, void* stream);
+/* The same with a gather: sample b of the pass is row x_index[b] (int64, device memory) of x, so the real rolls are read straight out of
+ * an HBM-resident training set by sampler index (what DataLoader(MaestroDatasetPickle(..., device), shuffle=True) delivers,
+ * network_tests.py:229-230,281) without materialising the batch.  x_index == NULL: rows 0..B-1. */
+int mmg_disc_fwd_fused_gather(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b,
+                              const float* fc_b, void* xs, void* p1, void* a2, float* logits, int64_t B, void* stream);
 
 /* ---- bf16 tensor-core generator blocks ([Linear -> BatchNorm1d -> Sigmoid], network_tests.py:75-80, as used by Generator
  * :58-90 and BeatGenerator :93-123) ----

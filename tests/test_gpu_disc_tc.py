@@ -133,3 +133,27 @@ def test_full_size_batch_properties():
         assert _rel_l2(parts[n], full[n]) < 5e-4, (n, _rel_l2(parts[n], full[n]))      # fp32 accumulation order under heavy cancellation (zero-mean dlogits)
     # idempotence of the forward on the same buffers
     assert (tc.forward(x) - full_logits).abs().max().item() <= 1e-5 * scale + 1e-6
+
+
+def test_forward_gathers_rows_by_index():
+    """mmg_disc_fwd_fused_gather: the pass on rows x[index] of a resident set (duplicates and arbitrary order included) == the pass on the
+    gathered copy, activations for the backward included."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.disc_tc import DiscTC
+    sd = mo.synth_state(mo.mmgan_shapes(), seed=31, d_scale=0.25)
+    D = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
+    D.load_state_dict({k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")})
+    NDS, B = 500, 333
+    for dtype in (torch.uint8, torch.float32):
+        pool = torch.from_numpy(mo.synth_rolls(NDS, 50, seed=2, p=0.05)).to(DEV).to(dtype)
+        idx = torch.randint(0, NDS, (B,), device=DEV)
+        idx[:7] = 3                                                   # duplicates
+        a = DiscTC(D, max_batch=B)
+        want = a.forward(pool[idx].contiguous()).clone()
+        want_p1, want_xs = a.p1[:B * 429].clone(), a.xs[:B * 1690].clone()
+        b = DiscTC(D, max_batch=B)
+        got = b.forward(pool, idx)
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 1e-6
+        assert torch.equal(b.p1[:B * 429], want_p1) and torch.equal(b.xs[:B * 1690], want_xs)
+    with pytest.raises(ValueError):
+        b.forward(pool, idx.int())
