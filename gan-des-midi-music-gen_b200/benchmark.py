@@ -316,7 +316,7 @@ def run(args):
                     "api": "trainer.HostBatchPipeline.run: pinned host batches = the note-event streams of the simulated songs (what the DES bridge hands to "
                            "generate_piano_roll: 320 messages per song, 12 B per message) + sampler indices; events copied H2D and rasterised on the device "
                            "(mmg_raster_piano_roll, bit-exact) into the uint8 fake rolls, real rolls / beats gathered from the HBM-resident training set, "
-                           "copies + rasterisation of batch i+1 overlapped with the iteration of batch i; losses read back every step",
+                           "real rolls read by index inside the discriminator kernel, copies + rasterisation of batch i+1 overlapped with the iteration of batch i; the two losses of every step are read back to pinned host memory (waited for one iteration later)",
                     "rolls_u8_variant": {"value": rolls / sec_e2e_rolls, "unit": "rolls/s", "h2d_bytes_per_step": pipe_rolls.h2d_bytes,
                                          "ms_per_step": sec_e2e_rolls / args.steps * 1e3,
                                          "api": "same pipeline fed with ready-made uint8 fake rolls (12.8 KB per roll over PCIe)"}},

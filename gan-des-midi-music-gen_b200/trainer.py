@@ -341,7 +341,8 @@ class HostBatchPipeline:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
-        self.losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        self.losses_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.read = [torch.cuda.Event() for _ in range(2)]
 
     def _raster(self, slot, dev_ev, host_ev, out):
         """H2D of one pass's message streams + device rasterisation into the pass's uint8 roll buffer (on the copy stream)."""
@@ -376,7 +377,10 @@ class HostBatchPipeline:
             self.ready[slot].record(self.copy_stream)
 
     def run(self, batches):
-        """Generator: yields the pinned (2,) tensor [disc_loss, gen_loss] after each batch's iteration."""
+        """Generator: yields the pinned (2,) tensor [disc_loss, gen_loss] of every batch, in order.  The read-back of iteration i is
+        enqueued right behind it (stream order) and waited for AFTER iteration i + 1 has been enqueued, so the host-side work of the next
+        iteration (copies, rasteriser launches, graph launch) does not leave the GPU idle behind a blocking ``.item()``
+        (network_tests.py:320-321 blocks; the values are the same, they arrive one iteration later; the last one is flushed at the end)."""
         main = torch.cuda.current_stream()
         it = iter(batches)
         cur = next(it, None)
@@ -384,6 +388,7 @@ class HostBatchPipeline:
             return
         self._issue(0, cur, True)
         i = 0
+        pending = None
         while cur is not None:
             slot = i & 1
             nxt = next(it, None)
@@ -399,6 +404,14 @@ class HostBatchPipeline:
             else:
                 dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
             self.free[slot].record(main)
-            self.losses_host.copy_(torch.stack([dl, gl]), non_blocking=False)
-            yield self.losses_host
+            host = self.losses_host[slot]
+            host[0:1].copy_(dl.reshape(1), non_blocking=True)
+            host[1:2].copy_(gl.reshape(1), non_blocking=True)
+            self.read[slot].record(main)
+            if pending is not None:
+                self.read[pending].synchronize()
+                yield self.losses_host[pending]
+            pending = slot
             cur, i = nxt, i + 1
+        self.read[pending].synchronize()
+        yield self.losses_host[pending]
