@@ -42,16 +42,20 @@ template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(unsig
 //   One __syncthreads() per chunk hands chunk k to the replay warp and buffer (k+1)&1 back to the chain warp.
 // The whole batch is in flight at once (15 KB of shared memory per song); the kernel's floor is the fp64 add latency x messages per song.
 // ------------------------------------------------------------------------------------------------
-constexpr int SK_CH = 512;            // messages per chunk
-constexpr int SK_CJ = SK_CH / 32;
+constexpr int SK_CH_LONG = 512;       // messages per chunk; short songs (a few hundred messages: the training loop's simulated songs) use 128 so that the
+constexpr int SK_CH_SHORT = 128;      // chain of chunk k + 1 still overlaps the replay of chunk k
 constexpr int SK_CAP = 8;             // bin capacity per pitch (a full bin triggers a drain of the warp's bins)
 constexpr int SK_R = 2;               // replay warps per song; warp w owns the pitches p with p % SK_R == w (rows are independent)
 
-template <typename OutT, int R>
+constexpr int SK_TILE_BYTES = 12800;  // songs whose two planes fit this many bytes (the training loop's 2 x 128 x 50 uint8 rolls) are built in SHARED
+                                      // memory and leave the SM as coalesced 16-byte stores: no scattered global stores at all
+
+template <typename OutT, int R, int SK_CH, bool SMEM_OUT>
 __global__ void __launch_bounds__(32 * (1 + R), R == 1 ? 12 : 9)
 raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta, const int64_t* __restrict__ offsets, int S, int W, int lo,
                      int hi, OutT* __restrict__ out, int32_t* __restrict__ status) {
-    static_assert(SK_CJ % R == 0 && 128 % (32 * R) == 0, "replay warps must divide the chunk groups and the pitch range");
+    constexpr int SK_CJ = SK_CH / 32;
+    static_assert(SK_CJ % R == 0 && 128 % (32 * R) == 0 && SK_CH % 32 == 0, "replay warps must divide the chunk groups and the pitch range");
     __shared__ __align__(16) double tbuf[2][SK_CH];
     __shared__ int bin_s[SK_CAP][128];              // per-pitch bins: steps ...
     __shared__ uint16_t bin_v[SK_CAP][128];         // ... and off | velocity << 1, in message order
@@ -59,6 +63,7 @@ raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__
     __shared__ int on[128];
     __shared__ int fh[R], fst[R];                   // per replay warp: first halting message of its share of the chunk, its status bits
     __shared__ int halt_flag;
+    __shared__ uint4 otile[SMEM_OUT ? SK_TILE_BYTES / 16 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t song = blockIdx.x;
     const int64_t a0 = offsets[song];
@@ -118,11 +123,12 @@ raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__
     const int rw = warp - 1;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int Wo = hi - lo;
-    OutT* __restrict__ oroll = out + (size_t)song * 2 * 128 * Wo;
-    OutT* __restrict__ odur = oroll + (size_t)128 * Wo;
+    OutT* gout = out + (size_t)song * 2 * 128 * Wo;
+    OutT* oroll = SMEM_OUT ? reinterpret_cast<OutT*>(otile) : gout;         // SMEM_OUT: the song's planes are built in shared memory
+    OutT* odur = oroll + (size_t)128 * Wo;
     // zero fill: just in time by 128-byte column blocks when a row is a whole number of 16-byte words, else the whole song up front
     const int row_bytes = Wo * (int)sizeof(OutT);
-    const bool jit = (row_bytes & 15) == 0;
+    const bool jit = !SMEM_OUT && (row_bytes & 15) == 0;
     const int rowq = row_bytes >> 4;                                // 16-byte words per row
     const int nblk = jit ? (rowq + 7) >> 3 : 0;
     constexpr int CPB = 128 / (int)sizeof(OutT);                    // output columns per fill block
@@ -278,6 +284,12 @@ raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__
     __syncwarp();
     drain();
     while (filled < nblk) fill_block(filled++);                     // columns no note of this warp's pitches reached
+    if (SMEM_OUT) {                                                 // the finished planes leave the SM once, as coalesced 16-byte stores
+        if (R > 1) asm volatile("bar.sync 1, %0;" ::"r"(32 * R) : "memory");
+        const int cnt = (int)((size_t)2 * 128 * Wo * sizeof(OutT) / 16);
+        uint4* g = reinterpret_cast<uint4*>(gout);
+        for (int i = lane + 32 * rw; i < cnt; i += 32 * R) g[i] = otile[i];
+    }
     if (status && rw == 0 && lane == 0) status[song] = st;
 }
 
@@ -643,12 +655,16 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
         MMG_LAUNCH_CHECK();
         return MMG_OK;
     }
-    if (out_dtype == 0)
-        raster_stream_kernel<float, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (float*)out, status);
-    else if (out_dtype == 1)
-        raster_stream_kernel<__nv_bfloat16, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (__nv_bfloat16*)out, status);
-    else
-        raster_stream_kernel<uint8_t, SK_R><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (uint8_t*)out, status);
+    const bool short_songs = total_events <= 1024 * n_songs;           // average song length decides the chunk size
+    const size_t esz = out_dtype == 0 ? 4 : out_dtype == 1 ? 2 : 1;
+    const bool tile = short_songs && (size_t)2 * 128 * (hi - lo) * esz <= (size_t)SK_TILE_BYTES;
+#define MMG_STREAM(T, CH, SM) raster_stream_kernel<T, SK_R, CH, SM><<<(int)n_songs, 32 * (1 + SK_R), 0, stream>>>(dt, meta, offsets, (int)S, (int)W, (int)lo, (int)hi, (T*)out, status)
+#define MMG_STREAM_T(T) do { if (tile) MMG_STREAM(T, SK_CH_SHORT, true); else if (short_songs) MMG_STREAM(T, SK_CH_SHORT, false); else MMG_STREAM(T, SK_CH_LONG, false); } while (0)
+    if (out_dtype == 0) MMG_STREAM_T(float);
+    else if (out_dtype == 1) MMG_STREAM_T(__nv_bfloat16);
+    else MMG_STREAM_T(uint8_t);
+#undef MMG_STREAM_T
+#undef MMG_STREAM
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
