@@ -328,6 +328,109 @@ __global__ void gen_pack_weights_kernel(const float* __restrict__ w, int N, int 
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// ------------------------------------------------------------------------------------------------
+// Analytic batch statistics of a WIDE layer fed by a NARROW one (the generator's 64 -> 4096 output layer): z = a W^T + b, so
+//   sum_r z[r][n]   = w_n . s + M b_n                       with s = sum_r a_r            (K values)
+//   sum_r z[r][n]^2 = w_n^T G w_n + 2 b_n (w_n . s) + M b_n^2   with G = sum_r a_r a_r^T  (K x K Gram matrix)
+// i.e. 64 x 64 + 64 numbers about the input replace a whole GEMM pass whose only product was the column sums (M x 4096 accumulators read back
+// from TMEM and squared).  a and w are the SAME bf16-rounded operands the tensor-core pass multiplies; sums are accumulated in fp64.
+// ------------------------------------------------------------------------------------------------
+constexpr int GS_K = 64;                           // input features handled by the Gram path
+constexpr int GS_ROWS = 64;                        // rows per shared-memory tile
+constexpr int GS_PART = GS_K * GS_K + GS_K;        // doubles per partial result: G then s
+
+__global__ void __launch_bounds__(256) gen_gram_partial_kernel(const float* __restrict__ z, long long M, int K, const double* __restrict__ in_sums,
+                                                               double count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                               double* __restrict__ part) {
+    __shared__ float at[GS_ROWS][GS_K + 1];
+    __shared__ float sc[GS_K], sh[GS_K];
+    const int tid = threadIdx.x;
+    if (tid < GS_K) {
+        float s = 0.f, h = 0.f, mu, var;
+        if (tid < K) bn_scale_shift(in_sums[tid], in_sums[K + tid], count, gamma[tid], beta[tid], eps, s, h, mu, var);
+        sc[tid] = s * NEG_LOG2E; sh[tid] = h * NEG_LOG2E;
+    }
+    __syncthreads();
+    const int i0 = (tid >> 4) * 4, j0 = (tid & 15) * 4;              // this thread's 4 x 4 block of G
+    double acc[16], ssum = 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+    const long long tiles = (M + GS_ROWS - 1) / GS_ROWS;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        {   // a = bf16(sigmoid(BN(z))) exactly as the tensor-core kernel builds its A operand; 16 values per thread
+            const int r = tid >> 2, k0 = (tid & 3) * 16;
+            const long long row = tile * GS_ROWS + r;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int k = k0 + e;
+                float v = 0.f;
+                if (row < M && k < K) v = __bfloat162float(__float2bfloat16(fast_sigmoid_affine(z[row * K + k], sc[k], sh[k])));
+                at[r][k] = v;
+            }
+        }
+        __syncthreads();
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < GS_ROWS; ++r) {
+            float ai[4], aj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ai[u] = at[r][i0 + u]; aj[u] = at[r][j0 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) f[4 * u + v] = fmaf(ai[u], aj[v], f[4 * u + v]);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += (double)f[e];        // fp32 inside a 64-row tile (values in (0,1)), fp64 across tiles
+        if (tid < GS_K) {
+            float c = 0.f;
+            for (int r = 0; r < GS_ROWS; ++r) c += at[r][tid];
+            ssum += (double)c;
+        }
+        __syncthreads();
+    }
+    double* out = part + (size_t)blockIdx.x * GS_PART;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) out[(i0 + u) * GS_K + j0 + v] = acc[4 * u + v];
+    if (tid < GS_K) out[GS_K * GS_K + tid] = ssum;
+}
+
+__global__ void gen_gram_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ red) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= GS_PART) return;
+    double a = 0.0;
+    for (int p = 0; p < nparts; ++p) a += part[(size_t)p * GS_PART + i];
+    red[i] = a;
+}
+
+__global__ void __launch_bounds__(128) gen_gram_colstats_kernel(const double* __restrict__ red, const float* __restrict__ w, const float* __restrict__ bias,
+                                                                int N, int K, double count, double* __restrict__ out_sums) {
+    __shared__ double Gs[GS_PART];
+    for (int i = threadIdx.x; i < GS_PART; i += blockDim.x) Gs[i] = red[i];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float wn[GS_K];
+#pragma unroll
+    for (int k = 0; k < GS_K; ++k) wn[k] = k < K ? __bfloat162float(__float2bfloat16(w[(size_t)n * K + k])) : 0.f;      // the bf16 operand of the GEMM
+    double q = 0.0, l = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < GS_K; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < GS_K; ++j) t = fma(Gs[i * GS_K + j], (double)wn[j], t);
+        q = fma(t, (double)wn[i], q);
+        l = fma(Gs[GS_K * GS_K + i], (double)wn[i], l);
+    }
+    const double b = bias ? (double)bias[n] : 0.0;
+    out_sums[n] = l + count * b;
+    out_sums[N + n] = q + 2.0 * b * l + count * b * b;
+}
+
 }  // namespace
 
 extern "C" {
@@ -343,6 +446,35 @@ int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream
     MMG_REQUIRE(w && packed && N > 0 && K > 0, MMG_EINVAL, "gen_pack_weight: bad arguments");
     const int Np = N > 256 ? round_up(N, 256) : round_up(N, 32), Kp = round_up(K, 64);
     gen_pack_weights_kernel<<<(Np * Kp + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, N, K, Np, Kp, (__nv_bfloat16*)packed);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// workspace of mmg_gen_layer_stats_gram: one partial (G, s) per CTA + the reduced copy
+size_t mmg_gen_layer_stats_gram_workspace(void) { return sizeof(double) * (size_t)GS_PART * (MMG_NUM_SMS + 1); }
+
+// Batch sums of z = sigmoid(BN(z_prev)) W^T + b over the M local rows, written to out_sums (sum | sum of squares, fp64 [2][N]) WITHOUT running
+// the GEMM: see the Gram-matrix comment above.  z_prev (M,K) fp32 with K <= 64 and K % 8 == 0 is the previous layer's pre-activation, in_sums its
+// batch sums over stat_count rows (0 = M); weight (N,K) / bias (N,) are the fp32 master tensors of the layer (rounded to bf16 here exactly as
+// mmg_gen_pack_weight does).  Train mode only.
+int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double* in_sums, int64_t stat_count, const float* in_gamma,
+                             const float* in_beta, float eps, const float* weight, const float* bias, int N, double* out_sums, void* workspace,
+                             size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMG_REQUIRE(z_prev && in_sums && in_gamma && in_beta && weight && out_sums && workspace && M > 0 && N > 0, MMG_EINVAL, "gen_layer_stats_gram: bad arguments");
+    MMG_REQUIRE(K > 0 && K <= GS_K, MMG_EUNSUPPORTED, "gen_layer_stats_gram: at most %d input features (got %d)", GS_K, K);
+    MMG_REQUIRE(ws_bytes >= mmg_gen_layer_stats_gram_workspace(), MMG_EINVAL, "gen_layer_stats_gram: workspace too small");
+    const double count = (double)(stat_count > 0 ? stat_count : M);
+    MMG_REQUIRE(count > 1, MMG_EINVAL, "Expected more than 1 value per channel when training, got input size (%lld, %d)", (long long)M, K);
+    double* part = (double*)workspace;
+    double* red = part + (size_t)GS_PART * MMG_NUM_SMS;
+    const long long tiles = (M + GS_ROWS - 1) / GS_ROWS;
+    const int grid = (int)(tiles < MMG_NUM_SMS ? tiles : MMG_NUM_SMS);
+    gen_gram_partial_kernel<<<grid, 256, 0, stream>>>(z_prev, (long long)M, K, in_sums, count, in_gamma, in_beta, eps, part);
+    MMG_LAUNCH_CHECK();
+    gen_gram_reduce_kernel<<<(GS_PART + 255) / 256, 256, 0, stream>>>(part, grid, red);
+    MMG_LAUNCH_CHECK();
+    gen_gram_colstats_kernel<<<(N + 127) / 128, 128, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

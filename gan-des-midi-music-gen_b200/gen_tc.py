@@ -19,7 +19,7 @@ from . import _native as N
 
 
 class GenTC:
-    def __init__(self, gen, max_batch, process_group=None, sync_bn=False):
+    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=False):
         self.g = gen
         dist = torch.distributed
         self.pg = process_group
@@ -42,6 +42,10 @@ class GenTC:
             o += 2 * w
         self.sums = torch.zeros(o, dtype=torch.float64, device=dev)     # [layer][sum | sumsq][width]
         self.sum_views = [self.sums[a:a + 2 * w] for a, w in zip(offs, self.widths)]
+        # the wide output layer's batch statistics come from the 64 x 64 Gram matrix of its input instead of a GEMM pass (csrc/gen_tc.cu)
+        last = self.blocks[-1][0]
+        self.gram_stats = bool(gram_stats) and last.in_features <= 64 and last.in_features % 8 == 0 and last.out_features >= 512
+        self.gram_ws = torch.empty(N.lib().mmg_gen_layer_stats_gram_workspace(), dtype=torch.uint8, device=dev) if self.gram_stats else None
         self.pack()
 
     def pack(self, force=True):
@@ -99,7 +103,13 @@ class GenTC:
             else:
                 a.out_gamma, a.out_beta = N.ptr(bn.weight.data), N.ptr(bn.bias.data)
                 a.out_run_mean, a.out_run_var = N.ptr(bn.running_mean), N.ptr(bn.running_var)
-                if training:                       # pass 1: batch sums only (also the one update of the previous layer's running stats)
+                if training and self.gram_stats:   # batch sums of this layer from the Gram matrix of its input: no GEMM pass for the statistics
+                    pbn = self.blocks[i - 1][1]
+                    N.call("mmg_gen_layer_stats_gram", N.ptr(self.z[i - 1]), B, self.widths[i - 1], N.ptr(self.sum_views[i - 1]), B * self.world,
+                           N.ptr(pbn.weight.data), N.ptr(pbn.bias.data), pbn.eps, N.ptr(lin.weight.data), N.ptr(lin.bias.data), lin.out_features,
+                           N.ptr(self.sum_views[i]), N.ptr(self.gram_ws), self.gram_ws.numel(), s)
+                    self._sync(i)                  # (the single pass below also makes the one update of the previous layer's running stats)
+                elif training:                     # pass 1: batch sums only (also the one update of the previous layer's running stats)
                     a.out_sums = N.ptr(self.sum_views[i])
                     N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
                     self._sync(i)

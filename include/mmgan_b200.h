@@ -153,6 +153,14 @@ typedef struct mmg_gen_layer_args {
 size_t mmg_gen_packed_weight_bytes(int N, int K);
 int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream);
 int mmg_gen_layer_fwd(const mmg_gen_layer_args* args, void* stream);
+/* Batch statistics of a wide layer fed by a narrow one (the generators' 64 -> 4096 output block, network_tests.py:71,78) without a GEMM pass:
+ * with a = sigmoid(BN(z_prev)) (the layer's bf16 input operand), s = sum_r a_r and G = sum_r a_r a_r^T, the column sums of z = a W^T + b are
+ * w_n.s + M b_n and those of z^2 are w_n^T G w_n + 2 b_n w_n.s + M b_n^2 (fp64).  Writes out_sums [2][N] for the M local rows; K <= 64;
+ * in_sums / stat_count as in mmg_gen_layer_args (in_mode 1).  workspace: mmg_gen_layer_stats_gram_workspace() bytes. */
+size_t mmg_gen_layer_stats_gram_workspace(void);
+int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double* in_sums, int64_t stat_count, const float* in_gamma,
+                             const float* in_beta, float eps, const float* weight, const float* bias, int N, double* out_sums, void* workspace,
+                             size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

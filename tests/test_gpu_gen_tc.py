@@ -79,3 +79,33 @@ def test_gen_tc_rejects_single_sample_in_training():
     g = nt.Generator(z_dim=50, adj_size=(64, 64), device="cuda").cuda().train()
     with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
         GenTC(g, 4).forward(torch.randn(1, 50).cuda(), torch.randn(1, 50).cuda())
+
+
+@pytest.mark.parametrize("B", [16, 333, 4096])
+def test_gram_statistics_match_the_gemm_statistics_pass(B):
+    """The wide output layer's batch sums from the 64 x 64 Gram matrix of its input (mmg_gen_layer_stats_gram) vs the GEMM statistics pass they
+    replace: same bf16 operands, so sums, outputs and running statistics agree to accumulation order (fp32 tensor-core sums vs fp64)."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    out = {}
+    for gram in (True, False):
+        torch.manual_seed(7)
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device="cuda")
+        g = m.generator1.train()
+        with torch.no_grad():
+            for blk in g.gen:
+                blk[1].weight.uniform_(0.5, 1.5); blk[1].bias.uniform_(-0.5, 0.5); blk[0].bias.uniform_(-0.2, 0.2)
+        torch.manual_seed(8)
+        noise, inner = torch.randn(B, 50, device="cuda"), torch.randn(B, 50, device="cuda")
+        tc = GenTC(g, max_batch=B, gram_stats=gram)
+        assert tc.gram_stats == gram
+        y = tc.forward(noise, inner).clone()
+        torch.cuda.synchronize()
+        out[gram] = (y, tc.sum_views[3].clone(), g.gen[3][1].running_mean.clone(), g.gen[3][1].running_var.clone(), g.gen[2][1].running_var.clone())
+    a, b = out[True], out[False]
+    n = 4096
+    assert torch.allclose(a[1][:n], b[1][:n], rtol=1e-5, atol=1e-4 * B), "column sums"
+    assert torch.allclose(a[1][n:], b[1][n:], rtol=1e-5, atol=1e-4 * B), "column sums of squares"
+    assert (a[0] - b[0]).abs().max().item() < 1e-4
+    assert torch.allclose(a[2], b[2], rtol=1e-5, atol=1e-6) and torch.allclose(a[3], b[3], rtol=1e-4, atol=1e-7)
+    assert torch.equal(a[4], b[4]), "the previous layer's running statistics are updated exactly once either way"
