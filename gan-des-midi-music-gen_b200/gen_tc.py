@@ -19,7 +19,7 @@ from . import _native as N
 
 
 class GenTC:
-    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=False):
+    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=True):
         self.g = gen
         dist = torch.distributed
         self.pg = process_group
