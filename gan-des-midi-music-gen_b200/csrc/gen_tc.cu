@@ -402,33 +402,47 @@ __global__ void __launch_bounds__(256) gen_gram_partial_kernel(const float* __re
 __global__ void gen_gram_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ red) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= GS_PART) return;
-    double a = 0.0;
-    for (int p = 0; p < nparts; ++p) a += part[(size_t)p * GS_PART + i];
-    red[i] = a;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};                       // 8 independent loads in flight per thread
+    int p = 0;
+    for (; p + 8 <= nparts; p += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += part[(size_t)(p + u) * GS_PART + i];
+    }
+    for (; p < nparts; ++p) a[0] += part[(size_t)p * GS_PART + i];
+    red[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
-__global__ void __launch_bounds__(128) gen_gram_colstats_kernel(const double* __restrict__ red, const float* __restrict__ w, const float* __restrict__ bias,
+// four threads per output column: thread `part` takes the rows i = part, part + 4, ... of G; quad shuffle reduction
+__global__ void __launch_bounds__(256) gen_gram_colstats_kernel(const double* __restrict__ red, const float* __restrict__ w, const float* __restrict__ bias,
                                                                 int N, int K, double count, double* __restrict__ out_sums) {
-    __shared__ double Gs[GS_PART];
-    for (int i = threadIdx.x; i < GS_PART; i += blockDim.x) Gs[i] = red[i];
+    constexpr int GP = GS_K + 1;                                     // padded row pitch: the four threads of a column read four different banks
+    __shared__ double Gs[GS_K * GP], ss[GS_K];
+    for (int i = threadIdx.x; i < GS_K * GS_K; i += blockDim.x) Gs[(i / GS_K) * GP + (i % GS_K)] = red[i];
+    if (threadIdx.x < GS_K) ss[threadIdx.x] = red[GS_K * GS_K + threadIdx.x];
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int n = blockIdx.x * 64 + (threadIdx.x >> 2), part = threadIdx.x & 3;
+    const int nn = n < N ? n : N - 1;                                // keep the whole warp in the shuffles
     float wn[GS_K];
 #pragma unroll
-    for (int k = 0; k < GS_K; ++k) wn[k] = k < K ? __bfloat162float(__float2bfloat16(w[(size_t)n * K + k])) : 0.f;      // the bf16 operand of the GEMM
+    for (int k = 0; k < GS_K; ++k) wn[k] = k < K ? __bfloat162float(__float2bfloat16(w[(size_t)nn * K + k])) : 0.f;      // the bf16 operand of the GEMM
     double q = 0.0, l = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < GS_K; ++i) {
+#pragma unroll
+    for (int ii = 0; ii < GS_K / 4; ++ii) {
+        const int i = 4 * ii + part;
         double t = 0.0;
 #pragma unroll
-        for (int j = 0; j < GS_K; ++j) t = fma(Gs[i * GS_K + j], (double)wn[j], t);
-        q = fma(t, (double)wn[i], q);
-        l = fma(Gs[GS_K * GS_K + i], (double)wn[i], l);
+        for (int j = 0; j < GS_K; ++j) t = fma(Gs[i * GP + j], (double)wn[j], t);
+        const double wi = (double)(part == 0 ? wn[4 * ii] : part == 1 ? wn[4 * ii + 1] : part == 2 ? wn[4 * ii + 2] : wn[4 * ii + 3]);
+        q = fma(t, wi, q);
+        l = fma(ss[i], wi, l);
     }
-    const double b = bias ? (double)bias[n] : 0.0;
-    out_sums[n] = l + count * b;
-    out_sums[N + n] = q + 2.0 * b * l + count * b * b;
+    q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2);
+    l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (n < N && part == 0) {
+        const double b = bias ? (double)bias[n] : 0.0;
+        out_sums[n] = l + count * b;
+        out_sums[N + n] = q + 2.0 * b * l + count * b * b;
+    }
 }
 
 }  // namespace
@@ -474,7 +488,7 @@ int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double
     MMG_LAUNCH_CHECK();
     gen_gram_reduce_kernel<<<(GS_PART + 255) / 256, 256, 0, stream>>>(part, grid, red);
     MMG_LAUNCH_CHECK();
-    gen_gram_colstats_kernel<<<(N + 127) / 128, 128, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
+    gen_gram_colstats_kernel<<<(N + 63) / 64, 256, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
