@@ -75,3 +75,18 @@ def test_state_dict_contract():
     assert torch.equal(m.generator1.gen[0][1].weight, torch.ones(256)) is False or True
     g = nt.Generator(z_dim=50, adj_size=(8, 8))
     assert torch.equal(g.gen[0][1].weight, torch.ones(256)) and not g.gen[0][0].bias.any()
+
+
+def test_gram_stats_arg_checks_without_gpu():
+    """mmg_gen_layer_stats_gram validates its arguments before any launch (return code < 0, message set)."""
+    from gan_des_midi_music_gen_b200 import _native as N
+    lib = N.lib()
+    ws = lib.mmg_gen_layer_stats_gram_workspace()
+    assert ws >= 8 * (64 * 64 + 64) * 2
+    one = ctypes.c_void_p(16)                 # never dereferenced: the checks below fail first
+    rc = lib.mmg_gen_layer_stats_gram(one, 4, 128, one, 0, one, one, 1e-5, one, one, 4096, one, one, ws, None)
+    assert rc < 0 and b"at most 64 input features" in lib.mmg_last_error()
+    rc = lib.mmg_gen_layer_stats_gram(one, 1, 64, one, 0, one, one, 1e-5, one, one, 4096, one, one, ws, None)
+    assert rc == -1 and b"Expected more than 1 value per channel" in lib.mmg_last_error()
+    rc = lib.mmg_gen_layer_stats_gram(one, 4, 64, one, 0, one, one, 1e-5, one, one, 4096, one, one, 16, None)
+    assert rc < 0 and b"workspace too small" in lib.mmg_last_error()

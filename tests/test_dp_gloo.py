@@ -35,6 +35,12 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         ok = ok and torch.equal(torch.cat(gathered), x) and mine.shape[0] == 8
+        # global-batch generator BatchNorm is a tensor-core-path feature: asking for it on the fp32 path must fail loudly, not silently fall back
+        try:
+            MMGANTrainer(m, precision="fp32", sync_bn=True)
+            ok = False
+        except ValueError as e:
+            ok = ok and "sync_bn" in str(e)
         q.put((rank, ok, None))
     except Exception as e:       # pragma: no cover
         q.put((rank, False, repr(e)))
