@@ -18,7 +18,9 @@
 // HBM per sample and pass: 110 KB read (the unfused chain: 382 KB read + 137 KB written).
 #include "common.cuh"
 #include "tc_common.cuh"
-#include <stdlib.h>
+#ifdef MMG_ABLATION
+#include <stdlib.h>      // timing experiments only: -DMMG_ABLATION builds read MMG_DBG_SKIP / MMG_DBG_SKIP_FWD
+#endif
 
 namespace {
 
@@ -375,7 +377,11 @@ int mmg_disc_bwd_fused(const void* xs, const void* p1, const void* a2, const flo
     FusedBwdArgs a;
     a.dlogit = dlogit; a.wfcp = (const float*)(pk + 2048 + 32768);
     a.dw1 = dconv1_w; a.db1 = dconv1_b; a.dw2 = dconv2_w; a.db2 = dconv2_b; a.dwfc = dfc_w; a.dbfc = dfc_b; a.B = (int)B;
+#ifdef MMG_ABLATION
     { const char* e = getenv("MMG_DBG_SKIP"); a.dbg_skip = e ? atoi(e) : 0; }
+#else
+    a.dbg_skip = 0;
+#endif
     const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
     MMG_CUDA(cudaFuncSetAttribute(disc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
     disc_bwd_fused_kernel<<<grid, FB_THREADS, SM_TOTAL + 1024, (cudaStream_t)stream>>>(map_xs, map_p1, map_a2, map_w, a);
@@ -701,7 +707,11 @@ int mmg_disc_fwd_fused_gather(const void* x, int x_dtype, const int64_t* x_index
     FusedFwdArgs a;
     a.x = x; a.x_f32 = x_dtype == 0; a.x_index = x_index; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
     a.xs = (__nv_bfloat16*)xs; a.a2 = (__nv_bfloat16*)a2; a.logits = logits; a.B = (int)B;
+#ifdef MMG_ABLATION
     { const char* e = getenv("MMG_DBG_SKIP_FWD"); a.dbg_skip = e ? atoi(e) : 0; }
+#else
+    a.dbg_skip = 0;
+#endif
     const int grid = (int)(B < MMG_NUM_SMS ? B : MMG_NUM_SMS);
     MMG_CUDA(cudaFuncSetAttribute(disc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_TOTAL + 1024));
     disc_fwd_fused_kernel<<<grid, FB_THREADS, FS_TOTAL + 1024, (cudaStream_t)stream>>>(map_w1, map_w2, map_p1a, map_p1b, map_a2a, map_a2b, a);

@@ -32,6 +32,7 @@ class DiscTC:
         self.dz1c = torch.zeros(self.cap * XROWS, 16, **bf)         # junk rows stay zero forever
         self.logits = torch.empty(self.cap, device=dev)
         self.x, self.B = None, 0
+        self.ws = torch.empty(N.lib().mmg_disc_pass_workspace_bytes(), dtype=torch.uint8, device=dev)     # per-CTA scratch of the one-kernel pass
         self.pack()
 
     def pack(self):
@@ -60,6 +61,30 @@ class DiscTC:
         N.call("mmg_disc_xs_pack", N.ptr(x), _XD[x.dtype], N.ptr(self.xs), B, s)
         N.call("mmg_disc_conv1_fwd", N.ptr(self.xs), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(self.p1), B, s)
         N.call("mmg_disc_conv2_fwd", N.ptr(self.p1), N.ptr(self.packed), N.ptr(d.conv2.bias.data), N.ptr(self.a2), N.ptr(logits), B, s)
+        self.x, self.B = x, B
+        return logits
+
+    def pass_fused(self, x, target, loss=None, index=None, loss_rows=0, want_logits=True, dbg=None):
+        """forward + BCE-with-logits against the constant ``target`` + backward of one batch in ONE kernel (csrc/disc_tc_pass.cu):
+        the six gradients are accumulated into ``param.grad``, ``loss[0] +=`` the mean BCE over ``loss_rows`` rows (0 = this batch),
+        the logits (B,) are returned (a view of an internal buffer) when ``want_logits``.  Nothing but the rolls is read from HBM."""
+        N.require_cuda(x, index, loss)
+        B = x.shape[0] if index is None else index.numel()
+        if B > self.cap or tuple(x.shape[1:]) != (2, 128, 50) or x.dtype not in _XD:
+            raise ValueError(f"bad discriminator input {tuple(x.shape)} {x.dtype} (capacity {self.cap})")
+        if index is not None and index.dtype != torch.int64:
+            raise ValueError("index must be an int64 tensor")
+        x = x.contiguous()
+        d = self.d
+        g = {k: self._grad(p) for k, p in d.named_parameters()}
+        logits = self.logits[:B] if want_logits else None
+        args = (N.ptr(x), _XD[x.dtype], N.ptr(index), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data), N.ptr(d.fc.bias.data),
+                float(target), int(loss_rows), N.ptr(logits), N.ptr(loss), N.ptr(g["conv1.weight"]), N.ptr(g["conv1.bias"]), N.ptr(g["conv2.weight"]),
+                N.ptr(g["conv2.bias"]), N.ptr(g["fc.weight"]), N.ptr(g["fc.bias"]), N.ptr(self.ws), self.ws.numel(), B, N.stream())
+        if dbg is None:
+            N.call("mmg_disc_pass_fused", *args)
+        else:
+            N.call("mmg_disc_pass_fused_dbg", *args, dbg)
         self.x, self.B = x, B
         return logits
 

@@ -45,7 +45,7 @@ def shard_batch(t, rank, world):
 
 class MMGANTrainer:
     def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None, use_graph=None,
-                 inner_rng="reference", sync_bn=False):
+                 inner_rng="reference", sync_bn=False, one_kernel_pass=True):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.m = mmgan
@@ -70,6 +70,7 @@ class MMGANTrainer:
         if self.sync_bn and precision != "bf16":
             raise ValueError("sync_bn is implemented on the bf16 tensor-core generator path (precision='bf16')")
         self.tc = None
+        self.one_kernel_pass = bool(one_kernel_pass)      # bf16 path: mmg_disc_pass_fused (False: forward kernel + BCE kernel + backward kernel)
         self._g_out = None
         self._side = torch.cuda.Stream(device=self.d_params[0].device) if precision == "bf16" else None
         if precision == "bf16":
@@ -168,6 +169,11 @@ class MMGANTrainer:
     def _d_pass(self, x, target, loss, accumulate, index=None):
         """forward + BCE + backward of the discriminator on one batch (rows ``x[index]`` when ``index`` is given); grads accumulate into flat_grad"""
         B = x.shape[0] if index is None else index.numel()
+        if self.tc is not None and self.one_kernel_pass:
+            # forward -> BCE -> backward per sample inside one persistent kernel (csrc/disc_tc_pass.cu): the activations never reach HBM
+            if not accumulate:
+                N.call("mmg_zero", N.ptr(loss), 4, N.stream())
+            return self.tc.pass_fused(x, float(target), loss, index)
         if self.tc is not None:
             logits = self.tc.forward(x, index)
             dl = self.dlogit[:B]

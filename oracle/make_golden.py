@@ -342,6 +342,110 @@ def make_simlog():
     np.savez_compressed(os.path.join(GOLD, "simlog_cases.npz"), **out)
 
 
+
+def make_artifacts():
+    """Shipped artefacts of the reference as drop-in fixtures: the MM-GAN checkpoint
+    MMGAN_MIDI_DES/models/mmgan_64_64_epoch_1.pth run through the UNMODIFIED reference classes
+    (network_tests.py:58-206: eval-mode generators as in generate_midi :198-203, discriminator forward and one
+    BCE backward per target), and the 30 shipped .mid files as parsed message streams.
+      tests/golden/ckpt_epoch1.npz  the state dict (so the GPU box can rebuild the model) + reference outputs
+      tests/golden/disc_epoch1.npz  SURVEY 8d's tolerance probe: discriminator of that checkpoint, B = 256 synthetic rolls,
+                                    fp32 reference logits / loss / gradients for target 0 and target 1
+      tests/golden/ckpt_keys.npz    key / shape / checksum tables of all shipped MM-GAN checkpoints (load contract)
+    GAN-DES: python oracle/make_golden.py artifacts_gandes -> tests/golden/ckpt_gandes_gen.npz (separate process)."""
+    nt, _ = R.import_mmgan()
+    ref_root = os.path.join(R.REF_ROOT, "MMGAN_MIDI_DES")
+    ck_path = os.path.join(ref_root, "models", "mmgan_64_64_epoch_1.pth")
+    sd = torch.load(ck_path, map_location="cpu")
+    mmgan = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device="cpu")
+    mmgan.load_state_dict(sd)                                                      # network_tests.py:240-245
+    gold = {"sd." + k: v.numpy() for k, v in sd.items()}
+    gold["keys"] = np.array(list(sd.keys()))
+    B = 8
+    inp = mo.synth_inputs(B, seed=2024)
+    mmgan.generator1.eval(); mmgan.generator2.eval()                                # generate_midi, :199-200
+    torch.manual_seed(777)
+    gold["eval.inner"] = torch.randn(B, 50).numpy()
+    torch.manual_seed(777)
+    with torch.no_grad():
+        g1 = mmgan.generator1(inp["noise1"])                                        # draws the inner randn
+        g2 = mmgan.generator2(inp["noise2"], inp["beats"])
+        logit = mmgan.discriminator(inp["real"])
+    gold["eval.g1"], gold["eval.g2"], gold["disc.logit_real"] = g1.numpy()[:, :, ::2, ::2].copy(), g2.numpy(), logit.numpy()
+    gold["eval.g1.sum"] = np.array([g1.double().sum().item(), (g1.double() ** 2).sum().item()])
+    gold["seed"] = np.array([2024, B], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "ckpt_epoch1.npz"), **gold)
+    # ---- SURVEY 8d probe conditions: this discriminator, B = 256
+    Bp = 256
+    D = mmgan.discriminator
+    crit = torch.nn.BCEWithLogitsLoss()
+    probe = {"meta": np.array([Bp, 50, 8], dtype=np.int64)}                        # batch, width, roll seed (mo.synth_rolls(B, 50, seed=8))
+    for k, p in D.named_parameters():
+        probe["w." + k] = p.detach().numpy().copy()
+    x = torch.from_numpy(mo.synth_rolls(Bp, 50, seed=8)).float()
+    for y in (0.0, 1.0):
+        D.zero_grad()
+        lg = D(x)
+        loss = crit(lg.squeeze(), torch.full((Bp,), y))
+        loss.backward()
+        probe[f"y{int(y)}.logits"], probe[f"y{int(y)}.loss"] = lg.detach().numpy().reshape(-1), loss.detach().numpy()
+        for k, p in D.named_parameters():
+            probe[f"y{int(y)}.grad." + k] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "disc_epoch1.npz"), **probe)
+    # ---- load contract of every shipped MM-GAN checkpoint
+    tab = {}
+    for rel in ("mmgan_64_64_epoch_1.pth", "MAE_loss/mmgan_64_64_epoch_35.pth", "V1_bad/mmgan_64_64_epoch_50.pth"):
+        s2 = torch.load(os.path.join(ref_root, "models", rel), map_location="cpu")
+        tab[rel + ".keys"] = np.array(list(s2.keys()))
+        tab[rel + ".shapes"] = np.array([",".join(map(str, v.shape)) for v in s2.values()])
+        tab[rel + ".sums"] = np.array([v.double().sum().item() for v in s2.values()])
+    np.savez_compressed(os.path.join(GOLD, "ckpt_keys.npz"), **tab)
+    print("artifact goldens: ckpt_epoch1 (%d tensors), disc_epoch1 (B=%d), ckpt_keys" % (len(sd), Bp))
+
+
+def make_artifacts_gandes():
+    """GAN_DES/models/gen_100_*.pt through the UNMODIFIED GAN_DES/SIMNN.py Generator (eval mode, demo.ipynb cells 25-27)."""
+    sim = R.import_gandes()
+    import glob
+    path = sorted(glob.glob(os.path.join(R.REF_ROOT, "GAN_DES", "models", "gen_100_*.pt")))[0]
+    sd = torch.load(path, map_location="cpu")
+    gen = sim.Generator()
+    gen.load_state_dict(sd)
+    gen.eval()
+    rng = np.random.default_rng(99)
+    noise = torch.from_numpy(rng.standard_normal((4, 100, 1, 1)).astype(np.float32))
+    with torch.no_grad():
+        out = gen(noise)
+    gold = {"sd." + k: v.numpy() for k, v in sd.items()}
+    gold["keys"] = np.array(list(sd.keys()))
+    gold["noise"], gold["out"] = noise.numpy(), out.numpy()
+    np.savez_compressed(os.path.join(GOLD, "ckpt_gandes_gen.npz"), **gold)
+    print("artifact golden: ckpt_gandes_gen", os.path.basename(path), tuple(out.shape))
+
+
+
+def make_midi():
+    """The 30 .mid files the reference ships (SURVEY 4 / 8d config 4 "plus the 30 shipped .mid") as post-mido message streams.
+    mido is absent here, so the streams come from this repo's own SMF reader (datasets.read_smf, which restates mido's merge / tempo
+    rules): parity of the PARSER is unpinned; what the fixture pins is the rasteriser on real songs -- the GPU test
+    rasterises these streams on the device and compares with the C oracle -- plus the facts the survey probed with its own reader
+    (simulation.mid: 202 events, 106 note_on / 91 note_off, 480 ticks per beat, tempo 423 130)."""
+    import glob
+    root = os.path.dirname(HERE)
+    sys.path.insert(0, root)
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    files = sorted(glob.glob(os.path.join(R.REF_ROOT, "**", "*.mid"), recursive=True))
+    gold, names = {}, []
+    for i, f in enumerate(files):
+        ev = ds.read_smf(f)
+        rel = os.path.relpath(f, R.REF_ROOT)
+        names.append(rel)
+        gold[f"s{i}.dt"], gold[f"s{i}.meta"], gold[f"s{i}.beats"] = ev.dt, ev.meta, ev.beats
+    gold["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "midi_streams.npz"), **gold)
+    print("midi goldens:", len(files), "files,", sum(len(gold[f"s{i}.dt"]) for i in range(len(files))), "messages")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -353,6 +457,13 @@ if __name__ == "__main__":
         make_gandes()
     if what in ("simlog", "all"):
         make_simlog()
+    if what in ("artifacts", "all"):
+        make_artifacts()
+    if what in ("midi", "all"):
+        make_midi()
+    if what == "artifacts_gandes":
+        make_artifacts_gandes()
     if what == "all":
         import subprocess
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "artifacts_gandes"])
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "gandes"])
