@@ -102,6 +102,48 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_eager(args):
+    """Library-GPU bar: the reference's modules and loop body under PyTorch EAGER on the same B200 (cuBLAS / cuDNN / ATen),
+    fp32 as the reference runs them and with bf16 autocast; same batch, same synthetic rolls (float32 device tensors, DES excluded), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import eager_baseline as eb
+    from gan_des_midi_music_gen_b200 import benchmark
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.batch or 16384
+    rolls = {k: benchmark._synth_rolls_u8(B, 50, i, "cpu").to(dev).float() for i, k in enumerate(("real", "fake_d", "fake_g"))}
+    noise1, noise2, beats = torch.randn(B, 50, device=dev), torch.randn(B, 50, device=dev), 25 * torch.rand(B, 50, device=dev)
+    out = {}
+    for name, kw in (("fp32", {}), ("fp32_tf32", {"tf32": True}), ("bf16_autocast", {"autocast": True}), ("bf16_autocast_channels_last", {"autocast": True, "channels_last": True})):
+        tf32 = kw.pop("tf32", False)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        m = eb.EagerMMGAN(dev, **kw)
+        x = {k: (v.contiguous(memory_format=torch.channels_last) if kw.get("channels_last") else v) for k, v in rolls.items()}
+        fn = lambda: m.iteration(noise1, noise2, beats, x["real"], x["fake_d"], x["fake_g"])
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / args.steps
+        out[name] = {"rolls_per_sec": B / sec, "ms_per_step": sec * 1e3}
+        del m
+        torch.cuda.empty_cache()
+    best = max(out, key=lambda k: out[k]["rolls_per_sec"])
+    print(json.dumps({"impl": "eager", "metric": METRIC, "value": out[best]["rolls_per_sec"], "unit": "rolls/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": out[best]["ms_per_step"], "higher_is_better": True, "dtype": best, "data": "synthetic",
+                      "config": {"workload": "MM-GAN G+D training iteration (network_tests.py:292-315) under PyTorch eager CUDA (stock nn modules, torch.optim.Adam), DES excluded",
+                                 "batch": B, "inputs": "float32 rolls resident on the device"}, "variants": out}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -109,7 +151,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="piano rolls per GPU per step")
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--ref-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
@@ -117,6 +159,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager":
+        return run_eager(args)
     from gan_des_midi_music_gen_b200 import benchmark
     benchmark.run(args)
 

@@ -67,8 +67,9 @@ SIGNATURES.update({
     "mmg_disc_fwd_fused_gather": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mmg_disc_bwd_fused": (_I, [_P] * 11 + [_L, _P]),
     "mmg_disc_pass_workspace_bytes": (_Z, []),
-    "mmg_disc_pass_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _L, _P, _P] + [_P] * 6 + [_P, _Z, _L, _P]),
-    "mmg_disc_pass_fused_dbg": (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _L, _P, _P] + [_P] * 6 + [_P, _Z, _L, _P, _P]),
+    "mmg_disc_pass_set_flags": (_I, [_I]),
+    "mmg_disc_pass_fused": (_I, [_P, _I, _P, _L, _P, _P, _P, _P, _F, _L, _P, _P] + [_P] * 6 + [_P, _Z, _L, _P]),
+    "mmg_disc_pass_fused_dbg": (_I, [_P, _I, _P, _L, _P, _P, _P, _P, _F, _L, _P, _P] + [_P] * 6 + [_P, _Z, _L, _P, _P]),
     "mmg_gen_packed_weight_bytes": (_Z, [_I, _I]),
     "mmg_gen_pack_weight": (_I, [_P, _I, _I, _P, _P]),
     "mmg_gen_layer_fwd": (_I, [ctypes.POINTER(GenLayerArgs), _P]),

@@ -26,27 +26,31 @@ namespace {
 
 constexpr int P1_ROWS = 429, P1_W = 13;       // 33 x 13 super pixels per sample (conv1 activations / conv2 row space)
 constexpr int XS_ROWS = 1690, XS_W = 26;      // 65 x 26 super pixels per sample (input / conv1 row space)
-constexpr int NWORK = 256;
-constexpr int NTHREADS = 64 + NWORK;          // warp 0 producer, warp 1 MMA, warps 2-9 workers
+constexpr int NWORK = 512;                    // warps 0-15: workers (4 warpgroups), warp 16 producer, warp 17 MMA, warps 18-19 idle (setmaxnreg needs whole warpgroups)
+constexpr int NTHREADS = NWORK + 128;
+constexpr int PRODUCER_WARP = 16, MMA_WARP = 17;
 
 // shared-memory map (offsets from a 1024-byte aligned base)
 constexpr int XS3_PLANE = 6912;               // 429 rows x 16 B, padded to 432 rows (rows 429..431 stay zero)
-constexpr int SM_XS3 = 0;                     // 9 planes (the M = 128 MMA also reads 7 junk "planes" out of what follows)      62464
-constexpr int SM_P1 = SM_XS3 + 62464;         // 448 rows x 128 B, SW128: P1, then DZ1 in place                                  57344
+constexpr int SM_XS3 = 0;                     // 9 gathered planes + plane 9 = all ones (its 8 TMEM lanes collect the column sums of DZ1 = conv1.bias gradient)   69120
+constexpr int SM_ONESA = SM_XS3 + 10 * XS3_PLANE;   // A tile of the bias MMAs: 8 rows [1, 1, 0 x 6] + 128 B of zeros (K chunk 1)                                256 (+256 pad)
+constexpr int SM_P1 = 69632;                  // 448 rows x 128 B, SW128: P1, then DZ1 in place                                  57344
 constexpr int SM_DZ2 = SM_P1 + 57344;         // 16 zero halo rows + 432 rows x 64 B, SW64: A2, then DZ2 in place                28672
 constexpr int SM_W2 = SM_DZ2 + 28672;         // [4 t][32 oc][64 k] bf16 SW128 (conv2 forward B)                                 16384
 constexpr int SM_W2D = SM_W2 + 16384;         // [4 t][64 n][32 oc] bf16 SW64 (conv2 dgrad B)                                    16384
 constexpr int SM_W1 = SM_W2D + 16384;         // [2 ty][16 oc][16 k] bf16 SW32 (conv1 forward B)                                 1024
-constexpr int SM_XS = SM_W1 + 1024;           // 1824 rows x 16 B (14 tiles x 128 + 27 halo rows, padded), no swizzle            29184
-constexpr int SM_X = SM_XS + 29184;           // staged uint8 roll                                                               12800
-constexpr int SM_TOTAL = SM_X + 12800;        // 224256
+constexpr int SM_BB = SM_W1 + 1024;           // B tiles of the bias MMAs: conv1 [16 n][16 k] 512 B, conv2 [32 n][16 k] 1024 B: k0 = bias hi, k1 = bias lo (bf16), rest 0
+constexpr int SM_XS = SM_BB + 1536;           // 1690 rows x 16 B, no swizzle (the junk rows of conv1's last tile read on into SM_X)  27040
+constexpr int SM_X = SM_XS + 27040;           // staged uint8 roll                                                               12800
+constexpr int SM_TOTAL = SM_X + 12800;        // 230816
 constexpr int A2_ROWS = 432;                  // rows of the A2 / DZ2 tile that exist (27 K steps of 16)
 constexpr int K2_STEPS = 27;
-static_assert(SM_P1 % 1024 == 0 && SM_DZ2 % 1024 == 0 && SM_W2 % 1024 == 0 && SM_W2D % 1024 == 0 && SM_W1 % 256 == 0 && SM_XS % 16 == 0 && SM_X % 16 == 0, "alignment");
+static_assert(SM_ONESA + 256 <= SM_P1 && SM_P1 % 1024 == 0 && SM_DZ2 % 1024 == 0 && SM_W2 % 1024 == 0 && SM_W2D % 1024 == 0 && SM_W1 % 256 == 0 && SM_BB % 128 == 0 &&
+              SM_XS % 128 == 0 && SM_X % 16 == 0 && SM_TOTAL + 1024 + 608 <= 232448, "shared-memory map");
 
 // TMEM columns
 constexpr uint32_t TM_W2 = 0;                 // 64:  conv2.weight gradient  [ty][oc]            (persistent)
-constexpr uint32_t TM_W1 = 64;                // 64:  conv1.weight gradient  lanes = patch value (persistent)
+constexpr uint32_t TM_W1 = 64;                // 64:  conv1.weight gradient  lanes = patch value, lanes 72..79 = column sums of DZ1 (persistent)
 constexpr uint32_t TM_FC = 128;               // 128: fc.weight gradient     [tile][oc]          (persistent)
 constexpr uint32_t TM_DG = 256;               // 256: conv2 dgrad [tile][cell*16 + ic]; the same columns hold, earlier in the sample,
 constexpr uint32_t TM_C1 = 256;               //      conv1 accumulators (14 x 16 columns) and
@@ -58,11 +62,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+// LeakyReLU'(a) for the two bf16 halves of a packed word, tested on the bits (a > 0 exactly as the float compare would)
+__device__ __forceinline__ bool pos_lo(uint32_t u) { return (int)(u << 16) > 0; }
+__device__ __forceinline__ bool pos_hi(uint32_t u) { return (int)u >= 0x10000; }
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-                   "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -71,10 +81,11 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 __device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 struct PassArgs {
-    const void* x; int x_f32; const int64_t* x_index;
+    const void* x; int x_f32; const int64_t* x_index; long long x_rows;      // x_rows > 0: gathered row numbers are checked against it
+    int* oob;                           // set to 1 when an index was out of range (the row is then read as row 0)
     const float* b1; const float* b2; const float* wfcp; const float* bfc;
     float y, inv_n;                     // BCE target of the pass; 1 / (rows behind the loss mean)
     float* logits; float* loss;         // optional outputs: logits (B,), loss[0] += sum_b bce_b * inv_n
@@ -85,16 +96,20 @@ struct PassArgs {
 };
 
 #define PASS_DBG(slot, val) do { if (a.dbg) a.dbg[(blockIdx.x * 4 + (slot))] = (val); } while (0)
+// timeline of CTA 0, samples 6 and 7 (debug entry point only): SM clock at the phase boundaries of worker thread 0 (k < 16) and of the MMA thread (16 + k)
+#define PASS_TS(k) do { if (a.dbg && blockIdx.x == 0 && (it == 6 || it == 7)) a.dbg[1024 + (it - 6) * 32 + (k)] = (int)clock64(); } while (0)
 
+// BIAS_MMA: the two convolution biases enter the accumulators through one extra MMA per tile (A = ones, B = bias hi | lo) instead of an
+// FADD per value in the epilogues.
+template <bool BIAS_MMA>
 __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __grid_constant__ CUtensorMap map_xs3, const __grid_constant__ CUtensorMap map_w1,
                                                                       const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2d,
                                                                       const PassArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t wbar, x_full, xs_ready, xs_saved, full_xs3, c1_done, p1_ready[4], c2_done[4], dz2_ready[4], dg_done[4], dz1_ready, mma2_done;
     __shared__ uint32_t tmem_s;
-    __shared__ float logit_s[2];
+    __shared__ __align__(16) float logit_part[2][16];     // per-warp partial fc dots of the current sample (two phases)
     __shared__ float red_s[48];
-    __shared__ __align__(16) float bias_s[48];      // conv1.bias (16) | conv2.bias (32): broadcast LDS.128 in the epilogues instead of 32 live registers
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = a.B > (int)blockIdx.x ? (a.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;      // samples blockIdx.x, +gridDim.x, ...
@@ -107,15 +122,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
             tc::mbar_init(&p1_ready[i], NWORK); tc::mbar_init(&c2_done[i], 1); tc::mbar_init(&dz2_ready[i], NWORK); tc::mbar_init(&dg_done[i], 1);
         }
         tc::fence_barrier_init();
-        logit_s[0] = logit_s[1] = 0.f;
     }
-    if (threadIdx.x < 48) { red_s[threadIdx.x] = 0.f; bias_s[threadIdx.x] = threadIdx.x < 16 ? a.b1[threadIdx.x] : a.b2[threadIdx.x - 16]; }
-    if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
-    {   // everything that is never written must read as zeros: plane pad rows, P1 pad cells / tail rows, the DZ2 halo, the XS halo
-        uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = threadIdx.x; i < SM_W2 / 16; i += NTHREADS) z[i] = make_uint4(0, 0, 0, 0);
-        uint4* zx = reinterpret_cast<uint4*>(smem + SM_XS);
-        for (int i = threadIdx.x; i < 29184 / 16; i += NTHREADS) zx[i] = make_uint4(0, 0, 0, 0);
+    float* bias_s = reinterpret_cast<float*>(smem + SM_BB);      // !BIAS_MMA: conv1.bias (16) | conv2.bias (32) as fp32 where the bias tiles would be
+    if (threadIdx.x < 48) red_s[threadIdx.x] = 0.f;
+    if (warp == MMA_WARP) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
+    {   // everything that is never written must read as zeros (plane pad rows, P1 pad cells / tail rows, the DZ2 halo); constants: the ones plane,
+        // the bias-MMA operands.  Every 16-byte word has exactly one writer here.
+        for (int i = threadIdx.x; i < SM_W2 / 16; i += NTHREADS) {
+            const int off = i * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (off >= SM_XS3 + 9 * XS3_PLANE && off < SM_ONESA) v = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // bf16 1.0 x 8
+            else if (off >= SM_ONESA && off < SM_ONESA + 128) v = make_uint4(0x3F803F80u, 0, 0, 0);                                    // [1, 1, 0 x 6]
+            *reinterpret_cast<uint4*>(smem + off) = v;
+        }
+        for (int i = threadIdx.x; i < (SM_X - SM_XS) / 16; i += NTHREADS) *reinterpret_cast<uint4*>(smem + SM_XS + i * 16) = make_uint4(0, 0, 0, 0);
+        if (!BIAS_MMA) {
+            if (threadIdx.x < 48) bias_s[threadIdx.x] = threadIdx.x < 16 ? a.b1[threadIdx.x] : a.b2[threadIdx.x - 16];
+        } else
+        for (int i = threadIdx.x; i < 1536 / 16; i += NTHREADS) {      // bias B tiles, K-major, no swizzle: core matrix (n group, k chunk) at n_g * 256 + k_c * 128
+            const bool c2 = i >= 32;
+            const int j = c2 ? i - 32 : i, n_g = j >> 4, k_c = (j >> 3) & 1, n = n_g * 8 + (j & 7);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (k_c == 0) {
+                const float b = c2 ? a.b2[n] : a.b1[n];
+                const __nv_bfloat16 hi = __float2bfloat16(b), lo = __float2bfloat16(b - __bfloat162float(hi));
+                v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+            }
+            *reinterpret_cast<uint4*>(smem + SM_BB + i * 16) = v;
+        }
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
@@ -123,144 +157,165 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0 && n_my > 0) {
-            tc::mbar_expect_tx(&wbar, 16384 + 16384 + 1024);
-            tc::tma_load_2d(smem + SM_W2, &map_w2, &wbar, 0, 0);
-            tc::tma_load_2d(smem + SM_W2D, &map_w2d, &wbar, 0, 0);
-            tc::tma_load_2d(smem + SM_W1, &map_w1, &wbar, 0, 0);
-            auto load_x = [&](int it) {
-                const int b = blockIdx.x + it * gridDim.x;
-                tc::mbar_expect_tx(&x_full, 12800);
-                bulk_load_1d(smem + SM_X, (const unsigned char*)a.x + (size_t)(a.x_index ? a.x_index[b] : b) * 12800, 12800, &x_full);
-            };
-            if (!a.x_f32) load_x(0);
-            for (int it = 0; it < n_my; ++it) {
-                const int slot = (int)blockIdx.x * 2 + (it & 1);
-                tc::mbar_wait(&xs_ready, (uint32_t)(it & 1));                     // XS(it) is complete; the staged roll has been consumed
-                PASS_DBG(0, it * 16 + 1);
-                if (!a.x_f32 && it + 1 < n_my) load_x(it + 1);
-                tc::bulk_store_1d(a.scratch + (size_t)slot * XS_ROWS * 8, tc::smem_u32(smem + SM_XS), XS_ROWS * 16);
-                tc::bulk_commit_group();
-                bulk_wait_group_all();                                            // the rows are in L2 (and shared memory has been read)
-                fence_proxy_async_all();
-                tc::mbar_arrive(&xs_saved);
-                PASS_DBG(0, it * 16 + 2);
-                if (it > 0) tc::mbar_wait(&mma2_done, (uint32_t)((it - 1) & 1));  // the conv1 wgrad MMAs of the previous sample have read XS3
-                tc::mbar_expect_tx(&full_xs3, 9 * P1_ROWS * 16);
+    if (warp >= 16) {
+        // register pool of the CTA = 640 threads x 96: the four non-worker warps give 4 x 32 x 32 registers back, the sixteen worker warps take 16 x 32 x 8
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == PRODUCER_WARP) {
+            // ------------------------------------------------------------------ producer
+            if (lane == 0 && n_my > 0) {
+                tc::mbar_expect_tx(&wbar, 16384 + 16384 + 1024);
+                tc::tma_load_2d(smem + SM_W2, &map_w2, &wbar, 0, 0);
+                tc::tma_load_2d(smem + SM_W2D, &map_w2d, &wbar, 0, 0);
+                tc::tma_load_2d(smem + SM_W1, &map_w1, &wbar, 0, 0);
+                auto load_x = [&](int it) {
+                    const int b = blockIdx.x + it * gridDim.x;
+                    tc::mbar_expect_tx(&x_full, 12800);
+                    long long row = a.x_index ? a.x_index[b] : b;
+                    if (a.x_rows > 0 && (unsigned long long)row >= (unsigned long long)a.x_rows) { *a.oob = 1; row = 0; }
+                    bulk_load_1d(smem + SM_X, (const unsigned char*)a.x + (size_t)row * 12800, 12800, &x_full);
+                };
+                if (!a.x_f32) load_x(0);
+                for (int it = 0; it < n_my; ++it) {
+                    const int slot = (int)blockIdx.x * 2 + (it & 1);
+                    tc::mbar_wait(&xs_ready, (uint32_t)(it & 1));                     // XS(it) is complete; the staged roll has been consumed
+                    PASS_DBG(0, it * 16 + 1);
+                    if (!a.x_f32 && it + 1 < n_my) load_x(it + 1);
+                    tc::bulk_store_1d(a.scratch + (size_t)slot * XS_ROWS * 8, tc::smem_u32(smem + SM_XS), XS_ROWS * 16);
+                    tc::bulk_commit_group();
+                    bulk_wait_group_all();                                            // the rows are in L2 (and shared memory has been read)
+                    fence_proxy_async_all();
+                    tc::mbar_arrive(&xs_saved);
+                    PASS_DBG(0, it * 16 + 2);
+                    if (it > 0) tc::mbar_wait(&mma2_done, (uint32_t)((it - 1) & 1));  // the conv1 wgrad MMAs of the previous sample have read XS3
+                    tc::mbar_expect_tx(&full_xs3, 9 * P1_ROWS * 16);
 #pragma unroll
-                for (int pl = 0; pl < 9; ++pl)                                    // plane (ay, ax): XS super pixel (2 sy - 1 + ay, 2 sx - 1 + ax), zero outside
-                    tc::tma_load_4d(smem + SM_XS3 + pl * XS3_PLANE, &map_xs3, &full_xs3, 0, pl % 3 - 1, pl / 3 - 1, slot);
-                PASS_DBG(0, it * 16 + 3);
+                    for (int pl = 0; pl < 9; ++pl)                                    // plane (ay, ax): XS super pixel (2 sy - 1 + ay, 2 sx - 1 + ax), zero outside
+                        tc::tma_load_4d(smem + SM_XS3 + pl * XS3_PLANE, &map_xs3, &full_xs3, 0, pl % 3 - 1, pl / 3 - 1, slot);
+                    PASS_DBG(0, it * 16 + 3);
+                }
             }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (n_my > 0 && tc::elect_one()) {
-            const uint32_t leader = 1;
-            // forward
-            constexpr uint64_t XS_K = tc::smem_desc_base(16, 128, tc::SW_NONE);       // conv1 A: K chunk 1 = the next 16-byte row
-            constexpr uint64_t W1_K = tc::smem_desc_base(0, 256, tc::SW_32B);
-            constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);      // conv2 A (P1 rows) and B (W2p)
-            constexpr uint32_t ID_C1 = tc::idesc_bf16(128, 16), ID_C2 = tc::idesc_bf16(128, 32);
-            // backward
-            constexpr uint64_t P1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);    // conv2 wgrad A: atom 1 = one row (128 B) later
-            constexpr uint64_t DZ2_MN = tc::smem_desc_base(0, 512, tc::SW_64B);       // conv2 wgrad B
-            constexpr uint64_t KM64 = tc::smem_desc_base(0, 512, tc::SW_64B);         // conv2 dgrad A (DZ2 rows) and B (W2d)
-            constexpr uint64_t XS3_MN = tc::smem_desc_base(128, XS3_PLANE, tc::SW_NONE);   // conv1 wgrad A: 8-row K groups 128 B apart, M atoms one plane apart
-            constexpr uint64_t DZ1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);        // conv1 wgrad B: DZ1 rows (64 values), one atom
-            constexpr uint32_t ID_WG2 = tc::idesc_bf16(128, 32, 1, 1), ID_DG = tc::idesc_bf16(128, 64), ID_WG1 = tc::idesc_bf16(128, 64, 1, 1);
-            const uint32_t xs = tc::smem_u32(smem + SM_XS), p1 = tc::smem_u32(smem + SM_P1), w1 = tc::smem_u32(smem + SM_W1), w2 = tc::smem_u32(smem + SM_W2);
-            const uint32_t dz2 = tc::smem_u32(smem + SM_DZ2) + 1024, w2d = tc::smem_u32(smem + SM_W2D), xs3 = tc::smem_u32(smem + SM_XS3);
-            tc::mbar_wait(&wbar, 0);
-            for (int it = 0; it < n_my; ++it) {
-                const uint32_t ph = (uint32_t)(it & 1);
-                // ---- C1 (the TMEM columns were released by dz1_ready of the previous sample, waited for below before its M2)
-                tc::mbar_wait(&xs_ready, ph);
-                tc::tc_fence_after();
-                PASS_DBG(1, it * 16 + 1);
-#pragma unroll
-                for (int tile = 0; tile < 14; ++tile)
-#pragma unroll
-                    for (int ty = 0; ty < 2; ++ty)
-                        tc::mma_f16_ss_pred(tmem + TM_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512), ID_C1,
-                                            ty != 0, leader);
-                tc::mma_commit_pred(&c1_done, leader);
-                // ---- C2, tile by tile behind the conv1 epilogue
-#pragma unroll
-                for (int tile = 0; tile < 4; ++tile) {
-                    tc::mbar_wait(&p1_ready[tile], ph);
+        } else if (warp == MMA_WARP) {
+            // ------------------------------------------------------------------ MMA issuer
+            if (n_my > 0 && tc::elect_one()) {
+                const uint32_t leader = 1;
+                // forward
+                constexpr uint64_t XS_K = tc::smem_desc_base(16, 128, tc::SW_NONE);       // conv1 A: K chunk 1 = the next 16-byte row
+                constexpr uint64_t W1_K = tc::smem_desc_base(0, 256, tc::SW_32B);
+                constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);      // conv2 A (P1 rows) and B (W2p)
+                constexpr uint64_t ONES_K = tc::smem_desc_base(128, 0, tc::SW_NONE);      // bias A: every 8-row group is the same 128 bytes; K chunk 1 = zeros
+                constexpr uint64_t BB_K = tc::smem_desc_base(128, 256, tc::SW_NONE);      // bias B
+                constexpr uint32_t ID_C1 = tc::idesc_bf16(128, 16), ID_C2 = tc::idesc_bf16(128, 32);
+                // backward
+                constexpr uint64_t P1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);    // conv2 wgrad A: atom 1 = one row (128 B) later
+                constexpr uint64_t DZ2_MN = tc::smem_desc_base(0, 512, tc::SW_64B);       // conv2 wgrad B
+                constexpr uint64_t KM64 = tc::smem_desc_base(0, 512, tc::SW_64B);         // conv2 dgrad A (DZ2 rows) and B (W2d)
+                constexpr uint64_t XS3_MN = tc::smem_desc_base(128, XS3_PLANE, tc::SW_NONE);   // conv1 wgrad A: 8-row K groups 128 B apart, M atoms one plane apart
+                constexpr uint64_t DZ1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);        // conv1 wgrad B: DZ1 rows (64 values), one atom
+                constexpr uint32_t ID_WG2 = tc::idesc_bf16(128, 32, 1, 1), ID_DG = tc::idesc_bf16(128, 64), ID_WG1 = tc::idesc_bf16(128, 64, 1, 1);
+                const uint32_t xs = tc::smem_u32(smem + SM_XS), p1 = tc::smem_u32(smem + SM_P1), w1 = tc::smem_u32(smem + SM_W1), w2 = tc::smem_u32(smem + SM_W2);
+                const uint32_t dz2 = tc::smem_u32(smem + SM_DZ2) + 1024, w2d = tc::smem_u32(smem + SM_W2D), xs3 = tc::smem_u32(smem + SM_XS3);
+                const uint32_t onesa = tc::smem_u32(smem + SM_ONESA), bb1 = tc::smem_u32(smem + SM_BB), bb2 = bb1 + 512;
+                tc::mbar_wait(&wbar, 0);
+                for (int it = 0; it < n_my; ++it) {
+                    const uint32_t ph = (uint32_t)(it & 1);
+                    // ---- C1 (the TMEM columns were released by dz1_ready of the previous sample, waited for below before its M2)
+                    PASS_TS(16);
+                    tc::mbar_wait(&xs_ready, ph);
                     tc::tc_fence_after();
+                    PASS_DBG(1, it * 16 + 1);
+                    PASS_TS(17);
+#pragma unroll 1
+                    for (int tile = 0; tile < 14; ++tile) {
+                        if (BIAS_MMA) tc::mma_f16_ss_pred(tmem + TM_C1 + tile * 16, tc::smem_desc(ONES_K, onesa), tc::smem_desc(BB_K, bb1), ID_C1, 0, leader);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
+                        for (int ty = 0; ty < 2; ++ty)
+                            tc::mma_f16_ss_pred(tmem + TM_C1 + tile * 16, tc::smem_desc(XS_K, xs + (tile * 128 + ty * XS_W) * 16), tc::smem_desc(W1_K, w1 + ty * 512),
+                                                ID_C1, (BIAS_MMA || ty != 0) ? 1u : 0u, leader);
+                    }
+                    tc::mma_commit_pred(&c1_done, leader);
+                    PASS_TS(18);
+                    // ---- C2, tile by tile behind the conv1 epilogue
+#pragma unroll 1
+                    for (int tile = 0; tile < 4; ++tile) {
+                        tc::mbar_wait(&p1_ready[tile], ph);
+                        tc::tc_fence_after();
+                        if (BIAS_MMA) tc::mma_f16_ss_pred(tmem + TM_C2 + tile * 32, tc::smem_desc(ONES_K, onesa), tc::smem_desc(BB_K, bb2), ID_C2, 0, leader);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc::mma_f16_ss_pred(tmem + TM_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
-                                                tc::smem_desc(KM128, w2 + t * 4096 + k * 32), ID_C2, (t | k) != 0, leader);
-                    tc::mma_commit_pred(&c2_done[tile], leader);
-                }
-                PASS_DBG(1, it * 16 + 2);
-                // ---- M1: conv2 wgrad K steps + dgrad tile, tile by tile behind the DZ2 pass
+                        for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int tile = 0; tile < 4; ++tile) {
-                    tc::mbar_wait(&dz2_ready[tile], ph);
+                            for (int k = 0; k < 4; ++k)
+                                tc::mma_f16_ss_pred(tmem + TM_C2 + tile * 32, tc::smem_desc(KM128, p1 + (tile * 128 + (t >> 1) * P1_W + (t & 1)) * 128 + k * 32),
+                                                    tc::smem_desc(KM128, w2 + t * 4096 + k * 32), ID_C2, (BIAS_MMA || (t | k) != 0) ? 1u : 0u, leader);
+                        tc::mma_commit_pred(&c2_done[tile], leader);
+                    }
+                    PASS_DBG(1, it * 16 + 2);
+                    PASS_TS(19);
+                    // ---- M1: conv2 wgrad K steps + dgrad tile, tile by tile behind the DZ2 pass
+#pragma unroll 1
+                    for (int tile = 0; tile < 4; ++tile) {
+                        tc::mbar_wait(&dz2_ready[tile], ph);
+                        tc::tc_fence_after();
+                        const int k_lo = tile * 8, k_hi = tile == 3 ? K2_STEPS : tile * 8 + 8;
+#pragma unroll
+                        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+                            for (int k = k_lo; k < k_hi; ++k)
+                                tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
+                                                    ID_WG2, (it | k) != 0, leader);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                tc::mma_f16_ss_pred(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
+                                                    tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0, leader);
+                        tc::mma_commit_pred(&dg_done[tile], leader);
+                    }
+                    PASS_DBG(1, it * 16 + 3);
+                    PASS_TS(20);
+                    // ---- M2: conv1 wgrad (+ column sums of DZ1 in the lanes of the ones plane)
+                    tc::mbar_wait(&dz1_ready, ph);
+                    PASS_TS(21);
+                    tc::mbar_wait(&full_xs3, ph);
                     tc::tc_fence_after();
-                    const int k_lo = tile * 8, k_hi = tile == 3 ? K2_STEPS : tile * 8 + 8;
-#pragma unroll
-                    for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-                        for (int k = k_lo; k < k_hi; ++k)
-                            tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
-                                                ID_WG2, (it | k) != 0, leader);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            tc::mma_f16_ss_pred(tmem + TM_DG + tile * 64, tc::smem_desc(KM64, dz2 + (tile * 128 - ((t >> 1) * P1_W + (t & 1))) * 64 + k * 32),
-                                                tc::smem_desc(KM64, w2d + t * 4096 + k * 32), ID_DG, (t | k) != 0, leader);
-                    tc::mma_commit_pred(&dg_done[tile], leader);
-                }
-                PASS_DBG(1, it * 16 + 3);
-                // ---- M2: conv1 wgrad
-                tc::mbar_wait(&dz1_ready, ph);
-                tc::mbar_wait(&full_xs3, ph);
-                tc::tc_fence_after();
+                    PASS_TS(22);
 #pragma unroll 9
-                for (int k = 0; k < K2_STEPS; ++k)
-                    tc::mma_f16_ss_pred(tmem + TM_W1, tc::smem_desc(XS3_MN, xs3 + k * 256), tc::smem_desc(DZ1_MN, p1 + k * 16 * 128), ID_WG1, (it | k) != 0, leader);
-                tc::mma_commit_pred(&mma2_done, leader);
-                PASS_DBG(1, it * 16 + 4);
+                    for (int k = 0; k < K2_STEPS; ++k)
+                        tc::mma_f16_ss_pred(tmem + TM_W1, tc::smem_desc(XS3_MN, xs3 + k * 256), tc::smem_desc(DZ1_MN, p1 + k * 16 * 128), ID_WG1, (it | k) != 0, leader);
+                    tc::mma_commit_pred(&mma2_done, leader);
+                    PASS_DBG(1, it * 16 + 4);
+                    PASS_TS(23);
+                }
             }
         }
     } else {
-        // ------------------------------------------------------------------ workers: thread (q, lane, h) owns TMEM lane q*32+lane, column half h
-        const int q = warp & 3, h = (warp - 2) >> 2, tl = q * 32 + lane, w = threadIdx.x - 64;
+        // ------------------------------------------------------------------ workers: thread (q, lane, g) owns TMEM lane q*32+lane, column group g
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int q = warp & 3, g = warp >> 2, tl = q * 32 + lane, w = threadIdx.x;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const uint32_t xs_s = tc::smem_u32(smem + SM_XS), p1_s = tc::smem_u32(smem + SM_P1), x_s = tc::smem_u32(smem + SM_X), dz2s = tc::smem_u32(smem + SM_DZ2) + 1024;
-        const uint32_t b1_s = tc::smem_u32(bias_s), b2_s = tc::smem_u32(bias_s + 16 + h * 16);
-        float db2[16], db1[16];
+        const uint32_t b1_s = tc::smem_u32(bias_s) + (g & 1) * 32, b2_s = tc::smem_u32(bias_s + 16) + g * 32, lp_s = tc::smem_u32(&logit_part[0][0]);
+        float db2[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) db2[c] = db1[c] = 0.f;
+        for (int c = 0; c < 8; ++c) db2[c] = 0.f;
         float dbfc = 0.f;
         double loss_acc = 0.0;
         const float bfc = a.bfc[0];
         {   // fc.weight gradient accumulators start at zero
-            uint32_t zr[16];
+            uint32_t zr[8];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) zr[c] = 0u;
+            for (int c = 0; c < 8; ++c) zr[c] = 0u;
 #pragma unroll
-            for (int tile = 0; tile < 4; ++tile) tmem_st_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, zr);
+            for (int tile = 0; tile < 4; ++tile) tmem_st_32x8(tmem + tlane + TM_FC + tile * 32 + g * 8, zr);
             tmem_st_wait();
         }
-        // fc.weight slice of this thread's rows (the same rows for every sample): loaded once, kept in registers; used by the forward dot and by DZ2
-        float wreg[4][16];
+        // fc.weight slice of this thread's rows and columns (the same for every sample): kept in registers; used by the forward dot and by DZ2
+        float wreg[4][8];
 #pragma unroll
         for (int tile = 0; tile < 4; ++tile) {
             const int R = tile * 128 + tl;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 wv = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32 + h * 16)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c4 = 0; c4 < 2; ++c4) {
+                const float4 wv = R < P1_ROWS ? reinterpret_cast<const float4*>(a.wfcp + R * 32 + g * 8)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
                 wreg[tile][4 * c4] = wv.x; wreg[tile][4 * c4 + 1] = wv.y; wreg[tile][4 * c4 + 2] = wv.z; wreg[tile][4 * c4 + 3] = wv.w;
             }
         }
@@ -268,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
         auto build_xs = [&](int it) {
             if (!a.x_f32) {
                 tc::mbar_wait(&x_full, (uint32_t)(it & 1));
-                // all of this thread's byte loads (7 rows x 8) are issued before any is used: one shared-memory latency instead of seven
+                // all of this thread's byte loads (4 rows x 8) are issued before any is used: one shared-memory latency instead of four
                 constexpr int NR = (XS_ROWS + NWORK - 1) / NWORK;
                 uint32_t u[NR][8];
 #pragma unroll
@@ -296,7 +351,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                 }
             } else {
                 const int b = blockIdx.x + it * gridDim.x;
-                const long long xb = a.x_index ? a.x_index[b] : b;
+                long long xb = a.x_index ? a.x_index[b] : b;
+                if (a.x_rows > 0 && (unsigned long long)xb >= (unsigned long long)a.x_rows) { *a.oob = 1; xb = 0; }
                 for (int rr = w; rr < XS_ROWS; rr += NWORK) {
                     const int sy = rr / XS_W, sx = rr - sy * XS_W;
                     float v[8];
@@ -315,32 +371,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
         for (int it = 0; it < n_my; ++it) {
             const int b = blockIdx.x + it * gridDim.x;
             const uint32_t ph = (uint32_t)(it & 1);
-            // ---- S3: conv1 epilogue -> P1 (rows = super pixels, 64 values = (dy,dx,c16)); even tiles for h = 0, odd tiles for h = 1.
+            // ---- S3: conv1 epilogue -> P1 (rows = super pixels, 64 values = (dy,dx,c16)); tile parity g >> 1, 8 of the 16 channels (g & 1) per thread.
             // c1_done also tells that the previous sample's conv1 wgrad MMAs (issued before conv1) are done reading the P1 / DZ1 rows.
+            if (w == 0) PASS_TS(0);
             tc::mbar_wait(&c1_done, ph);
             tc::tc_fence_after();
-            if (w == 0) PASS_DBG(2, it * 16 + 1);
+            if (w == 0) { PASS_DBG(2, it * 16 + 1); PASS_TS(1); }
 #pragma unroll
             for (int tt = 0; tt < 7; ++tt) {
-                const int tile = 2 * tt + h;
-                uint32_t r[16];
-                tc::tmem_ld_32x16(tmem + tlane + TM_C1 + tile * 16, r);
+                const int tile = 2 * tt + (g >> 1);
+                uint32_t r[8];
+                tmem_ld_32x8(tmem + tlane + TM_C1 + tile * 16 + (g & 1) * 8, r);
                 tc::tmem_ld_wait();
                 const int m = tile * 128 + tl, oy = m / XS_W, ox = m - oy * XS_W;
                 if (m < XS_ROWS && oy < 64 && ox < 25) {
-                    uint32_t o[8];
+                    float z[8];
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const uint4 bq = tc::lds128(b1_s + c4 * 16);
-                        const float z0 = __uint_as_float(r[4 * c4]) + __uint_as_float(bq.x), z1 = __uint_as_float(r[4 * c4 + 1]) + __uint_as_float(bq.y);
-                        const float z2 = __uint_as_float(r[4 * c4 + 2]) + __uint_as_float(bq.z), z3 = __uint_as_float(r[4 * c4 + 3]) + __uint_as_float(bq.w);
-                        o[2 * c4] = pack_bf16x2(fmaxf(z0, 0.2f * z0), fmaxf(z1, 0.2f * z1));       // LeakyReLU(0.2) = max(z, 0.2 z)
-                        o[2 * c4 + 1] = pack_bf16x2(fmaxf(z2, 0.2f * z2), fmaxf(z3, 0.2f * z3));
+                    for (int c = 0; c < 8; ++c) z[c] = __uint_as_float(r[c]);
+                    if (!BIAS_MMA) {
+                        const uint4 bq0 = tc::lds128(b1_s), bq1 = tc::lds128(b1_s + 16);
+                        z[0] += __uint_as_float(bq0.x); z[1] += __uint_as_float(bq0.y); z[2] += __uint_as_float(bq0.z); z[3] += __uint_as_float(bq0.w);
+                        z[4] += __uint_as_float(bq1.x); z[5] += __uint_as_float(bq1.y); z[6] += __uint_as_float(bq1.z); z[7] += __uint_as_float(bq1.w);
                     }
+                    uint32_t o[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[c] = pack_bf16x2(fmaxf(z[2 * c], 0.2f * z[2 * c]), fmaxf(z[2 * c + 1], 0.2f * z[2 * c + 1]));      // LeakyReLU(0.2) = max(z, 0.2 z)
                     const int yp = oy + 1, xp = ox + 1, R = (yp >> 1) * P1_W + (xp >> 1), cell = (yp & 1) * 2 + (xp & 1);
-                    const uint32_t rowp = p1_s + R * 128;
-                    tc::sts128(rowp + (((2 * cell) ^ (R & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
-                    tc::sts128(rowp + (((2 * cell + 1) ^ (R & 7)) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                    tc::sts128(p1_s + R * 128 + (((2 * cell + (g & 1)) ^ (R & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
                 }
                 // conv1 tiles <= 2 tt + 1 are in P1 (and out of TMEM) once every worker is past this point: conv2 tile 0 reads P1 rows <= 141
                 // (conv1 rows <= 544: tiles 0..4), tile 1 rows <= 269 (tiles 0..8), tiles 2 and 3 everything
@@ -351,48 +408,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     if (tt == 6) tc::mbar_arrive(&p1_ready[3]);
                 }
             }
-            // ---- S5: conv2 epilogue -> A2 rows (64-byte swizzle, where DZ2 will be), fc partial dot
+            // ---- S5: conv2 epilogue -> A2 rows (64-byte swizzle, where DZ2 will be), fc partial dot; 8 of the 32 channels (g) per thread
+            if (w == 0) PASS_TS(2);
             float dot = 0.f;
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
                 tc::mbar_wait(&c2_done[tile], ph);
                 tc::tc_fence_after();
                 const int R = tile * 128 + tl;
-                uint32_t r[16];
-                tc::tmem_ld_32x16(tmem + tlane + TM_C2 + tile * 32 + h * 16, r);
+                uint32_t r[8];
+                tmem_ld_32x8(tmem + tlane + TM_C2 + tile * 32 + g * 8, r);
                 tc::tmem_ld_wait();
                 if (R >= P1_ROWS) continue;
                 const int oy = R / P1_W, ox = R - oy * P1_W;
                 const bool real = oy < 32 && ox < 12;                 // junk rows of the row space are stored as zeros
-                uint32_t o[8];
+                float z[8];
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const uint4 bq = tc::lds128(b2_s + c4 * 16);
-                    const float bb[4] = {__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w)};
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int c = 2 * c4 + e;
-                        float z0 = __uint_as_float(r[2 * c]) + bb[2 * e], z1 = __uint_as_float(r[2 * c + 1]) + bb[2 * e + 1];
-                        z0 = fmaxf(z0, 0.2f * z0); z1 = fmaxf(z1, 0.2f * z1);
-                        o[c] = real ? pack_bf16x2(z0, z1) : 0u;
-                        dot = fmaf(bf_lo(o[c]), wreg[tile][2 * c], dot);                      // the bf16 values the backward reads
-                        dot = fmaf(bf_hi(o[c]), wreg[tile][2 * c + 1], dot);
-                    }
+                for (int c = 0; c < 8; ++c) z[c] = __uint_as_float(r[c]);
+                if (!BIAS_MMA) {
+                    const uint4 bq0 = tc::lds128(b2_s), bq1 = tc::lds128(b2_s + 16);
+                    z[0] += __uint_as_float(bq0.x); z[1] += __uint_as_float(bq0.y); z[2] += __uint_as_float(bq0.z); z[3] += __uint_as_float(bq0.w);
+                    z[4] += __uint_as_float(bq1.x); z[5] += __uint_as_float(bq1.y); z[6] += __uint_as_float(bq1.z); z[7] += __uint_as_float(bq1.w);
                 }
-                const uint32_t rowp = dz2s + R * 64;
-                const int sw = (R >> 1) & 3;
-                tc::sts128(rowp + (((2 * h) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
-                tc::sts128(rowp + (((2 * h + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                uint32_t o[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    o[c] = real ? pack_bf16x2(fmaxf(z[2 * c], 0.2f * z[2 * c]), fmaxf(z[2 * c + 1], 0.2f * z[2 * c + 1])) : 0u;
+                    dot = fmaf(bf_lo(o[c]), wreg[tile][2 * c], dot);                      // the bf16 values the backward reads
+                    dot = fmaf(bf_hi(o[c]), wreg[tile][2 * c + 1], dot);
+                }
+                tc::sts128(dz2s + R * 64 + ((g ^ ((R >> 1) & 3)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
             }
             dot = warp_sum(dot);
-            if (lane == 0) atomicAdd(&logit_s[ph], dot);
+            if (lane == 0) logit_part[ph][warp] = dot;
             tc::tc_fence_before();
+            if (w == 0) PASS_TS(3);
             bar_workers();
-            // ---- BCE with logits (network_tests.py:304-306,313): loss_b = max(x,0) - x y + log1p(exp(-|x|)); dlogit = (sigmoid(x) - y) / n
-            const float xl = logit_s[ph] + bfc;
+            if (w == 0) PASS_TS(4);
+            // ---- BCE with logits (network_tests.py:304-306,313): loss_b = max(x,0) - x y + log1p(exp(-|x|)); dlogit = (sigmoid(x) - y) / n.
+            // The sixteen partial dots are added in a fixed order: the logit does not depend on which warp finished first.
+            float xl = bfc;
+            {
+                const uint32_t lp = lp_s + ph * 64;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const uint4 pq = tc::lds128(lp + i4 * 16);
+                    xl += __uint_as_float(pq.x); xl += __uint_as_float(pq.y); xl += __uint_as_float(pq.z); xl += __uint_as_float(pq.w);
+                }
+            }
             const float dl = (1.f / (1.f + expf(-xl)) - a.y) * a.inv_n;
             if (w == 0) {
-                logit_s[ph ^ 1] = 0.f;                                // the other buffer: read by everybody a sample ago, summed into a sample from now
                 if (a.logits) a.logits[b] = xl;
                 loss_acc += (double)(fmaxf(xl, 0.f) - xl * a.y + log1pf(expf(-fabsf(xl))));
                 dbfc += dl;
@@ -407,131 +472,123 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     continue;
                 }
                 const bool inb = R < A2_ROWS;                         // rows 429..431 have w = 0 -> they are (re)written as zeros
-                const uint32_t rowp = dz2s + (inb ? R : 0) * 64;
-                const int sw = (R >> 1) & 3;
-                const uint32_t c0p = rowp + (((2 * h) ^ sw) << 4), c1p = rowp + (((2 * h + 1) ^ sw) << 4);
-                const uint4 av0 = tc::lds128(c0p), av1 = tc::lds128(c1p);
-                const uint32_t au[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
-                uint32_t acc[16], o[8];
-                tc::tmem_ld_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, acc);    // .sync.aligned: every lane of the warp takes part
+                const uint32_t cp = dz2s + (inb ? R : 0) * 64 + ((g ^ ((R >> 1) & 3)) << 4);
+                const uint4 av = tc::lds128(cp);
+                const uint32_t au[4] = {av.x, av.y, av.z, av.w};
+                uint32_t acc[8], o[4];
+                tmem_ld_32x8(tmem + tlane + TM_FC + tile * 32 + g * 8, acc);          // .sync.aligned: every lane of the warp takes part
                 tc::tmem_ld_wait();
                 const bool real = R < P1_ROWS;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float x0 = real ? bf_lo(au[j]) : 0.f, x1 = real ? bf_hi(au[j]) : 0.f;
-                    const float g0 = dl * wreg[tile][2 * j] * (x0 > 0.f ? 1.f : 0.2f), g1 = dl * wreg[tile][2 * j + 1] * (x1 > 0.f ? 1.f : 0.2f);
+                    float g0 = dl * wreg[tile][2 * j], g1 = dl * wreg[tile][2 * j + 1];
+                    if (!(x0 > 0.f)) g0 *= 0.2f;
+                    if (!(x1 > 0.f)) g1 *= 0.2f;
                     o[j] = pack_bf16x2(g0, g1);
-                    db2[2 * j] += bf_lo(o[j]); db2[2 * j + 1] += bf_hi(o[j]);          // what the MMAs will read
+                    db2[2 * j] += g0; db2[2 * j + 1] += g1;
                     acc[2 * j] = __float_as_uint(fmaf(dl, x0, __uint_as_float(acc[2 * j])));
                     acc[2 * j + 1] = __float_as_uint(fmaf(dl, x1, __uint_as_float(acc[2 * j + 1])));
                 }
-                tmem_st_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, acc);
-                if (inb) {
-                    tc::sts128(c0p, make_uint4(o[0], o[1], o[2], o[3]));
-                    tc::sts128(c1p, make_uint4(o[4], o[5], o[6], o[7]));
-                }
+                tmem_st_32x8(tmem + tlane + TM_FC + tile * 32 + g * 8, acc);
+                if (inb) tc::sts128(cp, make_uint4(o[0], o[1], o[2], o[3]));
                 tc::fence_proxy_async_smem();
                 tc::mbar_arrive(&dz2_ready[tile]);                    // the MMAs of this tile may start
             }
             tmem_st_wait();
-            // ---- W3: conv2 dgrad epilogue -> DZ1 in place over P1, conv1.bias gradient (tile t as soon as its MMAs have committed)
+            if (w == 0) PASS_TS(5);
+            // ---- W3: conv2 dgrad epilogue -> DZ1 in place over P1 (tile t as soon as its MMAs have committed); cell g = (dy, dx) per thread.
+            // The conv1.bias gradient (column sums of DZ1) comes out of the conv1 wgrad MMAs (ones plane).
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {
                 tc::mbar_wait(&dg_done[tile], ph);
                 tc::tc_fence_after();
                 const int R = tile * 128 + tl;
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tmem + tlane + TM_DG + tile * 64 + h * 32, r);      // cells (dy = h, dx = 0 | 1) x 16 channels
+                uint32_t r[16];
+                tc::tmem_ld_32x16(tmem + tlane + TM_DG + tile * 64 + g * 16, r);
                 tc::tmem_ld_wait();
                 if (R >= A2_ROWS) continue;
                 const int sy = R / P1_W, sx = R - sy * P1_W;
-                const int oy = 2 * sy + h - 1;
+                const int oy = 2 * sy + (g >> 1) - 1, ox = 2 * sx + (g & 1) - 1;
+                // zero-padding cells of P1 have no conv1 output behind them; rows 429..431 are pad rows: both become 0
+                const bool cell = R < P1_ROWS && oy >= 0 && oy < 64 && ox >= 0 && ox < 25;
                 const uint32_t prow = p1_s + R * 128;
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int ox = 2 * sx + dx - 1;
-                    // zero-padding cells of P1 have no conv1 output behind them; rows 429..431 are pad rows: both become 0
-                    const bool cell = R < P1_ROWS && oy >= 0 && oy < 64 && ox >= 0 && ox < 25;
+                for (int hh = 0; hh < 2; ++hh) {                      // 8 channels per 16-byte chunk
+                    const uint32_t addr = prow + (((g * 2 + hh) ^ (R & 7)) << 4);
+                    uint32_t o[4] = {0u, 0u, 0u, 0u};
+                    if (cell) {
+                        const uint4 av = tc::lds128(addr);
+                        const uint32_t au[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {                  // 8 channels per 16-byte chunk
-                        const uint32_t addr = prow + ((((h * 2 + dx) * 2 + hh) ^ (R & 7)) << 4);
-                        uint32_t o[4] = {0u, 0u, 0u, 0u};
-                        if (cell) {
-                            const uint4 av = tc::lds128(addr);
-                            const uint32_t au[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int c = dx * 16 + hh * 8 + 2 * j;
-                                const float g0 = __uint_as_float(r[c]) * (bf_lo(au[j]) > 0.f ? 1.f : 0.2f);
-                                const float g1 = __uint_as_float(r[c + 1]) * (bf_hi(au[j]) > 0.f ? 1.f : 0.2f);
-                                o[j] = pack_bf16x2(g0, g1);
-                                db1[hh * 8 + 2 * j] += bf_lo(o[j]);
-                                db1[hh * 8 + 2 * j + 1] += bf_hi(o[j]);
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            float g0 = __uint_as_float(r[hh * 8 + 2 * j]), g1 = __uint_as_float(r[hh * 8 + 2 * j + 1]);
+                            if (!pos_lo(au[j])) g0 *= 0.2f;
+                            if (!pos_hi(au[j])) g1 *= 0.2f;
+                            o[j] = pack_bf16x2(g0, g1);
                         }
-                        tc::sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
                     }
+                    tc::sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
                 }
             }
             tc::tc_fence_before();
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&dz1_ready);                              // DZ1 is complete and the dgrad columns of TMEM are free (conv1 of the next sample)
-            if (w == 0) PASS_DBG(2, it * 16 + 3);
+            if (w == 0) { PASS_DBG(2, it * 16 + 3); PASS_TS(6); }
             // ---- XSb of the next sample, under this sample's conv1 wgrad MMAs
             if (it + 1 < n_my) {
                 tc::mbar_wait(&xs_saved, ph);                         // the producer's copy of XS(it) has read the rows
+                if (w == 0) PASS_TS(7);
                 build_xs(it + 1);
+                if (w == 0) PASS_TS(8);
             }
         }
         // ------------------------------------------------------------------ flush: weight gradients leave the SM once per launch
         if (n_my > 0) {
             tc::mbar_wait(&mma2_done, (uint32_t)((n_my - 1) & 1));
             tc::tc_fence_after();
-            if (h == 0) {
-                // conv2: TMEM lane m = tx*64 + (dy*2+dx)*16 + ic, column = ty*32 + oc  ->  conv2.weight[oc][ic][2ty+dy][2tx+dx]
-                const int tx = tl >> 6, dy = (tl >> 5) & 1, dx = (tl >> 4) & 1, ic = tl & 15;
+            {   // conv2: TMEM lane m = tx*64 + (dy*2+dx)*16 + ic, column = ty*32 + oc  ->  conv2.weight[oc][ic][2ty+dy][2tx+dx]; this thread: ty = g>>1, 16 oc
+                const int tx = tl >> 6, dy = (tl >> 5) & 1, dx = (tl >> 4) & 1, ic = tl & 15, ty = g >> 1, oc0 = (g & 1) * 16;
+                uint32_t r[16];
+                tc::tmem_ld_32x16(tmem + tlane + TM_W2 + g * 16, r);
+                tc::tmem_ld_wait();
 #pragma unroll
-                for (int ty = 0; ty < 2; ++ty) {
-                    uint32_t r[32];
-                    tc::tmem_ld_32x32(tmem + tlane + TM_W2 + ty * 32, r);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int oc = 0; oc < 32; ++oc) atomicAdd(&a.dw2[((oc * 16 + ic) * 4 + 2 * ty + dy) * 4 + 2 * tx + dx], __uint_as_float(r[oc]));
-                }
+                for (int c = 0; c < 16; ++c) atomicAdd(&a.dw2[(((oc0 + c) * 16 + ic) * 4 + 2 * ty + dy) * 4 + 2 * tx + dx], __uint_as_float(r[c]));
             }
             {   // conv1: TMEM lane m = patch value ((ay*3+ax)*8 + (dy',dx',ch)), column = cell*16 + oc; patch pixel (py,px) = (2ay+dy', 2ax+dx')
-                // feeds cell (dy,dx) through tap (ky,kx) = (py - 2dy, px - 2dx)  ->  conv1.weight[oc][ch][ky][kx]
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tmem + tlane + TM_W1 + h * 32, r);                  // cells 2h, 2h+1
+                // feeds cell (dy,dx) through tap (ky,kx) = (py - 2dy, px - 2dx)  ->  conv1.weight[oc][ch][ky][kx]; lanes 72..79: sum_R DZ1[R][cell*16+oc]
+                uint32_t r[16];
+                tc::tmem_ld_32x16(tmem + tlane + TM_W1 + g * 16, r);                  // cell g
                 tc::tmem_ld_wait();
                 if (tl < 72) {
                     const int at = tl >> 3, e = tl & 7, py = 2 * (at / 3) + (e >> 2), px = 2 * (at % 3) + ((e >> 1) & 1), ch = e & 1;
+                    const int ky = py - 2 * (g >> 1), kx = px - 2 * (g & 1);
+                    if (ky >= 0 && ky <= 3 && kx >= 0 && kx <= 3) {
 #pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const int ky = py - 2 * h, kx = px - 2 * dx;
-                        if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
-#pragma unroll
-                        for (int oc = 0; oc < 16; ++oc) atomicAdd(&a.dw1[((oc * 2 + ch) * 4 + ky) * 4 + kx], __uint_as_float(r[dx * 16 + oc]));
+                        for (int oc = 0; oc < 16; ++oc) atomicAdd(&a.dw1[((oc * 2 + ch) * 4 + ky) * 4 + kx], __uint_as_float(r[oc]));
                     }
+                } else if (tl == 72) {
+#pragma unroll
+                    for (int oc = 0; oc < 16; ++oc) atomicAdd(&red_s[32 + oc], __uint_as_float(r[oc]));
                 }
             }
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) {                    // fc.weight[0, oc*384 + oy*12 + ox]
                 const int R = tile * 128 + tl;
-                uint32_t r[16];
-                tc::tmem_ld_32x16(tmem + tlane + TM_FC + tile * 32 + h * 16, r);
+                uint32_t r[8];
+                tmem_ld_32x8(tmem + tlane + TM_FC + tile * 32 + g * 8, r);
                 tc::tmem_ld_wait();
                 const int oy = R / P1_W, ox = R - oy * P1_W;
                 if (R < P1_ROWS && oy < 32 && ox < 12) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) atomicAdd(&a.dwfc[(h * 16 + c) * 384 + oy * 12 + ox], __uint_as_float(r[c]));
+                    for (int c = 0; c < 8; ++c) atomicAdd(&a.dwfc[(g * 8 + c) * 384 + oy * 12 + ox], __uint_as_float(r[c]));
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float s2 = warp_sum(db2[c]), s1 = warp_sum(db1[c]);
-            if (lane == 0) { atomicAdd(&red_s[h * 16 + c], s2); atomicAdd(&red_s[32 + c], s1); }
+        for (int c = 0; c < 8; ++c) {
+            const float s2 = warp_sum(db2[c]);
+            if (lane == 0) atomicAdd(&red_s[g * 8 + c], s2);
         }
         if (w == 0 && n_my > 0) {
             atomicAdd(a.dbfc, dbfc);
@@ -540,20 +597,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+    if (warp == MMA_WARP) tc::tmem_dealloc(tmem, 512);
     if (threadIdx.x < 32) atomicAdd(&a.db2[threadIdx.x], red_s[threadIdx.x]);
     else if (threadIdx.x < 48) atomicAdd(&a.db1[threadIdx.x - 32], red_s[threadIdx.x]);
 }
 
 }  // namespace
 
+static int g_pass_flags = 0;
+
 extern "C" {
 
-size_t mmg_disc_pass_workspace_bytes(void) { return (size_t)MMG_NUM_SMS * 2 * XS_ROWS * 16; }
+// bit 0: biases in the epilogues (kernel variant without the bias MMAs).  Process-wide; for A/B checks of the two variants.
+int mmg_disc_pass_set_flags(int flags) { g_pass_flags = flags; return MMG_OK; }
 
-// x (B,2,128,50) uint8 (x_dtype 2) or float32 (0), optionally gathered through x_index (int64, device).  BCE target `target`, loss mean and
+size_t mmg_disc_pass_workspace_bytes(void) { return (size_t)MMG_NUM_SMS * 2 * XS_ROWS * 16 + 128; }      // scratch slots + the out-of-range flag
+
+// x (B,2,128,50) uint8 (x_dtype 2) or float32 (0), optionally gathered through x_index (int64, device; checked against x_rows when > 0: an
+// out-of-range index reads row 0 and sets the int32 flag in the last 128 bytes of the workspace).  BCE target `target`, loss mean and
 // dlogit over `loss_rows` rows (0 = B).  logits (B,) and loss[0] (+=) are optional; the six fp32 gradients are ACCUMULATED (+=).
-int mmg_disc_pass_fused_dbg(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
+int mmg_disc_pass_fused_dbg(const void* x, int x_dtype, const int64_t* x_index, int64_t x_rows, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
                             float target, int64_t loss_rows, float* logits, float* loss, float* dconv1_w, float* dconv1_b, float* dconv2_w, float* dconv2_b,
                             float* dfc_w, float* dfc_b, void* workspace, size_t ws_bytes, int64_t B, void* stream, int* dbg) {
     MMG_REQUIRE(x && packed && conv1_b && conv2_b && fc_b && dconv1_w && dconv1_b && dconv2_w && dconv2_b && dfc_w && dfc_b && workspace && B >= 0 && loss_rows >= 0,
@@ -576,20 +639,26 @@ int mmg_disc_pass_fused_dbg(const void* x, int x_dtype, const int64_t* x_index, 
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w2, pk + 2048, 64, 128, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "disc_pass_fused: tensor map (w2p)");
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w2d, pk + 2048 + 16384, 32, 256, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B) == 0, MMG_EINVAL, "disc_pass_fused: tensor map (w2d)");
     PassArgs a;
-    a.x = x; a.x_f32 = x_dtype == 0; a.x_index = x_index; a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
+    a.x = x; a.x_f32 = x_dtype == 0; a.x_index = x_index; a.x_rows = x_index ? x_rows : 0; a.oob = (int*)((unsigned char*)workspace + (size_t)MMG_NUM_SMS * 2 * XS_ROWS * 16);
+    a.b1 = conv1_b; a.b2 = conv2_b; a.wfcp = (const float*)(pk + 2048 + 32768); a.bfc = fc_b;
     a.y = target; a.inv_n = 1.f / (float)(loss_rows ? loss_rows : B); a.logits = logits; a.loss = loss;
     a.dw1 = dconv1_w; a.db1 = dconv1_b; a.dw2 = dconv2_w; a.db2 = dconv2_b; a.dwfc = dfc_w; a.dbfc = dfc_b;
     a.scratch = (__nv_bfloat16*)workspace; a.B = (int)B; a.dbg = dbg;
-    MMG_CUDA(cudaFuncSetAttribute(disc_pass_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
-    disc_pass_fused_kernel<<<grid, NTHREADS, SM_TOTAL + 1024, (cudaStream_t)stream>>>(map_xs3, map_w1, map_w2, map_w2d, a);
+    if (g_pass_flags & 1) {         // debugging aid (mmg_disc_pass_set_flags): biases added in the epilogues instead of by the bias MMAs
+        MMG_CUDA(cudaFuncSetAttribute(disc_pass_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        disc_pass_fused_kernel<false><<<grid, NTHREADS, SM_TOTAL + 1024, (cudaStream_t)stream>>>(map_xs3, map_w1, map_w2, map_w2d, a);
+    } else {
+        MMG_CUDA(cudaFuncSetAttribute(disc_pass_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        disc_pass_fused_kernel<true><<<grid, NTHREADS, SM_TOTAL + 1024, (cudaStream_t)stream>>>(map_xs3, map_w1, map_w2, map_w2d, a);
+    }
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
 
-int mmg_disc_pass_fused(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
+int mmg_disc_pass_fused(const void* x, int x_dtype, const int64_t* x_index, int64_t x_rows, const void* packed, const float* conv1_b, const float* conv2_b, const float* fc_b,
                         float target, int64_t loss_rows, float* logits, float* loss, float* dconv1_w, float* dconv1_b, float* dconv2_w, float* dconv2_b,
                         float* dfc_w, float* dfc_b, void* workspace, size_t ws_bytes, int64_t B, void* stream) {
-    return mmg_disc_pass_fused_dbg(x, x_dtype, x_index, packed, conv1_b, conv2_b, fc_b, target, loss_rows, logits, loss, dconv1_w, dconv1_b, dconv2_w, dconv2_b, dfc_w,
+    return mmg_disc_pass_fused_dbg(x, x_dtype, x_index, x_rows, packed, conv1_b, conv2_b, fc_b, target, loss_rows, logits, loss, dconv1_w, dconv1_b, dconv2_w, dconv2_b, dfc_w,
                                    dfc_b, workspace, ws_bytes, B, stream, nullptr);
 }
 

@@ -32,7 +32,7 @@ class DiscTC:
         self.dz1c = torch.zeros(self.cap * XROWS, 16, **bf)         # junk rows stay zero forever
         self.logits = torch.empty(self.cap, device=dev)
         self.x, self.B = None, 0
-        self.ws = torch.empty(N.lib().mmg_disc_pass_workspace_bytes(), dtype=torch.uint8, device=dev)     # per-CTA scratch of the one-kernel pass
+        self.ws = torch.zeros(N.lib().mmg_disc_pass_workspace_bytes(), dtype=torch.uint8, device=dev)     # per-CTA scratch of the one-kernel pass + index flag
         self.pack()
 
     def pack(self):
@@ -78,7 +78,7 @@ class DiscTC:
         d = self.d
         g = {k: self._grad(p) for k, p in d.named_parameters()}
         logits = self.logits[:B] if want_logits else None
-        args = (N.ptr(x), _XD[x.dtype], N.ptr(index), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data), N.ptr(d.fc.bias.data),
+        args = (N.ptr(x), _XD[x.dtype], N.ptr(index), x.shape[0], N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data), N.ptr(d.fc.bias.data),
                 float(target), int(loss_rows), N.ptr(logits), N.ptr(loss), N.ptr(g["conv1.weight"]), N.ptr(g["conv1.bias"]), N.ptr(g["conv2.weight"]),
                 N.ptr(g["conv2.bias"]), N.ptr(g["fc.weight"]), N.ptr(g["fc.bias"]), N.ptr(self.ws), self.ws.numel(), B, N.stream())
         if dbg is None:
@@ -87,6 +87,13 @@ class DiscTC:
             N.call("mmg_disc_pass_fused_dbg", *args, dbg)
         self.x, self.B = x, B
         return logits
+
+    def index_out_of_range(self):
+        """True if a gathered pass met a row index outside the resident set since the last call (synchronises; the row was read as row 0)."""
+        flag = self.ws[-128:-124].view(torch.int32)
+        bad = bool(flag.item())
+        flag.zero_()
+        return bad
 
     def _grad(self, p):
         if p.grad is None:

@@ -10,6 +10,11 @@ The fake rolls are what the host DES bridge returned for the two generator forwa
 inputs.  Rolls may be float32 or uint8 (B,2,128,W) tensors (piano-roll values are integers 0..127 and
 durations < 256, so uint8 is exact and quarters the H2D / HBM traffic).
 
+Public segments (the reference's own dependency G -> host DES -> D, network_tests.py:177-196, expressed through the API): ``generators`` runs one
+pair of G1 / G2 train-mode forwards and returns the matrices the host bridge consumes; ``d_step(real, fake_d)`` and ``g_step(fake_g)`` then
+take the rolls the bridge made from them.  ``step`` = generators, d_step, generators, g_step on given rolls (bench / parity: the DES is
+excluded there, so its rolls are inputs that by construction do not depend on this step's generator outputs).
+
 precision='fp32' : the drop-in nn.Modules + autograd over the fp32 SIMT kernels (reference tolerance).
 precision='bf16' : discriminator on the tcgen05 tensor-core kernels (disc_tc.DiscTC): bf16 operands,
                    fp32 accumulation, fp32 master weights / Adam state; fused BCE and multi-tensor Adam.
@@ -70,6 +75,7 @@ class MMGANTrainer:
         if self.sync_bn and precision != "bf16":
             raise ValueError("sync_bn is implemented on the bf16 tensor-core generator path (precision='bf16')")
         self.tc = None
+        self._g_out_owned = True
         self.one_kernel_pass = bool(one_kernel_pass)      # bf16 path: mmg_disc_pass_fused (False: forward kernel + BCE kernel + backward kernel)
         self._g_out = None
         self._side = torch.cuda.Stream(device=self.d_params[0].device) if precision == "bf16" else None
@@ -86,7 +92,7 @@ class MMGANTrainer:
             raise ValueError("inner_rng must be 'reference' or 'device'")
         self.inner_rng = inner_rng
         self.use_graph = (precision == "bf16") if use_graph is None else bool(use_graph)
-        self._graphs, self._seen, self._inner = {}, {}, {}
+        self._graphs, self._seg_graphs, self._seen, self._inner = {}, {}, {}, {}
         self.graph_launches = 0                      # kernels inside one captured iteration (for launch accounting)
         self.replayed_launches = 0                   # kernels launched through graph replays so far
         self.adam_hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float32, device=dev)
@@ -142,13 +148,16 @@ class MMGANTrainer:
             buf.copy_(torch.randn(B, dim))
         return buf
 
-    def _generators(self, noise1, noise2, beats, inner):
+    def _generators(self, noise1, noise2, beats, inner, out=None):
         m = self.m
         with torch.no_grad():
             if self.tc is not None:          # bf16 tcgen05 blocks (csrc/gen_tc.cu); outputs land in static buffers
                 B = noise1.shape[0]
-                if self._g_out is None or self._g_out[0].shape[0] != B:
+                if out is not None:
+                    self._g_out = out
+                elif self._g_out is None or self._g_out[0].shape[0] != B or self._g_out_owned is False:
                     self._g_out = (torch.empty(B, self.gtc1.widths[-1], device=noise1.device), torch.empty(B, self.gtc2.widths[-1], device=noise1.device))
+                self._g_out_owned = out is None
                 a = m.generator1.adj_size
                 if self.sync_bn:
                     # SyncBN: the statistics all-reduces sit between the layer kernels; both generators on this stream (one collective order)
@@ -200,6 +209,8 @@ class MMGANTrainer:
     def _seg_d_disc(self, noise1, noise2, beats, real, fake_d, inner_d, real_index=None):
         """D step up to the gradients (:293, :304-307)"""
         self._zero_d_grads()
+        if self.tc is not None:
+            self.tc.pack()               # one tiny launch: weights edited since the last optimiser step (load_state_dict, manual surgery) are picked up
         self.logit_fake_d = self._d_pass(fake_d, 0.0, self.loss_d, False)
         if self.tc is not None:
             self.logit_fake_d = self.logit_fake_d.clone()
@@ -216,12 +227,19 @@ class MMGANTrainer:
         3.1), so when sharded they run while the D-gradient all-reduce is in flight."""
         self._generators(noise1, noise2, beats, inner_g)
 
-    def _seg_g(self, noise1, noise2, beats, fake_g, inner_g):
-        """Adam on D (:308), then the rest of the G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them"""
+    def _seg_d_opt(self):
+        """Adam on D (:308) and the bf16 operand copies of the new weights"""
         self._disc_adam()
         if self.tc is not None:
             self.tc.pack()
+
+    def _seg_g_disc(self, fake_g):
+        """the rest of the G step (:311-315): gen_opt.zero_grad() leaves the D grads in place, gen_loss.backward() adds to them"""
         self.logit_fake_g = self._d_pass(fake_g, 1.0, self.loss_g, False)
+
+    def _seg_g(self, noise1, noise2, beats, fake_g, inner_g):
+        self._seg_d_opt()
+        self._seg_g_disc(fake_g)
 
     def _capture(self, fn, *args):
         g = torch.cuda.CUDAGraph()
@@ -230,6 +248,68 @@ class MMGANTrainer:
             fn(*args)
         self.graph_launches += N.lib().mmg_launch_count() - l0
         return g
+
+    # ------------------------------------------------------------------ public segments
+    def _segment(self, name, fn, tensors, extra=()):
+        """Run ``fn()`` eagerly the first time it is seen on these buffers, capture it in a CUDA graph the second time, replay afterwards."""
+        if not (self.use_graph and self.on_d_grads is None):
+            return fn()
+        key = (name,) + tuple(t.data_ptr() if t is not None else 0 for t in tensors) + tuple(extra)
+        g = self._seg_graphs.get(key)
+        if g is None:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] == 1:
+                return fn()
+            torch.cuda.synchronize()
+            l0 = N.lib().mmg_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._seg_graphs[key] = (g, N.lib().mmg_launch_count() - l0)
+            g = self._seg_graphs[key]
+        self.replayed_launches += g[1]
+        g[0].replay()
+
+    def generators(self, noise1, noise2, beats, inner=None, out=None):
+        """One pair of train-mode generator forwards (network_tests.py:294 / :312 -> :177-178; BatchNorm running statistics advance once).
+        Returns ``(g1_out (B,1,S,S), g2_out (B,output_dim))`` fp32 -- what ``matrix_to_midi`` takes (matrix_sim_process.py:15,28-29).
+        ``out=(buf1 (B,S*S), buf2 (B,output_dim))``: write into these buffers (the bf16 path otherwise reuses one internal pair per call);
+        ``inner``: the Generator's in-forward randn (network_tests.py:83-84), drawn here when None."""
+        B = noise1.shape[0]
+        if inner is None:
+            inner = self._draw_inner(B, "d")
+        sync = self.sync_bn                        # collectives between the layer kernels: not captured
+        if sync or self.tc is None:
+            self._generators(noise1, noise2, beats, inner, out)
+        else:
+            self._segment("gen", lambda: self._generators(noise1, noise2, beats, inner, out), (noise1, noise2, beats, inner) + tuple(out or ()), (B,))
+            if out is not None:
+                a = self.m.generator1.adj_size
+                self.g1_out, self.g2_out = out[0].view(B, -1, a[0], a[1]), out[1]
+        return self.g1_out, self.g2_out
+
+    def d_step(self, real, fake_d, real_index=None):
+        """The D step after the bridge has returned ``fake_d`` (network_tests.py:293, :304-308): zero grads, D on the fake rolls vs 0 and on the real
+        rolls vs 1, backward, gradient all-reduce when sharded, Adam.  Returns the loss (device scalar)."""
+        B = real.shape[0] if real_index is None else real_index.numel()
+        a_d = (None, None, None, real, fake_d, None, real_index)
+        self._sync_hyper()
+        self._segment("d_bwd", lambda: self._seg_d_disc(*a_d), (real, fake_d, real_index), (B, real.dtype, fake_d.dtype))
+        work = self._allreduce_d_grads(async_op=True)
+        if work is not None:
+            work.wait()
+        if self.on_d_grads is not None:
+            self.on_d_grads(self)
+        self._segment("d_opt", self._seg_d_opt, ())
+        return self.loss_d[0]
+
+    def g_step(self, fake_g):
+        """The G step after the bridge has returned ``fake_g`` (network_tests.py:311-315): D on the fake rolls vs 1, backward onto the D-step
+        gradients (gen_opt.zero_grad() leaves them), generator Adam = no-op (no generator parameter has a grad).  Returns the loss."""
+        self.gen_opt.zero_grad(set_to_none=True)
+        self._segment("g", lambda: self._seg_g_disc(fake_g), (fake_g,), (fake_g.shape[0], fake_g.dtype))
+        self.gen_opt.step()
+        return self.loss_g[0]
 
     def step(self, noise1, noise2, beats, real, fake_d, fake_g, inner_d=None, inner_g=None, real_index=None):
         """``real_index`` (B,) int64 CUDA tensor: the real batch is ``real[real_index]`` -- ``real`` is then the whole HBM-resident training set and
@@ -304,9 +384,10 @@ class HostBatchPipeline:
 
     KEYS = ("beats", "real", "fake_d", "fake_g")
 
-    def __init__(self, trainer, example, dataset=None, max_events=None, raster=(100, 0, 50)):
+    def __init__(self, trainer, example, dataset=None, max_events=None, raster=(100, 0, 50), g_out_host=False):
         self.t = trainer
         dev = trainer.flat_grad.device
+        self.g_out_host = bool(g_out_host)
         self.dataset = dataset
         self.events = "fake_d_events" in example
         self.gather_in_kernel = dataset is not None and trainer.tc is not None and getattr(trainer.tc, "fused_forward", False)
@@ -349,6 +430,19 @@ class HostBatchPipeline:
         self.free = [torch.cuda.Event() for _ in range(2)]
         self.losses_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.read = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_bytes = 8
+        self.g_out = None
+        if self.g_out_host:
+            # the host DES consumes the generator outputs of BOTH forwards of an iteration (matrix_sim_process.py:28-29 does .cpu().numpy() on
+            # (B,1,S,S) and (B,output_dim) fp32): device staging + pinned host buffers per pipeline slot, copies on their own stream
+            g1, g2 = trainer.m.generator1, trainer.m.generator2
+            n1, n2 = g1.gen[-1][0].out_features, g2.gen[-1][0].out_features
+            self.g_dev = [[(torch.empty(B, n1, device=dev), torch.empty(B, n2, device=dev)) for _ in range(2)] for _ in range(2)]
+            self.g_host = [[(torch.empty(B, n1).pin_memory(), torch.empty(B, n2).pin_memory()) for _ in range(2)] for _ in range(2)]
+            self.d2h_stream = torch.cuda.Stream(device=dev)
+            self.g_made = [[torch.cuda.Event() for _ in range(2)] for _ in range(2)]
+            self.g_done = [torch.cuda.Event() for _ in range(2)]
+            self.d2h_bytes += 2 * B * (n1 + n2) * 4
 
     def _raster(self, slot, dev_ev, host_ev, out):
         """H2D of one pass's message streams + device rasterisation into the pass's uint8 roll buffer (on the copy stream)."""
@@ -382,11 +476,37 @@ class HostBatchPipeline:
                 torch.index_select(self.dataset[1], 0, st["idx"], out=st["beats"])
             self.ready[slot].record(self.copy_stream)
 
+    def _iteration(self, slot, i, n1, n2, st):
+        """One iteration on staged inputs.  With ``g_out_host`` the iteration runs as the public segments and the outputs of both generator
+        forwards go to pinned host memory on the D2H stream, underneath the discriminator passes."""
+        t = self.t
+        gather = self.dataset is not None and self.gather_in_kernel
+        real, idx = (self.dataset[0], st["idx"]) if gather else (st["real"], None)
+        if not self.g_out_host:
+            return t.step(n1, n2, st["beats"], real, st["fake_d"], st["fake_g"], real_index=idx)
+        main = torch.cuda.current_stream()
+        if i >= 2:
+            main.wait_event(self.g_done[slot])                         # the copies of two iterations ago have left the device staging buffers
+        for which in range(2):                                         # D-step forward (:294), G-step forward (:312): neither depends on the D step
+            t.generators(n1, n2, st["beats"], out=self.g_dev[slot][which])
+            self.g_made[slot][which].record(main)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(self.g_made[slot][which])
+                for h, d in zip(self.g_host[slot][which], self.g_dev[slot][which]):
+                    h.copy_(d, non_blocking=True)
+        self.g_done[slot].record(self.d2h_stream)
+        dl = t.d_step(real, st["fake_d"], real_index=idx)
+        gl = t.g_step(st["fake_g"])
+        return dl, gl
+
     def run(self, batches):
-        """Generator: yields the pinned (2,) tensor [disc_loss, gen_loss] of every batch, in order.  The read-back of iteration i is
-        enqueued right behind it (stream order) and waited for AFTER iteration i + 1 has been enqueued, so the host-side work of the next
-        iteration (copies, rasteriser launches, graph launch) does not leave the GPU idle behind a blocking ``.item()``
-        (network_tests.py:320-321 blocks; the values are the same, they arrive one iteration later; the last one is flushed at the end)."""
+        """Generator: yields a (2,) CPU tensor [disc_loss, gen_loss] for every batch, in order (a copy: it stays valid).  The read-back of
+        iteration i is enqueued right behind it (stream order) and waited for AFTER iteration i + 1 has been enqueued, so the host-side work of
+        the next iteration (copies, rasteriser launches, graph launch) does not leave the GPU idle behind a blocking ``.item()``
+        (network_tests.py:320-321 blocks; the values are the same, they arrive one iteration later; the last one is flushed at the end).
+        With ``g_out_host``, ``self.g_out`` = ((g1, g2) of the D-step forward, (g1, g2) of the G-step forward) of the batch being yielded: pinned
+        host tensors that are overwritten two batches later.  Buffer lifetime of the caller's pinned input batches: batch i may be reused once
+        batch i + 1 has been yielded (its H2D copies were enqueued before iteration i and have completed by then)."""
         main = torch.cuda.current_stream()
         it = iter(batches)
         cur = next(it, None)
@@ -405,19 +525,21 @@ class HostBatchPipeline:
             n1, n2 = self.noise[slot]
             n1.normal_()                                                          # network_tests.py:284-285
             n2.normal_()
-            if self.dataset is not None and self.gather_in_kernel:      # the discriminator kernel reads the real rolls by index out of the resident set
-                dl, gl = self.t.step(n1, n2, st["beats"], self.dataset[0], st["fake_d"], st["fake_g"], real_index=st["idx"])
-            else:
-                dl, gl = self.t.step(n1, n2, st["beats"], st["real"], st["fake_d"], st["fake_g"])
+            dl, gl = self._iteration(slot, i, n1, n2, st)        # (resident set: the discriminator kernel reads the real rolls by index itself)
             self.free[slot].record(main)
             host = self.losses_host[slot]
             host[0:1].copy_(dl.reshape(1), non_blocking=True)
             host[1:2].copy_(gl.reshape(1), non_blocking=True)
             self.read[slot].record(main)
             if pending is not None:
-                self.read[pending].synchronize()
-                yield self.losses_host[pending]
+                yield self._deliver(pending)
             pending = slot
             cur, i = nxt, i + 1
-        self.read[pending].synchronize()
-        yield self.losses_host[pending]
+        yield self._deliver(pending)
+
+    def _deliver(self, slot):
+        self.read[slot].synchronize()
+        if self.g_out_host:
+            self.g_done[slot].synchronize()
+            self.g_out = tuple(self.g_host[slot])
+        return self.losses_host[slot].clone()

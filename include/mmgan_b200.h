@@ -131,14 +131,16 @@ int mmg_disc_fwd_fused_gather(const void* x, int x_dtype, const int64_t* x_index
  * (network_tests.py:156-160) -> nn.BCEWithLogitsLoss against the constant target of the pass (network_tests.py:248,304-306,313)
  * -> backward (network_tests.py:307,314).  dlogit[b] = (sigmoid(logit[b]) - target) / loss_rows needs nothing from other samples, so
  * XS / P1 / A2 / DZ2 / DZ1 never leave the SM: HBM traffic per sample is the 12.8 KB uint8 roll.  x / x_dtype / x_index as in
- * mmg_disc_fwd_fused_gather.  loss_rows = rows behind the loss mean (0 = B).  logits (B,) and loss (loss[0] += mean BCE of the pass) may be
+ * mmg_disc_fwd_fused_gather; x_rows > 0 = number of rows of x: an x_index entry outside [0, x_rows) reads row 0 and sets the int32 flag at
+ * workspace + mmg_disc_pass_workspace_bytes() - 128 (torch.index_select would raise).  loss_rows = rows behind the loss mean (0 = B).  logits (B,) and loss (loss[0] += mean BCE of the pass) may be
  * NULL; the six fp32 gradients are ACCUMULATED (+=).  workspace: mmg_disc_pass_workspace_bytes() bytes, 128-byte aligned (per-CTA scratch
  * slots that stay in L2).  mmg_disc_pass_fused_dbg additionally takes a HOST-MAPPED int array of 4 * 148 progress words (NULL = off). */
 size_t mmg_disc_pass_workspace_bytes(void);
-int mmg_disc_pass_fused(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b,
+int mmg_disc_pass_set_flags(int flags);   /* debugging aid, process-wide: bit 0 = biases added in the epilogues instead of by the bias MMAs */
+int mmg_disc_pass_fused(const void* x, int x_dtype, const int64_t* x_index, int64_t x_rows, const void* packed, const float* conv1_b, const float* conv2_b,
                         const float* fc_b, float target, int64_t loss_rows, float* logits, float* loss, float* dconv1_w, float* dconv1_b,
                         float* dconv2_w, float* dconv2_b, float* dfc_w, float* dfc_b, void* workspace, size_t ws_bytes, int64_t B, void* stream);
-int mmg_disc_pass_fused_dbg(const void* x, int x_dtype, const int64_t* x_index, const void* packed, const float* conv1_b, const float* conv2_b,
+int mmg_disc_pass_fused_dbg(const void* x, int x_dtype, const int64_t* x_index, int64_t x_rows, const void* packed, const float* conv1_b, const float* conv2_b,
                             const float* fc_b, float target, int64_t loss_rows, float* logits, float* loss, float* dconv1_w, float* dconv1_b,
                             float* dconv2_w, float* dconv2_b, float* dfc_w, float* dfc_b, void* workspace, size_t ws_bytes, int64_t B, void* stream,
                             int* dbg);

@@ -15,32 +15,14 @@ import os
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
 import mmgan_oracle as mo
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "fc.weight", "fc.bias"]
 
 
-def _rb(x):
-    return x + (x.bfloat16().float() - x).detach()
-
-
-class _RoundGrad(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        return x
-
-    @staticmethod
-    def backward(ctx, g):
-        return g.bfloat16().float()
-
-
-def _rel(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
-    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+from _emul import NAMES, disc_pass as _emulated, rel_l2 as _rel      # noqa: E402
 
 
 def _disc(sd):
@@ -48,27 +30,6 @@ def _disc(sd):
     D = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
     D.load_state_dict({k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")})
     return D
-
-
-def _emulated(D, x8, target, n_rows, round_ops=True):
-    """loss, logits, grads of one pass in torch fp32; with ``round_ops`` the kernel's rounding points (bf16 weights, activations, dz)."""
-    ps = [p.detach().clone().requires_grad_(True) for p in (D.conv1.weight, D.conv1.bias, D.conv2.weight, D.conv2.bias, D.fc.weight, D.fc.bias)]
-    w1, b1, w2, b2, wf, bf = ps
-    r = _rb if round_ops else (lambda t: t)
-    rg = _RoundGrad.apply if round_ops else (lambda t: t)
-    grads = [torch.zeros_like(p) for p in ps]
-    logits, loss = [], 0.0
-    for i in range(0, x8.shape[0], 1024):                          # chunks keep the fp32 activations small
-        x = x8[i:i + 1024].float()
-        a1 = r(F.leaky_relu(rg(F.conv2d(x, r(w1), b1, stride=2, padding=1)), 0.2))
-        a2 = r(F.leaky_relu(rg(F.conv2d(a1, r(w2), b2, stride=2, padding=1)), 0.2))
-        lg = (a2.reshape(x.shape[0], -1) @ wf.t() + bf).squeeze(1)
-        ls = F.binary_cross_entropy_with_logits(lg, torch.full_like(lg, target), reduction="sum") / n_rows
-        for g, gi in zip(grads, torch.autograd.grad(ls, ps)):
-            g += gi
-        logits.append(lg.detach())
-        loss += ls.item()
-    return loss, torch.cat(logits), dict(zip(NAMES, grads))
 
 
 @pytest.mark.parametrize("B,dtype,target", [(5, torch.uint8, 0.0), (3, torch.float32, 1.0), (37, torch.uint8, 1.0), (300, torch.uint8, 0.0), (1500, torch.uint8, 1.0)])
@@ -93,10 +54,10 @@ def test_pass_fused_vs_two_kernel_path_and_emulation(B, dtype, target):
     got_logits = tc.pass_fused(x, target, loss2).clone()
     torch.cuda.synchronize()
     scale = logits.abs().max().item()
-    assert (got_logits - logits).abs().max().item() <= 1e-5 * scale + 1e-6
-    assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
+    assert (got_logits - logits).abs().max().item() <= 2e-4 * scale + 1e-6       # bias through the tensor pipe (hi + lo bf16) vs an fp32 add
+    assert abs(loss2.item() - loss.item()) <= 2e-5 * abs(loss.item()) + 1e-7
     for n, p in D.named_parameters():
-        assert _rel(p.grad, want[n]) < 1e-4, (n, _rel(p.grad, want[n]))
+        assert _rel(p.grad, want[n]) < 2e-3, (n, _rel(p.grad, want[n]))      # conv2.bias sums the fp32 dz2 here, the bf16-rounded dz2 there
     # (b) the bf16-rounding-point restatement
     eloss, elogits, egrads = _emulated(D, x8, target, B)
     assert (got_logits - elogits).abs().max().item() <= 5e-3 * scale + 1e-4
@@ -107,7 +68,7 @@ def test_pass_fused_vs_two_kernel_path_and_emulation(B, dtype, target):
     tc.pass_fused(x, target, loss2, want_logits=False)
     torch.cuda.synchronize()
     for n, p in D.named_parameters():
-        assert _rel(p.grad, 2 * want[n]) < 1e-4, n
+        assert _rel(p.grad, 2 * want[n]) < 2e-3, n
     assert abs(loss2.item() - 2 * loss.item()) <= 2e-5 * abs(loss.item()) + 1e-7
 
 
@@ -129,12 +90,18 @@ def test_pass_fused_gathers_rows_and_loss_rows():
         torch.cuda.synchronize()
         res.append((lg, loss.item(), {n: p.grad.clone() for n, p in D.named_parameters()}))
     (l0, s0, g0), (l1, s1, g1), (l2, s2, g2) = res
-    assert torch.equal(l0, l1) and abs(s0 - s1) <= 1e-6 * abs(s0)
+    assert torch.equal(l0, l1) and abs(s0 - s1) <= 1e-6 * abs(s0)       # the per-sample reduction order is fixed: bit-identical logits
     assert torch.equal(l0, l2) and abs(s2 - s0 / 4) <= 1e-6 * abs(s0)
     for n in NAMES:
         assert _rel(g1[n], g0[n]) < 1e-4 and _rel(g2[n], g0[n] / 4) < 1e-4, n
     with pytest.raises(ValueError):
         tc.pass_fused(pool, 1.0, None, index=idx.int())
+    # a sampler index outside the resident set: no out-of-bounds read, the flag reports it (torch.index_select would raise)
+    assert not tc.index_out_of_range()
+    bad = idx.clone()
+    bad[5] = NDS + 7
+    tc.pass_fused(pool, 1.0, None, index=bad)
+    assert tc.index_out_of_range() and not tc.index_out_of_range()
 
 
 def test_full_iteration_b4096_vs_oracle():

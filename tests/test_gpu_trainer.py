@@ -1,10 +1,11 @@
 """GPU parity of the fused training iteration (MMGANTrainer.step) against the vectors frozen from the
 unmodified reference loop body (tests/golden/mmgan_b16.npz), in both precisions.
 fp32: losses / logits rel 2e-5, grads and post-Adam weights rel-L2 1e-4.
-bf16: loss rel 1e-3, logits abs 0.5 % of scale, grads rel-L2 1e-2, generator outputs as fp32 (the
-generators still run on the fp32 kernels).  Measured on B200 (round 1): conv1.weight 2.9e-2, conv2.weight 1.9e-2, biases
-7e-3: the convolution WEIGHT gradients pass through bf16-stored gradient tensors (dz2, dz1) on top of the bf16 operands,
-so their bound here is 5e-2; everything else keeps 1e-2."""
+bf16: loss rel 1e-3, logits abs 0.5 % of scale, grads rel-L2 1e-2, generator outputs abs 2e-2 (tcgen05 generator blocks).
+The bf16 gradients of conv1.weight / conv2.weight sit at 2-3e-2 from the fp32 reference on THIS synthetic state for any bf16-operand
+arithmetic (rounding w1 / w2 / a1 flips LeakyReLU masks; tools/bf16_error_budget.py), independent of how DZ2 / DZ1 are stored: they are
+bounded by the kernel-vs-emulation distance (<= 1e-2) and by the emulation's own distance to the reference.  With the reference's shipped
+discriminator (SURVEY 8d's probe conditions) all six tensors meet 1e-2: tests/test_artifacts.py::test_bf16_pass_under_survey_probe_conditions."""
 import os
 
 import numpy as np
@@ -25,6 +26,13 @@ def _rel_l2(a, b):
 
 @pytest.mark.parametrize("precision,u8", [("fp32", False), ("fp32", True), ("bf16", True), ("bf16", False)])
 def test_trainer_step_vs_reference_golden(golden_dir, precision, u8):
+    """Every observable of the reference loop body, iteration by iteration.  fp32: the trainer runs its own trajectory and must stay on the
+    reference's.  bf16: D-step quantities (logits, loss, the gradients Adam consumes) are compared strictly in EVERY iteration by starting each
+    iteration from the reference's weights (teacher forcing) -- Adam turns the sign of every near-zero gradient element into a +-lr step, so a
+    free-running bf16 trajectory leaves the fp32 one by design; the G-step quantities (computed after the optimiser step) are checked from the
+    reference's post-Adam weights in test_bf16_g_step_from_reference_weights.  The bf16 gradients of the two convolution weights are bounded
+    through the bf16-rounding-point emulation (tests/_emul.py): kernel vs emulation <= 1e-2, kernel vs reference no worse than the emulation."""
+    from _emul import disc_pass, rel_l2
     from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
     from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
     g = np.load(os.path.join(golden_dir, "mmgan_b16.npz"))
@@ -35,49 +43,69 @@ def test_trainer_step_vs_reference_golden(golden_dir, precision, u8):
     m.load_state_dict(sd0)
     m.train()
     tr = MMGANTrainer(m, lr=0.01, precision=precision, max_batch=B)
-    strict = dict(loss=2e-5, logit=2e-5, grad=1e-4, par=1e-4) if precision == "fp32" else dict(loss=1e-3, logit=5e-3, grad=1e-2, par=2e-2)
-    # bf16 only: Adam's first steps move every weight by ~lr*sign(g), so bf16 rounding of near-zero gradient elements flips
-    # update signs; quantities computed AFTER an optimiser step are compared loosely here and strictly in the next test
-    # (test_bf16_g_step_from_reference_weights): here they only have to stay sane.
-    loose = strict if precision == "fp32" else dict(loss=0.5, logit=10.0, grad=2.0, par=1.0)
+    bf = precision == "bf16"
+    tol = dict(loss=1e-3, logit=5e-3, grad=1e-2) if bf else dict(loss=2e-5, logit=2e-5, grad=1e-4, par=1e-4)
     snap = {}
     tr.on_d_grads = lambda t: snap.__setitem__("g", t.flat_grad.clone())
+    named = dict(m.discriminator.named_parameters())
     for it in range(iters):
         inp = {k: v.to(DEV) for k, v in mo.synth_inputs(B, seed=seed * 1000 + it).items()}
         conv = (lambda t: t.to(torch.uint8)) if u8 else (lambda t: t)
         pre = f"it{it}."
-        tol = strict if it == 0 else loose
+        if bf and it > 0:          # teacher forcing: this iteration starts from the reference's weights (Adam moments keep their own history)
+            with torch.no_grad():
+                for k, p in named.items():
+                    p.copy_(torch.from_numpy(g[f"it{it - 1}.param_d.discriminator." + k]))
+            tr.tc.pack()
+        w_before = {k: p.detach().clone() for k, p in named.items()}
         dl, gl = tr.step(inp["noise1"], inp["noise2"], inp["beats"], conv(inp["real"]), conv(inp["fake_d"]), conv(inp["fake_g"]),
                          torch.from_numpy(g[pre + "inner_d"]).to(DEV), torch.from_numpy(g[pre + "inner_g"]).to(DEV))
         torch.cuda.synchronize()
         assert abs(dl.item() - g[pre + "disc_loss"].item()) <= tol["loss"] * abs(g[pre + "disc_loss"].item()), ("disc_loss", it, dl.item())
-        assert abs(gl.item() - g[pre + "gen_loss"].item()) <= loose["loss"] * abs(g[pre + "gen_loss"].item()), ("gen_loss", it, gl.item())
-        for nm, got, tl in (("logit_fake_d", tr.logit_fake_d, tol), ("logit_real", tr.logit_real, tol), ("logit_fake_g", tr.logit_fake_g, loose)):
+        for nm, got in (("logit_fake_d", tr.logit_fake_d), ("logit_real", tr.logit_real)):
             want = g[pre + nm].reshape(-1)
-            assert np.abs(got.cpu().numpy().reshape(-1) - want).max() <= tl["logit"] * np.abs(want).max() + 2e-6, (nm, it)
-        named = dict(m.discriminator.named_parameters())
+            assert np.abs(got.cpu().numpy().reshape(-1) - want).max() <= tol["logit"] * np.abs(want).max() + 2e-6, (nm, it)
+        if bf:                     # what ideal bf16-operand arithmetic gives for the same two passes, from the same weights
+            Dw = nt.DiscriminatorCNN(roll_size=(2, 128, 50)).to(DEV)
+            Dw.load_state_dict(w_before)
+            _, _, ef = disc_pass(Dw, inp["fake_d"], 0.0, B)
+            _, _, er = disc_pass(Dw, inp["real"], 1.0, B)
         o = 0
-        errs, lim = {}, {}
+        report = {}
         for k, p in named.items():
             gd = snap["g"][o:o + p.numel()].detach().cpu().double().numpy().ravel()
             o += p.numel()
             want_d = g[pre + "grad_d.discriminator." + k].astype(np.float64).ravel()
-            want_gstep = g[pre + "grad_g.discriminator." + k].astype(np.float64).ravel() - want_d
-            # The D-step gradient is (fake-vs-0 part) + (real-vs-1 part); with synthetic fake and real rolls of identical statistics
-            # the two parts nearly cancel, so in bf16 the error is measured against the size of ONE part (the G-step gradient of the
-            # same iteration is such a part) rather than against the much smaller difference.
-            scale = np.linalg.norm(want_d) if precision == "fp32" else max(np.linalg.norm(want_d), np.linalg.norm(want_gstep))
-            errs[k] = np.linalg.norm(gd - want_d) / max(scale, 1e-30)
-            lim[k] = tol["grad"] * (5.0 if (precision == "bf16" and k in ("conv1.weight", "conv2.weight")) else 1.0)
-        assert all(errs[k] <= lim[k] for k in errs), ("grad_d", it, errs)
-        for k, p in named.items():
-            # after the G step .grad holds D-step + G-step gradients (reference: gen_opt.zero_grad() leaves them)
-            assert _rel_l2(p.grad, g[pre + "grad_g.discriminator." + k]) <= loose["grad"], ("grad_g." + k, it, _rel_l2(p.grad, g[pre + "grad_g.discriminator." + k]))
-            assert _rel_l2(p, g[pre + "param_d.discriminator." + k]) <= loose["par"], ("param." + k, it, _rel_l2(p, g[pre + "param_d.discriminator." + k]))
-        if precision == "bf16":       # Adam sanity: |delta p| <= lr per step for every element
+            k_o = np.linalg.norm(gd - want_d) / max(np.linalg.norm(want_d), 1e-30)
+            if not bf:
+                assert k_o <= tol["grad"], ("grad_d", k, it, k_o)
+                continue
+            emu = (ef[k] + er[k]).cpu().double().numpy().ravel()
+            k_e = np.linalg.norm(gd - emu) / max(np.linalg.norm(emu), 1e-30)
+            e_o = np.linalg.norm(emu - want_d) / max(np.linalg.norm(want_d), 1e-30)
+            report[k] = (k_e, e_o, k_o)
+            assert k_e <= tol["grad"], ("grad_d kernel vs bf16 emulation", k, it, report[k])
+            assert k_o <= max(tol["grad"], 1.25 * e_o + k_e), ("grad_d kernel vs reference", k, it, report[k])
+        if bf:
+            print(f"it {it}: grad rel-L2 (kernel vs emulation, emulation vs reference, kernel vs reference)", {k: tuple(f"{x:.1e}" for x in v) for k, v in report.items()})
+            # Adam's first steps are +-lr per element: where the reference gradient is clearly non-zero (>= a quarter of the tensor's rms) the
+            # bf16 update must be the reference's update; nowhere may it differ by more than one full step in the opposite direction
             for k, p in named.items():
                 ref_p = torch.from_numpy(g[pre + "param_d.discriminator." + k]).to(DEV)
-                assert (p - ref_p).abs().max().item() <= 2 * 0.01 * (it + 1) + 1e-6, k
+                gr = torch.from_numpy(g[pre + "grad_d.discriminator." + k]).to(DEV)
+                clear = gr.abs() >= 0.25 * gr.pow(2).mean().sqrt()
+                if it == 0:        # later iterations carry this run's own Adam moments
+                    assert (p - ref_p)[clear].abs().max().item() <= 2e-4, ("post-Adam weights where the gradient is clear", k)
+                assert (p - ref_p).abs().max().item() <= 2 * 0.01 + 1e-6, k
+        else:
+            assert abs(gl.item() - g[pre + "gen_loss"].item()) <= tol["loss"] * abs(g[pre + "gen_loss"].item()), ("gen_loss", it, gl.item())
+            want = g[pre + "logit_fake_g"].reshape(-1)
+            assert np.abs(tr.logit_fake_g.cpu().numpy().reshape(-1) - want).max() <= tol["logit"] * np.abs(want).max() + 2e-6, ("logit_fake_g", it)
+            for k, p in named.items():
+                # after the G step .grad holds D-step + G-step gradients (reference: gen_opt.zero_grad() leaves them)
+                assert _rel_l2(p.grad, g[pre + "grad_g.discriminator." + k]) <= tol["grad"], ("grad_g." + k, it)
+                assert _rel_l2(p, g[pre + "param_d.discriminator." + k]) <= tol["par"], ("param." + k, it)
+        assert np.isfinite(gl.item())
         assert _rel_l2(tr.g2_out, g[pre + "g2_g"]) <= (2e-5 if precision == "fp32" else 1e-2)      # bf16: tcgen05 generator blocks
         assert np.abs(tr.g1_out.cpu().numpy()[:, :, ::4, ::4] - g[pre + "g1_g.sub"]).max() <= (1e-5 if precision == "fp32" else 2e-2)
         assert all(p.grad is None for p in m.generator1.parameters()) and len(tr.gen_opt.state) == 0
@@ -112,11 +140,12 @@ def test_bf16_g_step_from_reference_weights(golden_dir):
         want = g[pre + "logit_fake_g"].reshape(-1)
         assert np.abs(logits.cpu().numpy() - want).max() <= 5e-3 * np.abs(want).max() + 2e-6
         assert abs(tr.loss_g.item() - g[pre + "gen_loss"].item()) <= 1e-3 * abs(g[pre + "gen_loss"].item())
-        errs = {}
+        from _emul import disc_pass, rel_l2
+        _, _, emu = disc_pass(m.discriminator, inp["fake_g"].to(DEV), 1.0, B)       # ideal bf16-operand arithmetic from the same weights
         for k, p in m.discriminator.named_parameters():
-            want_g = g[pre + "grad_g.discriminator." + k] - g[pre + "grad_d.discriminator." + k]       # the G-step contribution alone
-            errs[k] = _rel_l2(p.grad, want_g)
-        assert all(v <= (5e-2 if k in ("conv1.weight", "conv2.weight") else 1e-2) for k, v in errs.items()), (it, errs)
+            want_g = torch.from_numpy(g[pre + "grad_g.discriminator." + k] - g[pre + "grad_d.discriminator." + k]).to(DEV)       # the G-step contribution alone
+            k_e, e_o, k_o = rel_l2(p.grad, emu[k]), rel_l2(emu[k], want_g), rel_l2(p.grad, want_g)
+            assert k_e <= 1e-2 and k_o <= max(1e-2, 1.25 * e_o + k_e), (it, k, k_e, e_o, k_o)
 
 
 def test_graph_replay_matches_eager():
