@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
     const uint32_t tmem = tmem_s;
 
     if (warp >= 16) {
-        // register pool of the CTA = 640 threads x 96: the four non-worker warps give 4 x 32 x 32 registers back, the sixteen worker warps take 16 x 32 x 8
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // (no setmaxnreg: the MMA issue loops must stay fully unrolled -- with run-time tile indices ptxas builds the descriptors in vector registers and
+        // wraps every UTCHMMA in an ELECT / R2UR uniformisation loop, 40-70 cycles per MMA -- and unrolled they need ~88 registers; the pool of the CTA
+        // is 640 x 96, so nothing is left to hand to the workers)
         if (warp == PRODUCER_WARP) {
             // ------------------------------------------------------------------ producer
             if (lane == 0 && n_my > 0) {
@@ -207,11 +208,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                 constexpr uint32_t ID_C1 = tc::idesc_bf16(128, 16), ID_C2 = tc::idesc_bf16(128, 32);
                 // backward
                 constexpr uint64_t P1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);    // conv2 wgrad A: atom 1 = one row (128 B) later
-                constexpr uint64_t DZ2_MN = tc::smem_desc_base(0, 512, tc::SW_64B);       // conv2 wgrad B
+                constexpr uint64_t DZ2_MN2 = tc::smem_desc_base(P1_W * 64, 512, tc::SW_64B);   // conv2 wgrad B: N atom 1 = thirteen rows (one super-pixel row) later
                 constexpr uint64_t KM64 = tc::smem_desc_base(0, 512, tc::SW_64B);         // conv2 dgrad A (DZ2 rows) and B (W2d)
                 constexpr uint64_t XS3_MN = tc::smem_desc_base(128, XS3_PLANE, tc::SW_NONE);   // conv1 wgrad A: 8-row K groups 128 B apart, M atoms one plane apart
                 constexpr uint64_t DZ1_MN = tc::smem_desc_base(128, 1024, tc::SW_128B);        // conv1 wgrad B: DZ1 rows (64 values), one atom
-                constexpr uint32_t ID_WG2 = tc::idesc_bf16(128, 32, 1, 1), ID_DG = tc::idesc_bf16(128, 64), ID_WG1 = tc::idesc_bf16(128, 64, 1, 1);
+                constexpr uint32_t ID_WG2 = tc::idesc_bf16(128, 64, 1, 1), ID_DG = tc::idesc_bf16(128, 64), ID_WG1 = tc::idesc_bf16(128, 64, 1, 1);
                 const uint32_t xs = tc::smem_u32(smem + SM_XS), p1 = tc::smem_u32(smem + SM_P1), w1 = tc::smem_u32(smem + SM_W1), w2 = tc::smem_u32(smem + SM_W2);
                 const uint32_t dz2 = tc::smem_u32(smem + SM_DZ2) + 1024, w2d = tc::smem_u32(smem + SM_W2D), xs3 = tc::smem_u32(smem + SM_XS3);
                 const uint32_t onesa = tc::smem_u32(smem + SM_ONESA), bb1 = tc::smem_u32(smem + SM_BB), bb2 = bb1 + 512;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     tc::tc_fence_after();
                     PASS_DBG(1, it * 16 + 1);
                     PASS_TS(17);
-#pragma unroll 1
+#pragma unroll
                     for (int tile = 0; tile < 14; ++tile) {
                         if (BIAS_MMA) tc::mma_f16_ss_pred(tmem + TM_C1 + tile * 16, tc::smem_desc(ONES_K, onesa), tc::smem_desc(BB_K, bb1), ID_C1, 0, leader);
 #pragma unroll
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     tc::mma_commit_pred(&c1_done, leader);
                     PASS_TS(18);
                     // ---- C2, tile by tile behind the conv1 epilogue
-#pragma unroll 1
+#pragma unroll
                     for (int tile = 0; tile < 4; ++tile) {
                         tc::mbar_wait(&p1_ready[tile], ph);
                         tc::tc_fence_after();
@@ -251,17 +252,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     PASS_DBG(1, it * 16 + 2);
                     PASS_TS(19);
                     // ---- M1: conv2 wgrad K steps + dgrad tile, tile by tile behind the DZ2 pass
-#pragma unroll 1
+#pragma unroll
                     for (int tile = 0; tile < 4; ++tile) {
                         tc::mbar_wait(&dz2_ready[tile], ph);
                         tc::tc_fence_after();
-                        const int k_lo = tile * 8, k_hi = tile == 3 ? K2_STEPS : tile * 8 + 8;
+                        // conv2 wgrad, both vertical taps in ONE MMA per K step: dW2[ty][tx][k][oc] = sum_R' P1[R' + tx][k] * DZ2[R' - 13 ty][oc], so with the A view fixed
+                        // the two ty's are two N atoms of B thirteen rows apart (columns [0,32) = ty 1, [32,64) = ty 0; the zero halo in front of DZ2 and the zero
+                        // rows behind P1 make the out-of-range products vanish).  K runs over R' = 0 .. 447; tile t may issue the steps whose DZ2 rows exist.
+                        const int k_lo = tile * 8, k_hi = tile == 3 ? K2_STEPS + 1 : tile * 8 + 8;
 #pragma unroll
-                        for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-                            for (int k = k_lo; k < k_hi; ++k)
-                                tc::mma_f16_ss_pred(tmem + TM_W2 + ty * 32, tc::smem_desc(P1_MN, p1 + (ty * P1_W + k * 16) * 128), tc::smem_desc(DZ2_MN, dz2 + k * 16 * 64),
-                                                    ID_WG2, (it | k) != 0, leader);
+                        for (int k = k_lo; k < k_hi; ++k)
+                            tc::mma_f16_ss_pred(tmem + TM_W2, tc::smem_desc(P1_MN, p1 + k * 16 * 128), tc::smem_desc(DZ2_MN2, dz2 + (k * 16 - P1_W) * 64), ID_WG2,
+                                                (it | k) != 0, leader);
 #pragma unroll
                         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -289,7 +291,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
         }
     } else {
         // ------------------------------------------------------------------ workers: thread (q, lane, g) owns TMEM lane q*32+lane, column group g
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int q = warp & 3, g = warp >> 2, tl = q * 32 + lane, w = threadIdx.x;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const uint32_t xs_s = tc::smem_u32(smem + SM_XS), p1_s = tc::smem_u32(smem + SM_P1), x_s = tc::smem_u32(smem + SM_X), dz2s = tc::smem_u32(smem + SM_DZ2) + 1024;
@@ -547,8 +548,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
         if (n_my > 0) {
             tc::mbar_wait(&mma2_done, (uint32_t)((n_my - 1) & 1));
             tc::tc_fence_after();
-            {   // conv2: TMEM lane m = tx*64 + (dy*2+dx)*16 + ic, column = ty*32 + oc  ->  conv2.weight[oc][ic][2ty+dy][2tx+dx]; this thread: ty = g>>1, 16 oc
-                const int tx = tl >> 6, dy = (tl >> 5) & 1, dx = (tl >> 4) & 1, ic = tl & 15, ty = g >> 1, oc0 = (g & 1) * 16;
+            {   // conv2: TMEM lane m = tx*64 + (dy*2+dx)*16 + ic, column = (1-ty)*32 + oc  ->  conv2.weight[oc][ic][2ty+dy][2tx+dx]; this thread: 16 oc of one ty
+                const int tx = tl >> 6, dy = (tl >> 5) & 1, dx = (tl >> 4) & 1, ic = tl & 15, ty = 1 - (g >> 1), oc0 = (g & 1) * 16;      // columns [0,32) hold ty = 1
                 uint32_t r[16];
                 tc::tmem_ld_32x16(tmem + tlane + TM_W2 + g * 16, r);
                 tc::tmem_ld_wait();

@@ -297,22 +297,26 @@ raster_stream_kernel(const double* __restrict__ dt, const uint32_t* __restrict__
 // fast path, K1: time chain + cut-off + note compaction (one warp per song)
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_WARPS = 4;
-constexpr int K1_CH = 512;            // messages per chain chunk
+constexpr int K1_CH = 512;            // messages per chunk
 constexpr int K1_CJ = K1_CH / 32;
+constexpr int K1_TB = K1_CH + K1_CH / 16;      // prefix-sum buffer of a warp; the parallel mode pads every 16 doubles by one (conflict-free transposition)
 
-__global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
-                                                                      const int64_t* __restrict__ offsets, int64_t n_songs, int S, int W,
-                                                                      uint32_t* __restrict__ notes, int32_t* __restrict__ note_count,
-                                                                      int32_t* __restrict__ status) {
-    __shared__ __align__(16) double tbuf[K1_WARPS][K1_CH];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t song = (int64_t)blockIdx.x * K1_WARPS + warp;
-    if (song >= n_songs) return;
+// The time steps of datasets.py:35-36 are round_half_even(s_i) with s_i the SEQUENTIAL float64 running sum.  Running that chain on one lane
+// costs >= one dependent DADD per message (round 1: 261 us for 19 M messages, the GPU 7x under-subscribed).  SPECULATE AND VERIFY instead:
+//   * a parallel prefix sum A_i of the same dt (any order of float64 additions of non-negative terms: |A_i - T_i| <= gamma_h T_i with T_i the
+//     exact sum and h the height of the addition tree, here h <= 64), while the sequential sum obeys |s_i - T_i| <= gamma_i T_i
+//     (gamma_k = k u / (1 - k u), u = 2^-53; Higham, Accuracy and Stability of Numerical Algorithms, section 4.2);
+//   * hence |s_i - A_i| <= (gamma_i + gamma_64) T_i < delta_i := 2 (i + 64) 2^-53 A_i, and round_half_even(s_i) == round(A_i) whenever no
+//     k + 1/2 lies within delta_i of A_i (rounding only changes at half-integers);
+//   * a song with ANY message that fails this test (or a negative / non-finite dt, where the bound does not hold) is redone from its first
+//     message by the exact sequential chain.  Bit-exactness is therefore preserved by construction; for continuous dt the fallback rate is
+//     ~ n * 2 delta ~ 3e-5 per 15 000-message song, while streams made of exact half-integers (the rounding tests) always take the chain.
+// PAR = parallel mode.  Returns false when the song has to be redone sequentially.
+template <bool PAR>
+__device__ __forceinline__ bool steps_song(const double* __restrict__ dt, const uint32_t* __restrict__ meta, int64_t a0, int64_t n, int S, int W,
+                                           double* tb, uint32_t* __restrict__ nout, int lane, int& count_out, unsigned& bigvel_out, int& st_out) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t a0 = offsets[song];
-    const int64_t n = offsets[song + 1] - a0;
-    double* tb = tbuf[warp];
-    uint32_t* nout = notes + a0;                                   // at most n records
+    auto TI = [](int e) { return PAR ? e + (e >> 4) : e; };
     double d[K1_CJ];
     uint32_t m[K1_CJ];
 #pragma unroll
@@ -321,24 +325,48 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const do
         d[j] = i < n ? dt[a0 + i] : 0.0;
         m[j] = i < n ? meta[a0 + i] : 0u;
     }
-    double t = 0.0;
+    double t = 0.0;                                                // my_time (datasets.py:32): lane 0's chain, or the chunk carry of the scan
     int st = 0, count = 0;
     unsigned bigvel = 0;                                           // any kept note with velocity > 127 (does not fit K2's packed shared-memory record)
     for (int64_t i0 = 0; i0 < n; i0 += K1_CH) {
         uint32_t cm[K1_CJ];
+        bool bad = false;                                          // PAR: a term the error bound does not cover
 #pragma unroll
-        for (int j = 0; j < K1_CJ; ++j) { tb[lane + 32 * j] = d[j]; cm[j] = m[j]; }
+        for (int j = 0; j < K1_CJ; ++j) {
+            tb[TI(lane + 32 * j)] = d[j];
+            cm[j] = m[j];
+            if (PAR) bad |= !(d[j] >= 0.0 && d[j] <= 1.7e308);
+        }
 #pragma unroll
-        for (int j = 0; j < K1_CJ; ++j) {                          // prefetch the next chunk behind the chain
+        for (int j = 0; j < K1_CJ; ++j) {                          // prefetch the next chunk behind the sums
             const int64_t i = i0 + K1_CH + lane + 32 * j;
             d[j] = i < n ? dt[a0 + i] : 0.0;
             m[j] = i < n ? meta[a0 + i] : 0u;
         }
         __syncwarp();
         const int cnt = (int)((n - i0) < K1_CH ? (n - i0) : K1_CH);
-        if (lane == 0) {                                           // sequential float64 running sum (datasets.py:35)
-            // 8 elements per trip: 4 LDS.128 for the next trip are in flight behind the 8 dependent adds, 4 STS.128 write the prefix sums
-            // back (about 2 instructions per element: with 3 chains per scheduler the loop is bound by the DADD latency, not by issue slots)
+        if (PAR) {
+            if (__any_sync(0xffffffffu, bad)) return false;
+            // lane l owns messages 16 l .. 16 l + 15 of the chunk: local prefix, warp scan of the lane totals, chunk carry (padding holds 0.0)
+            double p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p[j] = tb[17 * lane + j];
+#pragma unroll
+            for (int j = 1; j < 16; ++j) p[j] = __dadd_rn(p[j - 1], p[j]);
+            double inc = p[15];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = __dadd_rn(inc, v);
+            }
+            double excl = __shfl_up_sync(0xffffffffu, inc, 1);    // sum of the lanes below
+            if (lane == 0) excl = 0.0;
+            const double off = __dadd_rn(t, excl);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tb[17 * lane + j] = __dadd_rn(off, p[j]);
+            t = __shfl_sync(0xffffffffu, __dadd_rn(off, p[15]), 31);
+        } else if (lane == 0) {                                    // sequential float64 running sum (datasets.py:35)
+            // 8 elements per trip: 4 LDS.128 for the next trip are in flight behind the 8 dependent adds, 4 STS.128 write the prefix sums back
             const int lim8 = (cnt + 7) & ~7;                       // padding holds 0.0: t + 0.0 == t
             double2* tb2 = reinterpret_cast<double2*>(tb);
             double2 v[4], w[4];
@@ -363,10 +391,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const do
         int first_halt = K1_CH;
         uint32_t rec[K1_CJ];
         unsigned keep = 0;                                         // bit j: message lane+32j is a note inside the contract
+        bool unsure = false;
 #pragma unroll
         for (int j = 0; j < K1_CJ; ++j) {
             const int e = lane + 32 * j;
-            const long long step = __double2ll_rn(tb[e]);          // datasets.py:36 round-half-even
+            const double tv = tb[TI(e)];
+            const long long step = __double2ll_rn(tv);             // datasets.py:36 round-half-even
+            if (PAR && e < cnt) {                                  // is round(s_i) certain to equal round(A_i)?
+                const double dist = fabs((tv - floor(tv)) - 0.5);
+                const double delta = (double)(i0 + e + 64) * tv * 2.220446049250313e-16;      // 2 (i + 64) 2^-53 A_i
+                unsure |= !(dist > delta);
+            }
             const uint32_t kind = cm[j] & 0xFFu, pitch = (cm[j] >> 8) & 0xFFu;
             const bool note = kind == 1u || kind == 2u;
             bool halt = step >= S;                                 // :37-38, every message kind
@@ -383,6 +418,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const do
             rec[j] = ((uint32_t)step & 0xFFFFu) | ((kind == 2u ? 1u : 0u) << 16) | ((pitch & 0x7Fu) << 17) | (((cm[j] >> 16) & 0xFFu) << 24);
             if (note && e < cnt) keep |= 1u << j;
         }
+        if (PAR && __any_sync(0xffffffffu, unsure)) return false;
         const int lim = cnt < first_halt ? cnt : first_halt;
 #pragma unroll
         for (int j = 0; j < K1_CJ; ++j) {                          // ordered compaction, 32 messages per ballot
@@ -395,6 +431,30 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const do
         if (first_halt < K1_CH) break;
         __syncwarp();
     }
+    count_out = count; bigvel_out = bigvel; st_out = st;
+    return true;
+}
+
+// mode: 0 = speculate and verify (sequential chain only for the songs that need it), 1 = sequential chain for every song (round 1's kernel)
+__global__ void __launch_bounds__(K1_WARPS * 32, 3) raster_steps_kernel(const double* __restrict__ dt, const uint32_t* __restrict__ meta,
+                                                                      const int64_t* __restrict__ offsets, int64_t n_songs, int S, int W,
+                                                                      uint32_t* __restrict__ notes, int32_t* __restrict__ note_count,
+                                                                      int32_t* __restrict__ status, int mode, unsigned long long* __restrict__ n_fallback) {
+    __shared__ __align__(16) double tbuf[K1_WARPS][K1_TB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t song = (int64_t)blockIdx.x * K1_WARPS + warp;
+    if (song >= n_songs) return;
+    const int64_t a0 = offsets[song];
+    const int64_t n = offsets[song + 1] - a0;
+    int count = 0, st = 0;
+    unsigned bigvel = 0;
+    bool done = false;
+    if (mode == 0) {
+        done = steps_song<true>(dt, meta, a0, n, S, W, tbuf[warp], notes + a0, lane, count, bigvel, st);
+        if (!done && lane == 0 && n_fallback) atomicAdd(n_fallback, 1ull);
+        __syncwarp();
+    }
+    if (!done) steps_song<false>(dt, meta, a0, n, S, W, tbuf[warp], notes + a0, lane, count, bigvel, st);
     if (lane == 0) {
         note_count[song] = count | (bigvel ? 0x40000000 : 0);
         if (status) status[song] = st;
@@ -644,8 +704,13 @@ int mmg_raster_out_width(int start, int end) {
 // A smaller (or NULL) workspace selects the generic single-kernel path, which needs none.
 size_t mmg_raster_workspace_bytes(int64_t n_songs, int64_t total_events) {
     if (n_songs < 0 || total_events < 0) return 0;
-    return (size_t)total_events * 8 + (size_t)n_songs * 4 + 32;
+    return (size_t)total_events * 8 + (((size_t)n_songs * 4 + 7) & ~(size_t)7) + 32;
 }
+
+static int g_raster_mode = 0;
+// 0 (default): time steps by speculate-and-verify (parallel prefix sum, exact sequential chain only for the songs that need it);
+// 1: the sequential chain for every song.  Both are bit-exact; process-wide; for A/B measurements and tests.
+int mmg_raster_set_mode(int mode) { g_raster_mode = mode; return MMG_OK; }
 
 // out: (n_songs, 2, 128, Wout) of out_dtype (0 = float32, 1 = bfloat16, 2 = uint8 saturating); fully written.
 int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t* offsets, int64_t n_songs, int64_t total_events,
@@ -671,13 +736,15 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
     if (end < 128) clip_slice(start, end, W, &lo, &hi); else clip_slice(0, end, W, &lo, &hi);
     if (hi - lo == 0) return MMG_OK;                                    // nothing to write
     MMG_REQUIRE(n_songs <= 0x7fffffff, MMG_EUNSUPPORTED, "raster: too many songs");
-    if (S <= 65535 && workspace && ws_bytes >= mmg_raster_workspace_bytes(n_songs, total_events) && ((uintptr_t)workspace & 3) == 0) {
+    if (S <= 65535 && workspace && ws_bytes >= mmg_raster_workspace_bytes(n_songs, total_events) && ((uintptr_t)workspace & 7) == 0) {
         const size_t rec_bytes = ((size_t)total_events * 4 + 15) & ~(size_t)15;
         uint32_t* notes = (uint32_t*)workspace;
         uint32_t* sorted = (uint32_t*)((unsigned char*)workspace + rec_bytes);
         int32_t* counts = (int32_t*)((unsigned char*)workspace + 2 * rec_bytes);
+        // the last 8 bytes of the workspace: number of songs that fell back to the sequential chain (cumulative; the caller may zero it)
+        unsigned long long* n_fb = (unsigned long long*)((unsigned char*)workspace + mmg_raster_workspace_bytes(n_songs, total_events) - 8);
         raster_steps_kernel<<<(int)((n_songs + K1_WARPS - 1) / K1_WARPS), K1_WARPS * 32, 0, stream>>>(dt, meta, offsets, n_songs, (int)S, (int)W, notes,
-                                                                                                   counts, status);
+                                                                                                   counts, status, g_raster_mode, n_fb);
         MMG_LAUNCH_CHECK();
         if (out_dtype == 0)
             raster_rows_kernel<float><<<(int)n_songs, K2_THREADS, 0, stream>>>(notes, sorted, counts, offsets, (int)W, (int)lo, (int)hi, (float*)out);

@@ -39,6 +39,9 @@ uint64_t mmg_launch_count(void);      /* kernels launched by this library so far
  * bit1 = note with pitch >= 128 met (the reference's IndexError path). */
 int mmg_raster_out_width(int start, int end);                          /* datasets.py:49-54 re-slice */
 size_t mmg_raster_workspace_bytes(int64_t n_songs, int64_t total_events);
+/* time steps of the workspace path: 0 (default) speculate-and-verify parallel prefix sums, the exact sequential chain only for the songs that
+ * need it (their count accumulates in the last 8 bytes of the workspace, uint64); 1 = the sequential chain for every song.  Bit-exact both. */
+int mmg_raster_set_mode(int mode);
 int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t* offsets, int64_t n_songs,
                           int64_t total_events, int sequence_length, int start, int end, int out_dtype, void* out,
                           int32_t* status, void* workspace, size_t ws_bytes, void* stream);

@@ -36,7 +36,7 @@ class DiscriminatorCNN(nn.Module):                                              
     def forward(self, image):
         x = self.leaky_relu(self.conv1(image))
         x = self.leaky_relu(self.conv2(x))
-        return self.fc(x.view(len(x), -1))
+        return self.fc(x.reshape(len(x), -1))
 
 
 class EagerMMGAN:

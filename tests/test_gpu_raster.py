@@ -137,3 +137,60 @@ def test_preprocess_maestro_matches_notebook_loop(tmp_path):
     ds.save_preprocessed(got, p)
     back = pickle.load(open(p, "rb"))
     assert len(back) == len(got) and torch.equal(back[3][1], got[3][1])
+
+
+def test_speculative_steps_match_sequential_chain_and_fall_back_when_needed():
+    """csrc/raster.cu K1: time steps by a parallel prefix sum that is VERIFIED against an error bound, the exact sequential float64 chain only
+    for the songs that fail the test.  (a) both modes give the C oracle's rolls on continuous dt, with (almost) no fall-backs; (b) streams whose
+    prefix sums sit exactly on k + 1/2 (round-half-even territory) and streams that sit a few ulps next to k + 1/2 -- where a different
+    summation order WOULD round differently -- must take the fall-back and still be bit-exact; (c) negative dt (outside the contract) falls back."""
+    from gan_des_midi_music_gen_b200 import _native as N
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    if PATH["v"] != "sort":
+        pytest.skip("the speculative step kernel belongs to the workspace ('sort') path")
+    rng = np.random.default_rng(123)
+
+    def run(dt, meta, off, S, a, b, mode):
+        N.lib().mmg_raster_set_mode(mode)
+        try:
+            ws = torch.zeros(ds.raster_workspace_bytes(len(off) - 1, len(dt)), dtype=torch.uint8, device="cuda")
+            out = ds.rasterize_events(_dev(dt), _dev(meta.view(np.int32)), _dev(off), S, a, b, path="sort", workspace=ws)
+            torch.cuda.synchronize()
+            return out.cpu().numpy(), int(ws[-8:].view(torch.int64).item())
+        finally:
+            N.lib().mmg_raster_set_mode(0)
+
+    # (a) continuous dt, long songs (several 512-message chunks, carries between chunks)
+    dt, meta, off = ro.synth_songs(96, 6000, 300.0, seed=9)
+    want, _ = ro.raster_batch_c(dt, meta, off, 300, 0, 300)
+    got0, fb0 = run(dt, meta, off, 300, 0, 300, 0)
+    got1, fb1 = run(dt, meta, off, 300, 0, 300, 1)
+    assert np.array_equal(got0, want) and np.array_equal(got1, want)
+    assert fb1 == 0 and fb0 <= 1, (fb0, fb1)                       # expected fall-back rate ~1e-5 per song
+    # (b) exact half-integers, and half-integers perturbed by a few ulps (0.1 + 0.2 + 0.2 style sums)
+    songs = []
+    for k in range(24):
+        n = int(rng.integers(40, 1400))
+        if k % 3 == 0:
+            d = rng.integers(0, 4, n) * 0.5
+        elif k % 3 == 1:
+            d = rng.choice([0.1, 0.2, 0.3, 0.7, 0.15, 0.35], n)     # decimal fractions: prefix sums land within ulps of k + 1/2 again and again
+        else:
+            d = rng.choice([0.5, 0.25, 1.0 / 3.0, 1.0 / 6.0], n)
+        songs.append(d.astype(np.float64))
+    dt = np.concatenate(songs)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in songs])]).astype(np.int64)
+    kind = rng.integers(0, 3, len(dt)).astype(np.uint32)
+    meta = (kind | (rng.integers(21, 109, len(dt)).astype(np.uint32) << 8) | (rng.integers(0, 128, len(dt)).astype(np.uint32) << 16)).astype(np.uint32)
+    meta[kind == 0] = 0
+    want, _ = ro.raster_batch_c(dt, meta, off, 100, 0, 50)
+    got0, fb0 = run(dt, meta, off, 100, 0, 50, 0)
+    got1, _ = run(dt, meta, off, 100, 0, 50, 1)
+    assert np.array_equal(got0, want) and np.array_equal(got1, want)
+    assert fb0 >= 8, fb0                                           # at least the exact-half-integer songs went through the chain
+    # (c) a negative dt: the bound does not cover it
+    dt2, meta2, off2 = ro.synth_songs(4, 700, 60.0, seed=2)
+    dt2[1000] = -0.25
+    got0, fb0 = run(dt2, meta2, off2, 100, 0, 50, 0)
+    got1, _ = run(dt2, meta2, off2, 100, 0, 50, 1)
+    assert np.array_equal(got0, got1) and fb0 == 1                 # (decreasing time is outside the contract of the sort-by-pitch replay: only the step kernels are compared)
