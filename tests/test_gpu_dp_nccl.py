@@ -4,7 +4,9 @@
   batch (the fp64 column sums are all-reduced between the layer kernels; same bf16 operands, so the tolerance is fp32 summation order).
 * MMGANTrainer(sync_bn=True) over 2 ranks: summed D-step gradients / world, averaged losses and post-Adam discriminator weights == the
   single-process iteration on the global batch (D has no BatchNorm, mean-loss gradients are the average of shard gradients).
-Skipped on a box with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
+With 2+ GPUs the ranks sit on their own devices and talk NCCL (`gpurun --gpus 2`); on a 1-GPU box the same two rank processes share
+the device and talk gloo ("virtual shards"): the sharded code path -- batch sharding, SyncBN sum all-reduces, flat gradient all-reduce,
+1/world in the Adam kernel, per-segment CUDA graphs -- is the same, only the transport differs."""
 import os
 import sys
 
@@ -26,12 +28,15 @@ def _mk(device, seed=4):
     return m.train()
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, backend, ngpu):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.cuda.set_device(rank % ngpu)
+    dev = torch.device("cuda", rank % ngpu)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from gan_des_midi_music_gen_b200.gen_tc import GenTC
         from gan_des_midi_music_gen_b200.trainer import MMGANTrainer, shard_batch
@@ -86,12 +91,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sync_bn_and_sharded_iteration_match_global_batch():
+    ngpu = torch.cuda.device_count()
+    backend = "nccl" if ngpu >= 2 else "gloo"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, backend, max(1, min(ngpu, 2)))) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
