@@ -67,7 +67,23 @@ class _GenBase(nn.Module):
     def make_gen_block(self, input_dim, output_dim):
         return _GenBlock(input_dim, output_dim)
 
+    def enable_tensor_cores(self, max_batch, enabled=True):
+        """Route ``forward`` through the bf16 tcgen05 generator blocks (csrc/gen_tc.cu) whenever autograd is off (``torch.no_grad()`` / inference:
+        the reference never back-propagates into the generators; with autograd on the fp32 differentiable kernels are used)."""
+        if enabled:
+            from ..gen_tc import GenTC
+            self._tc = GenTC(self, int(max_batch))
+        else:
+            self._tc = None
+        return self
+
     def _features(self, noise, input_tensor):
+        tc = getattr(self, "_tc", None)
+        if tc is not None and not torch.is_grad_enabled() and len(noise) <= tc.cap:
+            if input_tensor is None:
+                input_tensor = torch.randn(len(noise), self.input_tensor_dim).to(self.device)      # same RNG consumption as below
+            require_cuda(noise, input_tensor)
+            return tc.forward(noise, input_tensor)
         if input_tensor is None:
             # drawn on the default (CPU) generator and then moved, like the reference (:83-84,:119-120),
             # so the global RNG stream is consumed identically
@@ -140,8 +156,25 @@ class DiscriminatorCNN(nn.Module):
         self.final_size = hidden_dim * 2 * ((roll_size[1] // 4) * (roll_size[2] // 4))
         self.fc = nn.Linear(self.final_size, 1)
 
+    def enable_tensor_cores(self, max_batch, enabled=True):
+        """Route ``forward`` (and its autograd backward) through the bf16 tcgen05 kernels (csrc/disc_tc_fused.cu) for inputs of shape
+        (B <= max_batch, 2, 128, 50), float32 or uint8: bf16 operands, fp32 accumulation, fp32 master weights (tolerances of SURVEY 8d).  Off by
+        default: the module then computes in fp32 like the reference.  The training loop proper should use ``trainer.MMGANTrainer`` (one kernel per
+        D pass); this switch is for code that keeps calling the module (the reference loop as written, demo notebooks)."""
+        if enabled:
+            from ..disc_tc import DiscTC
+            self._tc = DiscTC(self, int(max_batch))
+        else:
+            self._tc = None
+        return self
+
     def forward(self, image):
         require_cuda(image)
+        tc = getattr(self, "_tc", None)
+        if tc is not None and image.dim() == 4 and tuple(image.shape[1:]) == (2, 128, 50) and image.shape[0] <= tc.cap \
+                and image.dtype in (torch.float32, torch.uint8):
+            from ..disc_tc import DiscTCFunction
+            return DiscTCFunction.apply(image, tc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.fc.weight, self.fc.bias)
         x = Fn.conv2d(image, self.conv1.weight, self.conv1.bias, 2, 1, Fn.ACT_LRELU)
         x = Fn.conv2d(x, self.conv2.weight, self.conv2.bias, 2, 1, Fn.ACT_LRELU)
         return Fn.linear(x.view(len(x), -1), self.fc.weight, self.fc.bias)

@@ -399,17 +399,25 @@ __global__ void __launch_bounds__(256) gen_gram_partial_kernel(const float* __re
     if (tid < GS_K) out[GS_K * GS_K + tid] = ssum;
 }
 
-__global__ void gen_gram_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ red) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= GS_PART) return;
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};                       // 8 independent loads in flight per thread
-    int p = 0;
-    for (; p + 8 <= nparts; p += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] += part[(size_t)(p + u) * GS_PART + i];
+// 8 threads per output value (partials p = part, part + 8, ...), shuffle reduction: 4160 outputs x 8 threads = 130 CTAs of 256 threads
+// (the round-1 version used one thread per output in 17 CTAs: 27 us of load latency for 4.9 MB)
+__global__ void __launch_bounds__(256) gen_gram_reduce_kernel(const double* __restrict__ part, int nparts, double* __restrict__ red) {
+    const int i = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+    const int ii = i < GS_PART ? i : GS_PART - 1;                  // keep the whole warp in the shuffles
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int p = sub;
+    for (; p + 24 < nparts; p += 32) {                             // 4 independent loads in flight per thread
+        a0 += part[(size_t)p * GS_PART + ii];
+        a1 += part[(size_t)(p + 8) * GS_PART + ii];
+        a2 += part[(size_t)(p + 16) * GS_PART + ii];
+        a3 += part[(size_t)(p + 24) * GS_PART + ii];
     }
-    for (; p < nparts; ++p) a[0] += part[(size_t)p * GS_PART + i];
-    red[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (; p < nparts; p += 8) a0 += part[(size_t)p * GS_PART + ii];
+    double v = (a0 + a1) + (a2 + a3);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sub == 0 && i < GS_PART) red[i] = v;
 }
 
 // four threads per output column: thread `part` takes the rows i = part, part + 4, ... of G; quad shuffle reduction
@@ -486,7 +494,7 @@ int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double
     const int grid = (int)(tiles < MMG_NUM_SMS ? tiles : MMG_NUM_SMS);
     gen_gram_partial_kernel<<<grid, 256, 0, stream>>>(z_prev, (long long)M, K, in_sums, count, in_gamma, in_beta, eps, part);
     MMG_LAUNCH_CHECK();
-    gen_gram_reduce_kernel<<<(GS_PART + 255) / 256, 256, 0, stream>>>(part, grid, red);
+    gen_gram_reduce_kernel<<<(GS_PART + 31) / 32, 256, 0, stream>>>(part, grid, red);
     MMG_LAUNCH_CHECK();
     gen_gram_colstats_kernel<<<(N + 63) / 64, 256, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
     MMG_LAUNCH_CHECK();

@@ -40,9 +40,10 @@ class DiscTC:
         d = self.d
         N.call("mmg_disc_pack_weights", N.ptr(d.conv1.weight.data), N.ptr(d.conv2.weight.data), N.ptr(d.fc.weight.data), N.ptr(self.packed), N.stream())
 
-    def forward(self, x, index=None):
+    def forward(self, x, index=None, bufs=None):
         """x: (B,2,128,50) uint8 or float32 CUDA tensor -> logits (B,) fp32 (a view of an internal buffer).
-        ``index`` (B,) int64 CUDA tensor: the pass runs on rows ``x[index]`` of a larger resident set, gathered inside the kernel."""
+        ``index`` (B,) int64 CUDA tensor: the pass runs on rows ``x[index]`` of a larger resident set, gathered inside the kernel.
+        ``bufs`` = (xs, p1, a2, logits): activation buffers of this call instead of the internal ones (fused forward only; p1 zero-initialised)."""
         N.require_cuda(x, index)
         B = x.shape[0] if index is None else index.numel()
         if B > self.cap or tuple(x.shape[1:]) != (2, 128, 50) or x.dtype not in _XD:
@@ -53,8 +54,11 @@ class DiscTC:
         d, s = self.d, N.stream()
         logits = self.logits[:B]
         if self.fused_forward:       # one persistent kernel: P1 stays in shared memory between conv1 and conv2 (csrc/disc_tc_fused.cu)
+            xs, p1, a2 = (self.xs, self.p1, self.a2) if bufs is None else bufs[:3]
+            if bufs is not None:
+                logits = bufs[3]
             N.call("mmg_disc_fwd_fused_gather", N.ptr(x), _XD[x.dtype], N.ptr(index), N.ptr(self.packed), N.ptr(d.conv1.bias.data), N.ptr(d.conv2.bias.data),
-                   N.ptr(d.fc.bias.data), N.ptr(self.xs), N.ptr(self.p1), N.ptr(self.a2), N.ptr(logits), B, s)
+                   N.ptr(d.fc.bias.data), N.ptr(xs), N.ptr(p1), N.ptr(a2), N.ptr(logits), B, s)
             self.x, self.B = x, B
             return logits
         N.call("mmg_fill_scalar_f32", N.ptr(logits), N.ptr(d.fc.bias.data), B, s)
@@ -100,13 +104,14 @@ class DiscTC:
             p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
         return p.grad
 
-    def backward(self, dlogit):
-        """dlogit: (B,) fp32 = dLoss/dlogits of the last forward.  Accumulates into the six ``.grad`` tensors."""
-        B, d, s = self.B, self.d, N.stream()
+    def backward(self, dlogit, bufs=None):
+        """dlogit: (B,) fp32 = dLoss/dlogits of the last forward (or of the forward that filled ``bufs``).  Accumulates into the six ``.grad`` tensors."""
+        B, d, s = (self.B if bufs is None else dlogit.numel()), self.d, N.stream()
         dlogit = dlogit.contiguous()
         g = {k: self._grad(p) for k, p in d.named_parameters()}
         if self.fused_backward:      # one persistent kernel: dz2 / dz1c never leave the SM (csrc/disc_tc_fused.cu)
-            N.call("mmg_disc_bwd_fused", N.ptr(self.xs), N.ptr(self.p1), N.ptr(self.a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(g["conv1.weight"]),
+            xs, p1, a2 = (self.xs, self.p1, self.a2) if bufs is None else bufs[:3]
+            N.call("mmg_disc_bwd_fused", N.ptr(xs), N.ptr(p1), N.ptr(a2), N.ptr(dlogit), N.ptr(self.packed), N.ptr(g["conv1.weight"]),
                    N.ptr(g["conv1.bias"]), N.ptr(g["conv2.weight"]), N.ptr(g["conv2.bias"]), N.ptr(g["fc.weight"]), N.ptr(g["fc.bias"]), B, s)
             return
         N.call("mmg_sum_f32", N.ptr(dlogit), B, N.ptr(g["fc.bias"]), 1, s)
@@ -114,3 +119,34 @@ class DiscTC:
         N.call("mmg_disc_conv2_wgrad", N.ptr(self.p1), N.ptr(self.dz2), N.ptr(g["conv2.weight"]), B, s)
         N.call("mmg_disc_conv2_dgrad", N.ptr(self.dz2), N.ptr(self.packed), N.ptr(self.p1), N.ptr(self.dz1c), N.ptr(g["conv1.bias"]), B, s)
         N.call("mmg_disc_conv1_wgrad", N.ptr(self.xs), N.ptr(self.dz1c), N.ptr(g["conv1.weight"]), B, s)
+
+
+class DiscTCFunction(torch.autograd.Function):
+    """``DiscriminatorCNN.forward`` on the tensor-core kernels as an autograd node (``DiscriminatorCNN.enable_tensor_cores``): forward = the fused
+    forward kernel, backward = the fused backward kernel; every call owns its activation buffers (the reference calls the discriminator on the fake and
+    on the real batch before one backward, network_tests.py:294-307), parameter gradients are returned to autograd."""
+
+    @staticmethod
+    def forward(ctx, x, tc, w1, b1, w2, b2, wf, bf):
+        B = x.shape[0]
+        bfk = dict(dtype=torch.bfloat16, device=x.device)
+        bufs = (torch.empty(B * XROWS, 8, **bfk), torch.zeros(B * ROWS, 64, **bfk), torch.empty(B * ROWS, 32, **bfk), torch.empty(B, device=x.device))
+        with torch.no_grad():
+            tc.pack()                                   # the fp32 master weights may have changed since the last call
+            logits = tc.forward(x, bufs=bufs)
+        ctx.tc, ctx.bufs = tc, bufs
+        return logits.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        tc = ctx.tc
+        d = tc.d
+        saved = {k: p.grad for k, p in d.named_parameters()}
+        with torch.no_grad():
+            for p in d.parameters():
+                p.grad = None
+            tc.backward(dlogits.reshape(-1).float().contiguous(), bufs=ctx.bufs)      # accumulates into fresh zeroed .grad tensors
+            grads = [p.grad for p in (d.conv1.weight, d.conv1.bias, d.conv2.weight, d.conv2.bias, d.fc.weight, d.fc.bias)]
+            for k, p in d.named_parameters():
+                p.grad = saved[k]
+        return (None, None, *grads)

@@ -208,3 +208,83 @@ def test_gandes_loop_body(golden_dir, fused):
     gen.eval()
     with torch.no_grad():
         _close(gen(noise), g["eval.gen_out"], what="eval.gen_out")
+
+
+def test_mlp_discriminator_forward_backward_vs_oracle():
+    """R8: the MLP `Discriminator` (network_tests.py:126-144; unused by MultiModalGAN, part of the module's API): forward on a flattened roll and the
+    autograd backward of a BCE loss through it, against the oracle restatement (mmgan_oracle.disc_mlp_forward) with the same weights."""
+    import torch.nn.functional as F
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    B, roll = 6, (2, 32, 10)
+    torch.manual_seed(12)
+    D = nt.Discriminator(im_chan=1, hidden_dim=16, roll_size=roll, device=DEV).to(DEV)
+    assert [k for k in D.state_dict()] == [f"disc.{i}.0.{n}" for i in range(3) for n in ("weight", "bias")]
+    sd = {k: v.detach().cpu().clone() for k, v in D.state_dict().items()}
+    x = torch.from_numpy(mo.synth_rolls(B, roll[2], seed=3, p=0.2)[:, :, :roll[1], :]).float().reshape(B, -1)
+    assert x.shape[1] == roll[0] * roll[1] * roll[2]
+    # oracle, CPU fp32
+    ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = mo.disc_mlp_forward(ps, x)
+    loss_w = F.binary_cross_entropy_with_logits(want.squeeze(1), torch.ones(B))
+    gw = torch.autograd.grad(loss_w, list(ps.values()))
+    # this library's kernels
+    got = D(x.to(DEV))
+    assert got.shape == (B, 1)
+    loss = F.binary_cross_entropy_with_logits(got.squeeze(1), torch.ones(B, device=DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    scale = want.abs().max().item()
+    assert (got.detach().cpu() - want.detach()).abs().max().item() <= 2e-5 * scale + 1e-6
+    assert abs(loss.item() - loss_w.item()) <= 2e-5 * abs(loss_w.item())
+    for (k, p), g in zip(D.named_parameters(), gw):
+        err = ((p.grad.cpu() - g).norm() / g.norm().clamp_min(1e-30)).item()
+        assert err <= 1e-4, (k, err)
+    with pytest.raises(Exception):
+        D(x)                                   # CPU tensor: no fallback
+
+
+def test_modules_can_route_to_tensor_cores():
+    """the drop-in nn.Modules reach the tcgen05 kernels without the trainer: DiscriminatorCNN.enable_tensor_cores (forward +
+    autograd backward through the fused bf16 kernels) and Generator.enable_tensor_cores (under no_grad), against the fp32 modules (bf16 bars)."""
+    import torch.nn.functional as F
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    B = 24
+    sd = mo.synth_state(mo.mmgan_shapes(), seed=3, d_scale=0.25)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device=DEV)
+    m.load_state_dict(sd)
+    m.train()
+    inp = {k: v.to(DEV) for k, v in mo.synth_inputs(B, seed=5).items()}
+    D = m.discriminator
+    ones = torch.ones(B, device=DEV)
+    want = D(inp["real"])
+    F.binary_cross_entropy_with_logits(want.squeeze(1), ones).backward()
+    gw = {k: p.grad.clone() for k, p in D.named_parameters()}
+    for p in D.parameters():
+        p.grad = None
+    D.enable_tensor_cores(B)
+    got = D(inp["real"])
+    assert got.shape == (B, 1) and got.requires_grad
+    other = D(inp["fake_d"])                       # a second forward before the backward (the reference's D step does this): own activation buffers
+    F.binary_cross_entropy_with_logits(got.squeeze(1), ones).backward()
+    assert torch.isfinite(other).all()
+    torch.cuda.synchronize()
+    assert (got - want).abs().max().item() <= 5e-3 * want.abs().max().item() + 1e-4
+    for k, p in D.named_parameters():
+        err = ((p.grad - gw[k]).norm() / gw[k].norm()).item()
+        assert err <= 5e-2, (k, err)               # bf16 operands vs fp32 on this synthetic state (tests/_emul.py has the tight comparison)
+    g2 = D(inp["real"].to(torch.uint8))            # uint8 rolls are accepted on this path
+    assert (g2 - got).abs().max().item() <= 1e-5 * got.abs().max().item() + 1e-6
+    D.enable_tensor_cores(B, enabled=False)
+    assert (D(inp["real"]) - want).abs().max().item() <= 1e-6 * want.abs().max().item() + 1e-7
+    # generators: eval-mode forward under no_grad
+    m.eval()
+    with torch.no_grad():
+        w1 = m.generator1(inp["noise1"], inp["inner_d"])
+        w2 = m.generator2(inp["noise2"], inp["beats"])
+        m.generator1.enable_tensor_cores(B)
+        m.generator2.enable_tensor_cores(B)
+        y1 = m.generator1(inp["noise1"], inp["inner_d"])
+        y2 = m.generator2(inp["noise2"], inp["beats"])
+    assert y1.shape == w1.shape and (y1 - w1).abs().max().item() <= 2e-2 and (y2 - w2).abs().max().item() <= 2e-2
+    y3 = m.generator2(inp["noise2"], inp["beats"])     # autograd on: the fp32 differentiable kernels
+    assert y3.requires_grad and (y3 - w2).abs().max().item() <= 1e-5

@@ -167,6 +167,19 @@ def test_speculative_steps_match_sequential_chain_and_fall_back_when_needed():
     got1, fb1 = run(dt, meta, off, 300, 0, 300, 1)
     assert np.array_equal(got0, want) and np.array_equal(got1, want)
     assert fb1 == 0 and fb0 <= 1, (fb0, fb1)                       # expected fall-back rate ~1e-5 per song
+    # long ragged songs (several chunks, carries between chunks, a cut-off in the middle of a song, an empty song); every other song is made of
+    # exact quarter / tenth steps, so its prefix sums keep landing on or next to k + 1/2: those songs must fall back, and everything stays bit-exact
+    lens = [5000, 2049, 7777, 12, 0, 3000, 4097, 2600]
+    parts = [rng.choice([0.5, 0.25, 0.1, 0.2], n) if k % 2 == 0 else rng.exponential(0.02, n) for k, n in enumerate(lens)]
+    dtl = np.concatenate(parts)
+    offl = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    kindl = rng.integers(0, 3, len(dtl)).astype(np.uint32)
+    metal = (kindl | (rng.integers(21, 109, len(dtl)).astype(np.uint32) << 8) | (rng.integers(0, 128, len(dtl)).astype(np.uint32) << 16)).astype(np.uint32)
+    metal[kindl == 0] = 0
+    wantl, _ = ro.raster_batch_c(dtl, metal, offl, 300, 0, 300)
+    g0, f0 = run(dtl, metal, offl, 300, 0, 300, 0)
+    g1, _ = run(dtl, metal, offl, 300, 0, 300, 1)
+    assert np.array_equal(g0, wantl) and np.array_equal(g1, wantl) and f0 >= 3, f0
     # (b) exact half-integers, and half-integers perturbed by a few ulps (0.1 + 0.2 + 0.2 style sums)
     songs = []
     for k in range(24):
