@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                                                                       const PassArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t wbar, x_full, xs_ready, xs_saved, full_xs3, c1a_done, c1b_done, p1_ready[4], c2_done[4], dz2_ready[4], dg_done[4], dg_read[2],
-        dz1_ready[4], mma2_done;
+        dz1_ready[4], mma2_done, c2_read, wg1a_done;
     __shared__ uint32_t tmem_s;
     __shared__ __align__(16) float logit_part[2][16];     // per-warp partial fc dots of the current sample (two phases)
     __shared__ float red_s[48];
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
     if (threadIdx.x == 0) {
         tc::mbar_init(&wbar, 1); tc::mbar_init(&x_full, 1); tc::mbar_init(&xs_saved, 1); tc::mbar_init(&full_xs3, 1);
         tc::mbar_init(&c1a_done, 1); tc::mbar_init(&c1b_done, 1); tc::mbar_init(&mma2_done, 1);
-        tc::mbar_init(&xs_ready, NWORK);
+        tc::mbar_init(&xs_ready, NWORK); tc::mbar_init(&c2_read, NWORK); tc::mbar_init(&wg1a_done, 1);
         for (int i = 0; i < 4; ++i) {
             tc::mbar_init(&p1_ready[i], NWORK); tc::mbar_init(&c2_done[i], 1); tc::mbar_init(&dz2_ready[i], NWORK); tc::mbar_init(&dg_done[i], 1);
             tc::mbar_init(&dz1_ready[i], NWORK);
@@ -283,6 +283,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     }
                     PASS_DBG(1, it * 16 + 2);
                     PASS_TS(17);
+                    // ---- conv1 of the NEXT sample, tiles 0..7, in the window where the tensor pipe would wait for the loss and the DZ2 pass: its XS rows were
+                    // built under this sample's conv2, its accumulator columns held this sample's conv2 accumulators (read by the conv2 epilogue: c2_read)
+                    if (it + 1 < n_my) {
+                        tc::mbar_wait(&xs_ready, ph ^ 1u);
+                        tc::mbar_wait(&c2_read, ph);
+                        tc::tc_fence_after();
+#pragma unroll
+                        for (int tile = 0; tile < 8; ++tile) conv1_tile(tile);
+                        tc::mma_commit_pred(&c1a_done, leader);
+                    }
                     // ---- backward, conv2: wgrad K steps + dgrad tile, tile by tile behind the DZ2 pass (dgrad ring: tile t + 2 after the epilogue has read tile t)
 #pragma unroll
                     for (int tile = 0; tile < 4; ++tile) {
@@ -293,9 +303,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                     }
                     PASS_DBG(1, it * 16 + 3);
                     PASS_TS(18);
-                    // ---- backward, conv1 wgrad: the K steps of a P1-row tile as soon as its DZ1 rows exist; before the last part (which waits for the end of
-                    // the DZ1 epilogue) conv1 of the NEXT sample, tiles 0..7 (its XS rows were built under this sample's conv2; their columns held this
-                    // sample's conv2 accumulators, consumed before the DZ2 pass): the tensor pipe stays busy while the epilogue finishes
+                    // ---- backward, conv1 wgrad: the K steps of a P1-row tile as soon as its DZ1 rows exist.  Parts 0..2 (DZ1 rows < 384) get their own commit:
+                    // the next sample's conv1 epilogue may overwrite those rows while part 3 and conv1 tiles 8..13 are still in the pipe
                     tc::mbar_wait(&full_xs3, ph);
 #pragma unroll
                     for (int part = 0; part < 3; ++part) {
@@ -303,14 +312,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
                         tc::tc_fence_after();
                         wgrad1_part(it, part);
                     }
+                    tc::mma_commit_pred(&wg1a_done, leader);
                     PASS_TS(19);
-                    if (it + 1 < n_my) {
-                        tc::mbar_wait(&xs_ready, ph ^ 1u);
-                        tc::tc_fence_after();
-#pragma unroll
-                        for (int tile = 0; tile < 8; ++tile) conv1_tile(tile);
-                        tc::mma_commit_pred(&c1a_done, leader);
-                    }
                     tc::mbar_wait(&dz1_ready[3], ph);
                     tc::tc_fence_after();
                     wgrad1_part(it, 3);
@@ -414,14 +417,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
             // conv1 tiles 0..7 of this sample were issued in the middle of the previous sample's backward; the P1 rows are free once that sample's
             // conv1 wgrad MMAs have read DZ1.
             if (w == 0) PASS_TS(0);
-            if (it > 0) tc::mbar_wait(&mma2_done, ph ^ 1u);
+            if (it > 0) tc::mbar_wait(&wg1a_done, ph ^ 1u);           // DZ1 rows < 384 of the previous sample have been read (conv1 tiles <= 10 write P1 rows <= 363)
             tc::mbar_wait(&c1a_done, ph);
             tc::tc_fence_after();
             if (w == 0) { PASS_DBG(2, it * 16 + 1); PASS_TS(1); }
 #pragma unroll
             for (int tt = 0; tt < 7; ++tt) {
                 const int tile = 2 * tt + (g >> 1);
-                if (tt == 4) { tc::mbar_wait(&c1b_done, ph); tc::tc_fence_after(); }       // tiles 8..13 were issued behind the previous sample's conv1 wgrad
+                if (tt == 4) {                                        // tiles 8..13 were issued behind the previous sample's last conv1 wgrad part (DZ1 rows >= 384)
+                    if (it > 0) tc::mbar_wait(&mma2_done, ph ^ 1u);
+                    tc::mbar_wait(&c1b_done, ph);
+                    tc::tc_fence_after();
+                }
                 uint32_t r[8];
                 tmem_ld_32x8(tmem + tlane + TM_X + tile * 16 + (g & 1) * 8, r);
                 tc::tmem_ld_wait();
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) disc_pass_fused_kernel(const __gr
             dot = warp_sum(dot);
             if (lane == 0) logit_part[ph][warp] = dot;
             tc::tc_fence_before();
+            tc::mbar_arrive(&c2_read);                                // the conv2 accumulator columns may take conv1 tiles 0..7 of the next sample
             if (w == 0) PASS_TS(4);
             bar_workers();
             // ---- BCE with logits (network_tests.py:304-306,313): loss_b = max(x,0) - x y + log1p(exp(-|x|)); dlogit = (sigmoid(x) - y) / n.

@@ -184,6 +184,50 @@ def test_graph_replay_matches_eager():
         assert _rel_l2(a, b.cpu().numpy()) < 0.05
 
 
+def test_public_segments_match_step():
+    """generators / generators / d_step / g_step (the hand-over points of the host DES, network_tests.py:292-315) == step(): same kernels on the
+    same buffers, each segment replayed from its own CUDA graph from the third call on; the generator outputs are returned to the caller."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.trainer import MMGANTrainer
+    B = 96
+    torch.manual_seed(13)
+    rolls = [(torch.rand(B, 2, 128, 50) < 0.02).to(torch.uint8).cuda() * 77 for _ in range(3)]
+    noise = [torch.randn(B, 50).cuda() for _ in range(4)]
+    beats = (25 * torch.rand(B, 50)).cuda()
+    out = {}
+    for mode in ("step", "segments"):
+        torch.manual_seed(5)
+        m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150,
+                             device="cuda").train()
+        tr = MMGANTrainer(m, lr=0.01, precision="bf16", max_batch=B)
+        losses, gouts = [], []
+        for it in range(5):
+            if mode == "step":
+                dl, gl = tr.step(noise[0], noise[1], beats, rolls[0], rolls[1], rolls[2], noise[2], noise[3])
+                gouts.append((tr.g1_out.clone(), tr.g2_out.clone()))
+            else:
+                a1, v1 = tr.generators(noise[0], noise[1], beats, inner=noise[2])
+                assert a1.shape == (B, 1, 64, 64) and v1.shape == (B, 20)
+                dl = tr.d_step(rolls[0], rolls[1])
+                a2, v2 = tr.generators(noise[0], noise[1], beats, inner=noise[3])
+                gouts.append((a2.clone(), v2.clone()))
+                gl = tr.g_step(rolls[2])
+            losses.append((float(dl), float(gl)))
+        if mode == "segments":
+            assert {"gen", "d_bwd", "d_opt", "g"} <= {k[0] for k in tr._seg_graphs}, tr._seg_graphs.keys()
+        out[mode] = (losses, gouts, [p.detach().clone() for p in m.discriminator.parameters()], m.generator1.gen[0][1].running_var.clone(),
+                     int(m.generator1.gen[0][1].num_batches_tracked))
+    (l0, g0, p0, rv0, nb0), (l1, g1, p1, rv1, nb1) = out["step"], out["segments"]
+    assert nb0 == nb1 == 10 and torch.allclose(rv0, rv1, rtol=1e-5, atol=1e-7)
+    for (a1, v1), (a2, v2) in zip(g0, g1):               # the generators never change (their Adam is a no-op): same outputs every iteration
+        assert torch.equal(a1, a2) and torch.equal(v1, v2)
+    assert abs(l0[0][0] - l1[0][0]) <= 1e-6 * abs(l0[0][0])   # first iteration: identical weights; later ones differ by the order of fp32 gradient atomics
+    for a, b in zip(l0, l1):
+        assert abs(a[0] - b[0]) <= 2e-3 * max(1.0, abs(a[0])) and abs(a[1] - b[1]) <= 2e-3 * max(1.0, abs(a[1])), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert (a - b).abs().max() <= 5 * 0.01 + 1e-6
+
+
 @pytest.mark.parametrize("resident", [False, True])
 def test_host_batch_pipeline_matches_direct_steps(resident):
     """HostBatchPipeline (double-buffered H2D, optional HBM-resident training set gathered by index) must feed the iteration exactly

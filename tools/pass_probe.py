@@ -106,8 +106,8 @@ def timeline():
     torch.cuda.synchronize()
     print("progress words of CTA 0 / 147:", dbg.numpy()[:4].tolist(), dbg.numpy()[588:592].tolist(), "raw stamps:", dbg.numpy()[1024:1032].tolist(), dbg.numpy()[1040:1048].tolist())
     t = dbg.numpy()[1024:1024 + 64].astype(np.int64) & 0xFFFFFFFF
-    names_w = ["loop top", "mma2_done(prev) + c1a_done seen", "S3 done", "XSb(next) done", "S5 done", "W1 done", "W3 done"]
-    names_m = ["loop top", "C2 issued (all tiles)", "conv2 wgrad + dgrad issued (all tiles)", "conv1 wgrad parts 0..2 issued", "conv1(next) tiles 0..7 + wgrad part 3 issued", "conv1(next) tiles 8..13 issued"]
+    names_w = ["loop top", "wg1a_done(prev) + c1a_done seen", "S3 done", "XSb(next) done", "S5 done", "W1 done", "W3 done"]
+    names_m = ["loop top", "C2 issued (all tiles)", "conv1(next) tiles 0..7 + conv2 wgrad + dgrad issued (all tiles)", "conv1 wgrad parts 0..2 issued", "conv1 wgrad part 3 issued", "conv1(next) tiles 8..13 issued"]
     t0 = int(t[16])
     for smp in range(2):
         print(f"-- sample {6 + smp} of CTA 0 (cycles relative to the MMA thread's loop top of sample 6)")
