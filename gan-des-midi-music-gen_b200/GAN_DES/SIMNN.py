@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from .. import functional as Fn
+from .. import functional_tc as FnTC
 from .._native import require_cuda
 
 __all__ = ["get_noise", "weights_init", "Generator", "Discriminator"]
@@ -41,7 +42,14 @@ class Generator(nn.Module):
         self.batch_norm1 = nn.BatchNorm2d(gen_dim * 4)
         self.batch_norm2 = nn.BatchNorm2d(gen_dim * 2)
         self.batch_norm3 = nn.BatchNorm2d(gen_dim)
+        self._ops = Fn
         self._initialize_weights()
+
+    def enable_tensor_cores(self, enabled=True):
+        """Route the four transposed convolutions (forward, data and weight gradients) to the tcgen05 GEMM kernel (bf16 operands, fp32
+        accumulation: functional_tc.py); BatchNorm / activations stay on the fp32 kernels.  Parameters and state-dict keys are untouched."""
+        self._ops = FnTC if enabled else Fn
+        return self
 
     def _initialize_weights(self):
         for m in self.modules():
@@ -59,10 +67,11 @@ class Generator(nn.Module):
 
     def forward(self, input):
         require_cuda(input)
-        x = self._bn_relu(self.batch_norm1, Fn.conv_transpose2d(input, self.conv1.weight, 1, 0))
-        x = self._bn_relu(self.batch_norm2, Fn.conv_transpose2d(x, self.conv2.weight, 2, 1))
-        x = self._bn_relu(self.batch_norm3, Fn.conv_transpose2d(x, self.conv3.weight, 2, 1))
-        return Fn.conv_transpose2d(x, self.conv4.weight, 1, 0, Fn.ACT_SIGMOID)
+        ops = self._ops
+        x = self._bn_relu(self.batch_norm1, ops.conv_transpose2d(input, self.conv1.weight, 1, 0))
+        x = self._bn_relu(self.batch_norm2, ops.conv_transpose2d(x, self.conv2.weight, 2, 1))
+        x = self._bn_relu(self.batch_norm3, ops.conv_transpose2d(x, self.conv3.weight, 2, 1))
+        return ops.conv_transpose2d(x, self.conv4.weight, 1, 0, Fn.ACT_SIGMOID)
 
 
 class Discriminator(nn.Module):
@@ -77,12 +86,20 @@ class Discriminator(nn.Module):
         self.pool = nn.MaxPool2d(kernel_size=2, stride=2, padding=0)
         self.fc1 = nn.Linear(32 * 32 * 54, 128)
         self.fc2 = nn.Linear(128, 1)
+        self._ops = Fn
+
+    def enable_tensor_cores(self, enabled=True):
+        """Route conv1 / conv2 / fc1 / fc2 (forward, data and weight gradients) to the tcgen05 GEMM kernel (bf16 operands, fp32 accumulation:
+        functional_tc.py); max-pooling and the loss stay on the fp32 kernels.  Parameters and state-dict keys are untouched."""
+        self._ops = FnTC if enabled else Fn
+        return self
 
     def forward(self, input):
         require_cuda(input)
         x = torch.unsqueeze(input, 1)
-        x = Fn.max_pool2(Fn.conv2d(x, self.conv1.weight, self.conv1.bias, 1, 1, Fn.ACT_RELU))
-        x = Fn.max_pool2(Fn.conv2d(x, self.conv2.weight, self.conv2.bias, 1, 1, Fn.ACT_RELU))
+        ops = self._ops
+        x = Fn.max_pool2(ops.conv2d(x, self.conv1.weight, self.conv1.bias, 1, 1, Fn.ACT_RELU))
+        x = Fn.max_pool2(ops.conv2d(x, self.conv2.weight, self.conv2.bias, 1, 1, Fn.ACT_RELU))
         x = x.view(-1, 32 * 32 * 54)
-        x = Fn.linear(x, self.fc1.weight, self.fc1.bias, Fn.ACT_RELU)
-        return Fn.linear(x, self.fc2.weight, self.fc2.bias, Fn.ACT_SIGMOID)
+        x = ops.linear(x, self.fc1.weight, self.fc1.bias, Fn.ACT_RELU)
+        return ops.linear(x, self.fc2.weight, self.fc2.bias, Fn.ACT_SIGMOID)

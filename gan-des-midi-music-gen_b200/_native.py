@@ -38,6 +38,13 @@ SIGNATURES = {
     "mmg_conv2d_fwd_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
     "mmg_conv2d_bwd_data_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
     "mmg_conv2d_bwd_weight_f32": (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
+    "mmg_gemm_tc": (_I, [_P, _I, _L, _P, _I, _L, _P, _L, _I, _I, _I, _I, _I, _I, _L, _I, _P, _I, _I, _P]),
+    "mmg_pack_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _P]),
+    "mmg_im2col_bf16": (_I, [_P, _P] + [_I] * 10 + [_P]),
+    "mmg_col2im_f32": (_I, [_P, _P] + [_I] * 8 + [_L, _I, _P]),
+    "mmg_transpose_f32": (_I, [_P, _P, _I, _I, _L, _P]),
+    "mmg_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
+    "mmg_bias_act_inplace_f32": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmg_maxpool2_fwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "mmg_maxpool2_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "mmg_disc_packed_weights_bytes": (_Z, []),

@@ -109,38 +109,44 @@ def _raster_leg(device, peaks, quick):
 
 def _gandes_leg(device):
     """BASELINE config 2: GAN-DES (GAN_DES/SIMNN.py:275-334) G+D training iteration on one synthetic song matrix (B = 30 spectrograms of
-    128 x 216), fp32 kernels of this library, fused BCE / multi-tensor Adam; DES + FluidSynth bridge excluded (the fake spectrograms are inputs)."""
+    128 x 216); headline = every contraction on the tcgen05 GEMM kernel (bf16 operands, fp32 accumulation), the fp32 SIMT kernels of this
+    library beside it; fused BCE / multi-tensor Adam; DES + FluidSynth bridge excluded (the fake spectrograms are inputs)."""
     import mmgan_oracle as mo               # cpu_baseline sample only
     from .GAN_DES import SIMNN
     from . import optim as fo
     B = 30
     gshapes, dshapes = mo.gandes_shapes()
     gsd, dsd = mo.synth_state(gshapes, seed=11), mo.synth_state(dshapes, seed=12)
-    gen, disc = SIMNN.Generator().to(device), SIMNN.Discriminator().to(device)
-    gen.load_state_dict(gsd); disc.load_state_dict(dsd)
-    crit = fo.BCEWithLogitsLoss()
-    gen_opt = fo.FusedAdam(gen.parameters(), lr=2e-5, betas=(0.5, 0.999))
-    disc_opt = fo.FusedAdam(disc.parameters(), lr=2e-5, betas=(0.5, 0.999))
     g = torch.Generator().manual_seed(3)
     noise_h, real_h, fake_h = torch.randn(B, 100, 1, 1, generator=g), torch.randn(B, 128, 216, generator=g), torch.randn(B, 128, 216, generator=g)
     noise, real, fake = noise_h.to(device), real_h.to(device), fake_h.to(device)
     t09, t01, t1 = torch.full((B,), 0.9, device=device), torch.full((B,), 0.1, device=device), torch.ones(B, device=device)
+    res = {}
+    for name, tcores in (("fp32_simt", False), ("tensor_cores", True)):
+        gen, disc = SIMNN.Generator().to(device).enable_tensor_cores(tcores), SIMNN.Discriminator().to(device).enable_tensor_cores(tcores)
+        gen.load_state_dict(gsd); disc.load_state_dict(dsd)
+        crit = fo.BCEWithLogitsLoss()
+        gen_opt = fo.FusedAdam(gen.parameters(), lr=2e-5, betas=(0.5, 0.999))
+        disc_opt = fo.FusedAdam(disc.parameters(), lr=2e-5, betas=(0.5, 0.999))
 
-    def it(i):
-        disc_opt.zero_grad()
-        l_real = crit(disc(real).reshape(-1), t09)
-        with torch.no_grad():
-            gen(noise)
-        l_fake = crit(disc(fake.detach()).reshape(-1), t01)
-        (l_fake + l_real).backward()
-        disc_opt.step()
-        gen_opt.zero_grad()
-        crit(disc(fake).squeeze(), t1).backward()
-        gen_opt.step()
+        def it(i):
+            disc_opt.zero_grad()
+            l_real = crit(disc(real).reshape(-1), t09)
+            with torch.no_grad():
+                gen(noise)
+            l_fake = crit(disc(fake.detach()).reshape(-1), t01)
+            (l_fake + l_real).backward()
+            disc_opt.step()
+            gen_opt.zero_grad()
+            crit(disc(fake).squeeze(), t1).backward()
+            gen_opt.step()
 
-    for _ in range(3):
-        it(0)
-    sec = _timed(it, 10, torch.cuda.synchronize) / 10
+        for _ in range(3):
+            it(0)
+        l0 = N.lib().mmg_launch_count()
+        sec = _timed(it, 10, torch.cuda.synchronize) / 10
+        res[name] = (sec, (N.lib().mmg_launch_count() - l0) // 10)
+        del gen, disc, gen_opt, disc_opt
     adam = {}
     mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
     t0 = time.perf_counter()
@@ -149,7 +155,19 @@ def _gandes_leg(device):
         mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
         n += 1
     cs = (time.perf_counter() - t0) / n
-    return {"spectrograms_per_sec": B / sec, "ms_per_step": sec * 1e3, "batch": B, "dtype": "f32",
+    sec, launches = res["tensor_cores"]
+    # algorithmic HBM traffic of one iteration, fp32 tensors (the reference's): 3 D passes read a (B,128,216) batch and touch the conv1 / conv2
+    # activations (written, read by the pool, re-read by the backward) + fc1's 28.3 MB weight (3 forward + 3 dgrad reads, 3 wgrad writes) + Adam
+    # on 7.1 M parameters (28 B each)
+    act = B * 4 * (128 * 216 + 16 * 129 * 217 + 16 * 64 * 108 + 32 * 64 * 108 + 32 * 32 * 54)
+    alg_bytes = 3 * (3 * act) + 9 * 128 * 55296 * 4 + 7.1e6 * 28
+    peaks = _peaks()
+    return {"spectrograms_per_sec": B / sec, "ms_per_step": sec * 1e3, "batch": B, "dtype": "bf16 operands, fp32 accumulation (tcgen05)",
+            "launches_per_step": launches,
+            "fp32_simt": {"ms_per_step": res["fp32_simt"][0] * 1e3, "spectrograms_per_sec": B / res["fp32_simt"][0], "launches_per_step": res["fp32_simt"][1]},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"],
+                         "algorithmic_bytes": alg_bytes, "traffic": None, "peak_src": peaks["src"],
+                         "note": "whole iteration (about 150 small launches at B = 30: launch latency, not bandwidth, bounds it)"},
             "cpu_baseline": {"value": B / cs, "unit": "spectrograms/s", "cores": os.cpu_count() or 1, "kind": "port",
                              "sample": f"{n} iterations of batch {B} through oracle/mmgan_oracle.gandes_iteration"}}
 

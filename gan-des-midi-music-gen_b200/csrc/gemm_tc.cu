@@ -1,0 +1,334 @@
+// Tensor-core GEMM for the GAN-DES contractions (GAN_DES/SIMNN.py:70-84 ConvTranspose stack, :123-142 conv2 / fc1 / fc2) and the data
+// movement around it.  One kernel:
+//
+//     C[m][n] (+)= sum_k A(m,k) * B(n,k)          fp32 accumulators in TMEM, bf16 (kind::f16) or fp32-as-tf32 (kind::tf32) operands
+//
+// with each operand either K-major (stored [rows = M or N][K], K contiguous) or MN-major (stored [K][M or N], bf16 only), so that every
+// layer's forward / data-gradient / weight-gradient contraction reads its tensors where they lie:
+//
+//   fc1 forward      y^T[o][b]   = W[o][f] x[b][f]             A = W  (K-major, M = 128 outputs), B = x (K-major), split-K over f = 55 296
+//   fc1 dgrad        dx^T[f][b]  = W[o][f] dz[b][o]            A = W  (MN-major, M = f), B = dz (K-major, K = o)
+//   fc1 wgrad        dW[o][f]    = dz[b][o] x[b][f]            A = dz (MN-major), B = x (MN-major), K = batch
+//   conv forward     y[p][oc]    = col[p][k] W[oc][k]          A = im2col(x), B = W
+//   conv dgrad       dx[p][ci]   = col(dy)[p][k'] Wf[ci][k']   (a forward convolution with the flipped, transposed weights)
+//   conv wgrad       dW^T[k][oc] = col[p][k] dyT[oc][p]        A = col (MN-major), B = dy as [oc][b*p] (K-major)
+//   convT forward    col[p][co*taps] = x[p][ci] W[ci][co*taps] A = x (NHWC, K-major), B = W (MN-major), then col2im
+//
+// TMA (cp.async.bulk.tensor, 128-byte swizzle, zero fill outside the tensor = all M / N / K tails) feeds a 4-stage shared-memory ring;
+// warp 0 = producer, warp 1 = tcgen05.mma issuer + TMEM owner, warps 2-5 = epilogue (bias, activation, transposed / NCHW store or fp32
+// atomics for split-K).  The problems are small and HBM- or latency-bound (B = 30): the kernel is built for coverage of all layouts,
+// not for the last percent of the tensor pipe.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int GM_STAGES = 4;
+constexpr int GM_THREADS = 192;
+constexpr int GM_A_BYTES = 128 * 128;      // 128 rows x one 128-byte K chunk (K-major) = two 64 x 64 MN-major boxes
+
+struct GemmArgs {
+    int M, N, BN;                          // BN = tile width (32 / 64 / 128 / 256)
+    int a_mn, b_mn, tf32;
+    int chunks, chunks_per_split;          // 128-byte K chunks: 64 bf16 or 32 tf32 elements
+    float* C;
+    long long ldc;
+    int trans_out;                         // element (m, n) -> C[(m / inner) * N * inner + n * inner + m % inner]   (NCHW: inner = pixels per image)
+    long long inner;
+    int atomic;                            // fp32 atomicAdd (split-K); bias / act are then left to the caller
+    const float* bias;
+    int bias_on_m;
+    int act;
+};
+
+__device__ __forceinline__ void mma_tf32_ss_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full;
+    __shared__ uint32_t tmem_s;
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * a.BN;
+    const int c0 = blockIdx.z * a.chunks_per_split;
+    const int nck = min(a.chunks, c0 + a.chunks_per_split) - c0;
+    if (nck <= 0) return;                                                     // (split-K tail with nothing to add)
+    const int b_bytes = a.BN * 128, stage_bytes = GM_A_BYTES + b_bytes;
+    const int kelems = a.tf32 ? 32 : 64;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GM_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(&acc_full, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&map_a);
+        tc::tma_prefetch_desc(&map_b);
+    }
+    const uint32_t tm_cols = a.BN < 32 ? 32u : (uint32_t)a.BN;
+    if (warp == 1) { tc::tmem_alloc(&tmem_s, tm_cols); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nck; ++i) {
+                const int stage = i % GM_STAGES;
+                const uint32_t phase = (uint32_t)(i / GM_STAGES) & 1u;
+                tc::mbar_wait(&empty[stage], phase ^ 1u);
+                tc::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                unsigned char* sa = smem + stage * stage_bytes;
+                unsigned char* sb = sa + GM_A_BYTES;
+                const int kc = (c0 + i) * kelems;
+                if (!a.a_mn) tc::tma_load_2d(sa, &map_a, &full[stage], kc, m0);                   // box (K chunk, 128 rows)
+                else {                                                                              // two boxes (64 m, 64 k rows)
+                    tc::tma_load_2d(sa, &map_a, &full[stage], m0, kc);
+                    tc::tma_load_2d(sa + 8192, &map_a, &full[stage], m0 + 64, kc);
+                }
+                if (!a.b_mn) tc::tma_load_2d(sb, &map_b, &full[stage], kc, n0);                   // box (K chunk, BN rows)
+                else
+                    for (int j = 0; j < a.BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &map_b, &full[stage], n0 + 64 * j, kc);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t leader = tc::elect_one() ? 1u : 0u;
+        constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);                       // K-major: 8-row groups 1024 B apart
+        constexpr uint64_t MN128 = tc::smem_desc_base(8192, 1024, tc::SW_128B);                    // MN-major: 64-element MN atoms 8192 B apart, 8-row K groups 1024 B apart
+        const uint32_t idesc = a.tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | (8u << 24))
+                                      : tc::idesc_bf16(128, (uint32_t)a.BN, (uint32_t)a.a_mn, (uint32_t)a.b_mn);
+        const uint64_t da = a.a_mn ? MN128 : KM128, db = a.b_mn ? MN128 : KM128;
+        const uint32_t sa_step = a.a_mn ? 2048u : 32u, sb_step = a.b_mn ? 2048u : 32u;            // one MMA = 16 bf16 / 8 tf32 K elements = 32 B, or 16 K rows
+        for (int i = 0; i < nck; ++i) {
+            const int stage = i % GM_STAGES;
+            const uint32_t phase = (uint32_t)(i / GM_STAGES) & 1u;
+            tc::mbar_wait(&full[stage], phase);
+            tc::tc_fence_after();
+            const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes), sb = sa + GM_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (a.tf32) mma_tf32_ss_pred(tmem, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (i | k) != 0, leader);
+                else tc::mma_f16_ss_pred(tmem, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (i | k) != 0, leader);
+            }
+            tc::mma_commit_pred(&empty[stage], leader);
+        }
+        tc::mma_commit_pred(&acc_full, leader);
+    } else {
+        const int q = warp & 3;                                                                     // TMEM lane quadrant of this warp
+        const int m = m0 + q * 32 + lane;
+        tc::mbar_wait(&acc_full, 0);
+        tc::tc_fence_after();
+        const long long mo = a.trans_out ? (long long)(m / a.inner) * (long long)a.N * a.inner + (m % a.inner) : (long long)m * a.ldc;
+        const float bm = (a.bias && a.bias_on_m && m < a.M) ? a.bias[m] : 0.f;
+        for (int c = 0; c < a.BN; c += 32) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            tc::tmem_ld_wait();
+            if (m < a.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < a.N) {
+                        float v = __uint_as_float(r[j]);
+                        float* dst = a.C + (a.trans_out ? mo + (long long)n * a.inner : mo + n);
+                        if (a.atomic) atomicAdd(dst, v);
+                        else {
+                            v += a.bias ? (a.bias_on_m ? bm : a.bias[n]) : 0.f;
+                            *dst = mmg_act(v, a.act);
+                        }
+                    }
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, tm_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- data movement
+// fp32 -> bf16 with a permutation of a (d0, d1, d2) tensor: dst[i_a * a_stride + i_b * pitch + i_c] where (a, b, c) = perm of (0, 1, 2);
+// columns [n_c, pitch) are written as zeros (TMA needs 16-byte row pitches; K tails must read as zeros).
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int d0, int d1, int d2, int pa, int pb, int pc, long long pitch,
+                                 long long a_stride) {
+    const int dims[3] = {d0, d1, d2};
+    const long long sstr[3] = {(long long)d1 * d2, d2, 1};
+    const long long na = dims[pa], nb = dims[pb], nc = dims[pc];
+    const long long total = na * nb * pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i % pitch, ab = i / pitch, b = ab % nb, aa = ab / nb;
+        float v = 0.f;
+        if (c < nc) v = src[aa * sstr[pa] + b * sstr[pb] + c * sstr[pc]];
+        dst[aa * a_stride + b * pitch + c] = __float2bfloat16(v);
+    }
+}
+
+// im2col of an NCHW fp32 tensor into bf16 rows [b * OH * OW][Ci * kh * kw (+ optional ones column, + zero padding up to pitch)]
+__global__ void im2col_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int Ci, int H, int W, int kh, int kw, int stride, int pad,
+                                   int OH, int OW, int pitch, int ones_col) {
+    const int K = Ci * kh * kw;
+    const long long total = (long long)B * OH * OW * pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % pitch);
+        const long long p = i / pitch;
+        float v = (ones_col && k == K) ? 1.f : 0.f;                    // column K = 1: the bias rides the forward GEMM, its gradient the weight-gradient GEMM
+        if (k < K) {
+            const int kx = k % kw, ky = (k / kw) % kh, c = k / (kw * kh);
+            const int ox = (int)(p % OW), oy = (int)((p / OW) % OH), b = (int)(p / ((long long)OW * OH));
+            const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * Ci + c) * H + iy) * W + ix];
+        }
+        col[i] = __float2bfloat16(v);
+    }
+}
+
+// col2im (gather form, no atomics) of the transposed convolution: col fp32 [b * Hin * Win][Co * kh * kw (pitch ldc)] -> y NCHW [b][Co][Hout][Wout],
+// y[b][co][oy][ox] = act( sum over (ky, kx) with (oy + pad - ky) % stride == 0 ... of col[b, iy, ix][co, ky, kx] )
+__global__ void col2im_f32_kernel(const float* __restrict__ col, float* __restrict__ y, int B, int Co, int Hin, int Win, int kh, int kw, int stride, int pad,
+                                  int Hout, int Wout, long long ldc, int act) {
+    const long long total = (long long)B * Co * Hout * Wout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wout), oy = (int)((i / Wout) % Hout), co = (int)((i / ((long long)Wout * Hout)) % Co), b = (int)(i / ((long long)Wout * Hout * Co));
+        float s = 0.f;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int ty = oy + pad - ky;
+            if (ty < 0 || ty % stride) continue;
+            const int iy = ty / stride;
+            if (iy >= Hin) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int tx = ox + pad - kx;
+                if (tx < 0 || tx % stride) continue;
+                const int ix = tx / stride;
+                if (ix >= Win) continue;
+                s += col[(((long long)b * Hin + iy) * Win + ix) * ldc + (co * kh + ky) * kw + kx];
+            }
+        }
+        y[i] = mmg_act(s, act);
+    }
+}
+
+// fp32 [rows][cols] -> fp32 transposed copy [cols][rows] of small matrices (weight-gradient layouts)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, long long lds) {
+    const long long total = (long long)rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / rows), r = (int)(i % rows);
+        dst[i] = src[(long long)r * lds + c];
+    }
+}
+
+// column sums of an fp32 [rows][cols] matrix (bias gradients): one warp per column group, fixed order
+__global__ void colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += src[(long long)r * cols + c];
+    dst[c] = s;
+}
+
+// y[i][j] = act(y[i][j] + bias[j]) after a split-K accumulation
+__global__ void gemm_bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int N, int act) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        y[i] = mmg_act(y[i] + (bias ? bias[i % N] : 0.f), act);
+}
+
+}  // namespace
+
+// A: K-major [M][K] (lda = row pitch in elements) or MN-major [K][M]; B likewise with N.  dtype 0 = bf16, 1 = fp32 read as tf32 (K-major only).
+extern "C" int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, float* C, long long ldc, int M, int N, int K, int dtype,
+                           int split_k, int trans_out, long long inner, int atomic, const float* bias, int bias_on_m, int act, void* stream) {
+    MMG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, MMG_EINVAL, "gemm_tc: null pointer or empty problem");
+    MMG_REQUIRE(dtype == 0 || (dtype == 1 && !a_mn && !b_mn), MMG_EUNSUPPORTED, "gemm_tc: tf32 operands must be K-major");
+    const int esz = dtype ? 4 : 2, kelems = 128 / esz;
+    MMG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && (lda * esz) % 16 == 0 && (ldb * esz) % 16 == 0, MMG_EINVAL,
+                "gemm_tc: operands need 16-byte aligned bases and row pitches");
+    MMG_REQUIRE(!trans_out || inner > 0, MMG_EINVAL, "gemm_tc: trans_out needs inner > 0");
+    MMG_REQUIRE(!(atomic && (bias || act)), MMG_EINVAL, "gemm_tc: bias / activation cannot be fused into a split-K accumulation");
+    GemmArgs a{};
+    a.M = M; a.N = N;
+    a.BN = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    if (b_mn && a.BN < 64) a.BN = 64;
+    a.a_mn = a_mn; a.b_mn = b_mn; a.tf32 = dtype;
+    a.chunks = (K + kelems - 1) / kelems;
+    if (split_k < 1) split_k = 1;
+    if (split_k > a.chunks) split_k = a.chunks;
+    MMG_REQUIRE(split_k == 1 || atomic, MMG_EINVAL, "gemm_tc: split_k > 1 needs atomic accumulation into a zeroed C");
+    a.chunks_per_split = (a.chunks + split_k - 1) / split_k;
+    a.C = C; a.ldc = ldc; a.trans_out = trans_out; a.inner = inner; a.atomic = atomic; a.bias = bias; a.bias_on_m = bias_on_m; a.act = act;
+    CUtensorMap map_a, map_b;
+    const CUtensorMapDataType dt = dtype ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    int r;
+    if (!a_mn) r = tc::make_map_2d(&map_a, dt, esz, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * esz, (uint32_t)kelems, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    else r = tc::make_map_2d(&map_a, dt, esz, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * esz, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    MMG_REQUIRE(r == 0, MMG_EINVAL, "gemm_tc: cuTensorMapEncodeTiled(A) failed (%d)", r);
+    if (!b_mn) r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * esz, (uint32_t)kelems, (uint32_t)a.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    else r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * esz, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    MMG_REQUIRE(r == 0, MMG_EINVAL, "gemm_tc: cuTensorMapEncodeTiled(B) failed (%d)", r);
+    const int smem = 1024 + GM_STAGES * (GM_A_BYTES + a.BN * 128);
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + GM_STAGES * (GM_A_BYTES + 256 * 128)));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + a.BN - 1) / a.BN), (unsigned)split_k);
+    gemm_tc_kernel<<<grid, GM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// perm = (pa, pb, pc): destination index order over the source dimensions (d0, d1, d2); dst[i_a * a_stride + i_b * pitch + i_c] bf16, columns
+// [n_pc, pitch) zero; a_stride = 0 means n_pb * pitch (dense).
+extern "C" int mmg_pack_bf16(const float* src, void* dst, int d0, int d1, int d2, int pa, int pb, int pc, long long pitch, long long a_stride, void* stream) {
+    MMG_REQUIRE(src && dst && d0 > 0 && d1 > 0 && d2 > 0, MMG_EINVAL, "pack_bf16: null pointer or empty tensor");
+    MMG_REQUIRE(pa >= 0 && pa < 3 && pb >= 0 && pb < 3 && pc >= 0 && pc < 3 && pa != pb && pa != pc && pb != pc, MMG_EINVAL, "pack_bf16: perm must be a permutation of (0,1,2)");
+    const int dims[3] = {d0, d1, d2};
+    MMG_REQUIRE(pitch >= dims[pc], MMG_EINVAL, "pack_bf16: pitch smaller than the row");
+    if (a_stride <= 0) a_stride = (long long)dims[pb] * pitch;
+    MMG_REQUIRE(a_stride >= (long long)dims[pb] * pitch, MMG_EINVAL, "pack_bf16: a_stride smaller than one block");
+    const long long total = (long long)dims[pa] * dims[pb] * pitch;
+    pack_bf16_kernel<<<mmg_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, d0, d1, d2, pa, pb, pc, pitch, a_stride);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_im2col_bf16(const float* x, void* col, int B, int Ci, int H, int W, int kh, int kw, int stride, int pad, int pitch, int ones_col, void* stream) {
+    MMG_REQUIRE(x && col && B > 0 && Ci > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, MMG_EINVAL, "im2col_bf16: bad argument");
+    const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
+    MMG_REQUIRE(OH > 0 && OW > 0 && pitch >= Ci * kh * kw + (ones_col ? 1 : 0) && pitch % 8 == 0, MMG_EINVAL,
+                "im2col_bf16: pitch must cover Ci*kh*kw (+1 with a ones column) and be a multiple of 8");
+    im2col_bf16_kernel<<<mmg_grid((long long)B * OH * OW * pitch, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw, stride, pad, OH, OW, pitch,
+                                                                                                         ones_col);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_col2im_f32(const float* col, float* y, int B, int Co, int Hin, int Win, int kh, int kw, int stride, int pad, long long ldc, int act, void* stream) {
+    MMG_REQUIRE(col && y && B > 0 && Co > 0 && Hin > 0 && Win > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, MMG_EINVAL, "col2im_f32: bad argument");
+    const int Hout = (Hin - 1) * stride - 2 * pad + kh, Wout = (Win - 1) * stride - 2 * pad + kw;
+    MMG_REQUIRE(Hout > 0 && Wout > 0 && ldc >= (long long)Co * kh * kw, MMG_EINVAL, "col2im_f32: bad geometry");
+    col2im_f32_kernel<<<mmg_grid((long long)B * Co * Hout * Wout, 256), 256, 0, (cudaStream_t)stream>>>(col, y, B, Co, Hin, Win, kh, kw, stride, pad, Hout, Wout, ldc, act);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_transpose_f32(const float* src, float* dst, int rows, int cols, long long lds, void* stream) {
+    MMG_REQUIRE(src && dst && rows > 0 && cols > 0 && lds >= cols, MMG_EINVAL, "transpose_f32: bad argument");
+    transpose_f32_kernel<<<mmg_grid((long long)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols, lds);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_colsum_f32(const float* src, float* dst, int rows, int cols, void* stream) {
+    MMG_REQUIRE(src && dst && rows > 0 && cols > 0, MMG_EINVAL, "colsum_f32: bad argument");
+    colsum_f32_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, dst, rows, cols);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int cols, int act, void* stream) {
+    MMG_REQUIRE(y && rows > 0 && cols > 0, MMG_EINVAL, "bias_act_inplace_f32: bad argument");
+    gemm_bias_act_kernel<<<mmg_grid(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, rows * cols, cols, act);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}

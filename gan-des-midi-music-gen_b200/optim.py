@@ -9,6 +9,7 @@ whose ``grad is None`` are skipped and get no state, exactly like ``torch.optim.
 import torch
 
 from . import functional as Fn
+from . import functional_tc as FnTC
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -36,6 +37,7 @@ class FusedAdam(torch.optim.Optimizer):
             for step, ps in by_step.items():
                 Fn.adam_step([p.data for p in ps], [p.grad.contiguous() for p in ps], [self.state[p]["exp_avg"] for p in ps],
                              [self.state[p]["exp_avg_sq"] for p in ps], step, group["lr"], b1, b2, group["eps"])
+        FnTC.invalidate_weight_cache()           # the kernel wrote the parameters through raw pointers: packed bf16 copies are stale
         return loss
 
 

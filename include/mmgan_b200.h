@@ -98,6 +98,25 @@ int mmg_conv2d_bwd_weight_f32(const float* x, const float* dy, float* dw, float*
 int mmg_maxpool2_fwd_f32(const float* x, float* y, uint8_t* idx, int64_t NC, int H, int W, void* stream);
 int mmg_maxpool2_bwd_f32(const float* dy, const uint8_t* idx, float* dx, int64_t NC, int H, int W, void* stream);
 
+/* ---- GAN-DES contractions on the tensor cores (GAN_DES/SIMNN.py:70-84 ConvTranspose stack, :123-142 conv / fc layers) ----
+ * mmg_gemm_tc: C[m][n] (+)= sum_k A(m,k) B(n,k), fp32 accumulation in TMEM (tcgen05.mma fed by TMA).  A is K-major ([M][K], lda =
+ * row pitch in elements) or MN-major ([K][M]); B likewise.  dtype 0 = bf16, 1 = fp32 read as tf32 (K-major operands only).  Bases and row
+ * pitches must be 16-byte aligned; M / N / K tails are zero-filled by TMA.  trans_out: element (m, n) is stored at
+ * C[(m / inner) * N * inner + n * inner + m % inner] (inner = pixels per image gives NCHW, inner = M a plain transpose), else at
+ * C[m * ldc + n].  split_k > 1 needs atomic = 1 and a zeroed C (bias / act then through mmg_bias_act_inplace_f32). */
+int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, float* C, long long ldc, int M, int N, int K, int dtype,
+                int split_k, int trans_out, long long inner, int atomic, const float* bias, int bias_on_m, int act, void* stream);
+/* fp32 (d0,d1,d2) -> bf16 dst[i_pa * a_stride + i_pb * pitch + i_pc] with the dimensions permuted to (pa, pb, pc); columns [n_pc, pitch)
+ * are zeros; a_stride = 0 means n_pb * pitch */
+int mmg_pack_bf16(const float* src, void* dst, int d0, int d1, int d2, int pa, int pb, int pc, long long pitch, long long a_stride, void* stream);
+/* NCHW fp32 -> bf16 rows [B*OH*OW][pitch]: columns (c, ky, kx), column Ci*kh*kw = 1 when ones_col (bias / bias gradient ride the GEMMs) */
+int mmg_im2col_bf16(const float* x, void* col, int B, int Ci, int H, int W, int kh, int kw, int stride, int pad, int pitch, int ones_col, void* stream);
+/* transposed convolution, second half: col fp32 [B*Hin*Win][ldc >= Co*kh*kw] -> act(y) NCHW [B][Co][Hout][Wout], gather form (no atomics) */
+int mmg_col2im_f32(const float* col, float* y, int B, int Co, int Hin, int Win, int kh, int kw, int stride, int pad, long long ldc, int act, void* stream);
+int mmg_transpose_f32(const float* src, float* dst, int rows, int cols, long long lds, void* stream);
+int mmg_colsum_f32(const float* src, float* dst, int rows, int cols, void* stream);                 /* dst[c] = sum_r src[r][c] */
+int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int cols, int act, void* stream);
+
 /* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
  * Activations live in padded space-to-depth layouts (see csrc/disc_tc.cu): XS (B*1690, 8) is the input, P1 (B*429, 64)
  * the conv1 activations, A2 / DZ2 (B*429, 32) the conv2 activations / their gradient, DZ1C (B*1690, 16) the conv1
