@@ -31,6 +31,7 @@ struct GemmArgs {
     int M, N, BN;                          // BN = tile width (32 / 64 / 128 / 256)
     int a_mn, b_mn, tf32;
     int chunks, chunks_per_split;          // 128-byte K chunks: 64 bf16 or 32 tf32 elements
+    int stages;                            // depth of the shared-memory ring: min(GM_STAGES, chunks per CTA) -- short-K problems then fit several CTAs per SM
     float* C;
     long long ldc;
     int trans_out;                         // element (m, n) -> C[(m / inner) * N * inner + n * inner + m % inner]   (NCHW: inner = pixels per image)
@@ -41,12 +42,17 @@ struct GemmArgs {
     int act;
 };
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 __device__ __forceinline__ void mma_tf32_ss_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
+__global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full;
     __shared__ uint32_t tmem_s;
@@ -76,8 +82,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < nck; ++i) {
-                const int stage = i % GM_STAGES;
-                const uint32_t phase = (uint32_t)(i / GM_STAGES) & 1u;
+                const int stage = i % a.stages;
+                const uint32_t phase = (uint32_t)(i / a.stages) & 1u;
                 tc::mbar_wait(&empty[stage], phase ^ 1u);
                 tc::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                 unsigned char* sa = smem + stage * stage_bytes;
@@ -102,8 +108,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         const uint64_t da = a.a_mn ? MN128 : KM128, db = a.b_mn ? MN128 : KM128;
         const uint32_t sa_step = a.a_mn ? 2048u : 32u, sb_step = a.b_mn ? 2048u : 32u;            // one MMA = 16 bf16 / 8 tf32 K elements = 32 B, or 16 K rows
         for (int i = 0; i < nck; ++i) {
-            const int stage = i % GM_STAGES;
-            const uint32_t phase = (uint32_t)(i / GM_STAGES) & 1u;
+            const int stage = i % a.stages;
+            const uint32_t phase = (uint32_t)(i / a.stages) & 1u;
             tc::mbar_wait(&full[stage], phase);
             tc::tc_fence_after();
             const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes), sb = sa + GM_A_BYTES;
@@ -126,7 +132,20 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             uint32_t r[32];
             tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             tc::tmem_ld_wait();
-            if (m < a.M) {
+            if (m < a.M && !a.trans_out && !a.atomic && n0 + c + 32 <= a.N && (a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0 && ((n0 + c) & 3) == 0) {
+                // plain row-major store of 32 consecutive columns: eight 16-byte stores
+                float4* dst = reinterpret_cast<float4*>(a.C + mo + n0 + c);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = __uint_as_float(r[j + e]) + (a.bias ? (a.bias_on_m ? bm : a.bias[n0 + c + j + e]) : 0.f);
+                        v[e] = mmg_act(v[e], a.act);
+                    }
+                    dst[j >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            } else if (m < a.M) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c + j;
@@ -150,37 +169,70 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
 
 // ---------------------------------------------------------------------------------------------------------------- data movement
 // fp32 -> bf16 with a permutation of a (d0, d1, d2) tensor: dst[i_a * a_stride + i_b * pitch + i_c] where (a, b, c) = perm of (0, 1, 2);
-// columns [n_c, pitch) are written as zeros (TMA needs 16-byte row pitches; K tails must read as zeros).
+// columns [n_c, pitch) are written as zeros (TMA needs 16-byte row pitches; K tails must read as zeros).  One thread = 8 consecutive
+// columns of one row (one 16-byte store when the row is aligned), 32-bit index arithmetic.
 __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int d0, int d1, int d2, int pa, int pb, int pc, long long pitch,
                                  long long a_stride) {
-    const int dims[3] = {d0, d1, d2};
-    const long long sstr[3] = {(long long)d1 * d2, d2, 1};
-    const long long na = dims[pa], nb = dims[pb], nc = dims[pc];
-    const long long total = na * nb * pitch;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long c = i % pitch, ab = i / pitch, b = ab % nb, aa = ab / nb;
-        float v = 0.f;
-        if (c < nc) v = src[aa * sstr[pa] + b * sstr[pb] + c * sstr[pc]];
-        dst[aa * a_stride + b * pitch + c] = __float2bfloat16(v);
+    auto dim = [&](int i) { return i == 0 ? d0 : i == 1 ? d1 : d2; };
+    auto str = [&](int i) { return i == 0 ? (long long)d1 * d2 : i == 1 ? (long long)d2 : 1LL; };
+    const unsigned nb = (unsigned)dim(pb), nc = (unsigned)dim(pc);
+    const unsigned groups = (unsigned)((pitch + 7) >> 3);
+    const unsigned total = (unsigned)dim(pa) * nb * groups;
+    const long long sa = str(pa), sb = str(pb), sc = str(pc);
+    const bool vec = (pitch & 7) == 0 && (a_stride & 7) == 0 && ((uintptr_t)dst & 15) == 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned gq = i % groups, row = i / groups, bb = row % nb, aa = row / nb;
+        const unsigned c0 = gq * 8;
+        const float* sp = src + aa * sa + bb * sb + (long long)c0 * sc;
+        __nv_bfloat16* dp = dst + aa * a_stride + bb * pitch + c0;
+        float v[8];
+        if (sc == 1 && c0 + 8 <= nc && ((uintptr_t)sp & 15) == 0) {
+            const float4 q0 = reinterpret_cast<const float4*>(sp)[0], q1 = reinterpret_cast<const float4*>(sp)[1];
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = c0 + e < nc ? sp[e * sc] : 0.f;
+        }
+        if (vec) {
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(dp) = o;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (c0 + e < (unsigned)pitch) dp[e] = __float2bfloat16(v[e]);
+        }
     }
 }
 
-// im2col of an NCHW fp32 tensor into bf16 rows [b * OH * OW][Ci * kh * kw (+ optional ones column, + zero padding up to pitch)]
+// im2col of an NCHW fp32 tensor into bf16 rows [b * OH * OW][Ci * kh * kw (+ optional ones column, + zero padding up to pitch)].
+// One thread = 8 consecutive columns of one row (one 16-byte store); the (c, ky, kx) decode advances incrementally.
 __global__ void im2col_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int Ci, int H, int W, int kh, int kw, int stride, int pad,
                                    int OH, int OW, int pitch, int ones_col) {
     const int K = Ci * kh * kw;
-    const long long total = (long long)B * OH * OW * pitch;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % pitch);
-        const long long p = i / pitch;
-        float v = (ones_col && k == K) ? 1.f : 0.f;                    // column K = 1: the bias rides the forward GEMM, its gradient the weight-gradient GEMM
-        if (k < K) {
-            const int kx = k % kw, ky = (k / kw) % kh, c = k / (kw * kh);
-            const int ox = (int)(p % OW), oy = (int)((p / OW) % OH), b = (int)(p / ((long long)OW * OH));
-            const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * Ci + c) * H + iy) * W + ix];
+    const unsigned groups = (unsigned)pitch >> 3;
+    const unsigned total = (unsigned)B * OH * OW * groups;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned gq = i % groups, p = i / groups;
+        const int ox = (int)(p % (unsigned)OW), t = (int)(p / (unsigned)OW), oy = t % OH, b = t / OH;
+        int k = (int)gq * 8;
+        int kx = k % kw, t2 = k / kw, ky = t2 % kh, c = t2 / kh;
+        const float* xb = x + (long long)b * Ci * H * W;
+        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e, ++k) {
+            float val = (ones_col && k == K) ? 1.f : 0.f;                  // column K = 1: the bias rides the forward GEMM, its gradient the weight-gradient GEMM
+            if (k < K) {
+                const int iy = iy0 + ky, ix = ix0 + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = xb[((long long)c * H + iy) * W + ix];
+            }
+            v[e] = val;
+            if (++kx == kw) { kx = 0; if (++ky == kh) { ky = 0; ++c; } }
         }
-        col[i] = __float2bfloat16(v);
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(col + (long long)p * pitch + gq * 8) = o;
     }
 }
 
@@ -265,7 +317,8 @@ extern "C" int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B
     if (!b_mn) r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * esz, (uint32_t)kelems, (uint32_t)a.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     else r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * esz, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     MMG_REQUIRE(r == 0, MMG_EINVAL, "gemm_tc: cuTensorMapEncodeTiled(B) failed (%d)", r);
-    const int smem = 1024 + GM_STAGES * (GM_A_BYTES + a.BN * 128);
+    a.stages = a.chunks_per_split < GM_STAGES ? a.chunks_per_split : GM_STAGES;
+    const int smem = 1024 + a.stages * (GM_A_BYTES + a.BN * 128);
     static bool attr_done = false;
     if (!attr_done) {
         MMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + GM_STAGES * (GM_A_BYTES + 256 * 128)));
@@ -286,8 +339,9 @@ extern "C" int mmg_pack_bf16(const float* src, void* dst, int d0, int d1, int d2
     MMG_REQUIRE(pitch >= dims[pc], MMG_EINVAL, "pack_bf16: pitch smaller than the row");
     if (a_stride <= 0) a_stride = (long long)dims[pb] * pitch;
     MMG_REQUIRE(a_stride >= (long long)dims[pb] * pitch, MMG_EINVAL, "pack_bf16: a_stride smaller than one block");
-    const long long total = (long long)dims[pa] * dims[pb] * pitch;
-    pack_bf16_kernel<<<mmg_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, d0, d1, d2, pa, pb, pc, pitch, a_stride);
+    const long long total = (long long)dims[pa] * dims[pb] * ((pitch + 7) / 8);
+    MMG_REQUIRE(total < (1LL << 31), MMG_EUNSUPPORTED, "pack_bf16: tensor too large for 32-bit indexing");
+    pack_bf16_kernel<<<mmg_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, d0, d1, d2, pa, pb, pc, pitch, a_stride);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
@@ -297,7 +351,8 @@ extern "C" int mmg_im2col_bf16(const float* x, void* col, int B, int Ci, int H, 
     const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
     MMG_REQUIRE(OH > 0 && OW > 0 && pitch >= Ci * kh * kw + (ones_col ? 1 : 0) && pitch % 8 == 0, MMG_EINVAL,
                 "im2col_bf16: pitch must cover Ci*kh*kw (+1 with a ones column) and be a multiple of 8");
-    im2col_bf16_kernel<<<mmg_grid((long long)B * OH * OW * pitch, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw, stride, pad, OH, OW, pitch,
+    MMG_REQUIRE((long long)B * OH * OW * (pitch / 8) < (1LL << 31), MMG_EUNSUPPORTED, "im2col_bf16: tensor too large for 32-bit indexing");
+    im2col_bf16_kernel<<<mmg_grid((long long)B * OH * OW * (pitch / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw, stride, pad, OH, OW, pitch,
                                                                                                          ones_col);
     MMG_LAUNCH_CHECK();
     return MMG_OK;

@@ -21,6 +21,7 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        updated = False
         for group in self.param_groups:
             by_step = {}
             for p in group["params"]:
@@ -35,9 +36,11 @@ class FusedAdam(torch.optim.Optimizer):
                 by_step.setdefault(st["step"], []).append(p)
             b1, b2 = group["betas"]
             for step, ps in by_step.items():
+                updated = True
                 Fn.adam_step([p.data for p in ps], [p.grad.contiguous() for p in ps], [self.state[p]["exp_avg"] for p in ps],
                              [self.state[p]["exp_avg_sq"] for p in ps], step, group["lr"], b1, b2, group["eps"])
-        FnTC.invalidate_weight_cache()           # the kernel wrote the parameters through raw pointers: packed bf16 copies are stale
+        if updated:
+            FnTC.invalidate_weight_cache()       # the kernel wrote the parameters through raw pointers: packed bf16 copies are stale
         return loss
 
 
