@@ -29,6 +29,10 @@ live in ONE flat fp32 buffer (84 KB) that is all-reduced once per optimiser step
 generator forwards (the 1/world factor is folded into the Adam kernel); the G-step D grads are not reduced (the reference discards them).
 ``sync_bn=True`` (bf16 path): the generators' train-mode BatchNorm uses GLOBAL-batch statistics (fp64 column sums all-reduced between the
 layer kernels, gen_tc.GenTC), reproducing the reference's single-process batch; default False = per-replica statistics (torch-DDP semantics).
+
+Losses under data parallelism: ``step`` / ``d_step`` / ``g_step`` return the mean over THIS RANK's shard (the gradients are the global mean);
+the reference's global-batch loss is the average of the per-rank values: ``dist.all_reduce(loss); loss /= world`` (tests/test_gpu_dp_nccl.py).
+They are left per-rank so that no collective sits between an iteration and the next one's launch.
 """
 import ctypes
 
