@@ -393,4 +393,16 @@ def run(args):
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
+        # teardown: CUDA graphs that hold NCCL kernels (captured SyncBN all-reduces) go before the communicator; the JSON line is out, so a
+        # stalled communicator teardown must not keep the job alive
+        import gc
+        import threading
+        trainer._graphs.clear()
+        trainer._seg_graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()

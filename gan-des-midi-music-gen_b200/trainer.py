@@ -54,7 +54,7 @@ def shard_batch(t, rank, world):
 
 class MMGANTrainer:
     def __init__(self, mmgan, lr=0.01, betas=(0.9, 0.999), eps=1e-8, precision="fp32", max_batch=None, process_group=None, use_graph=None,
-                 inner_rng="reference", sync_bn=False, one_kernel_pass=True):
+                 inner_rng="reference", sync_bn=False, one_kernel_pass=True, capture_collectives=None):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.m = mmgan
@@ -76,6 +76,9 @@ class MMGANTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.on_d_grads = None
         self.sync_bn = bool(sync_bn) and self.world > 1
+        # SyncBN's statistics all-reduces sit between the generator layer kernels: with NCCL they are captured into the CUDA graphs like any
+        # kernel (one replay per segment); gloo collectives are host calls, so those generator forwards stay eager
+        self.capture_collectives = (self.world > 1 and dist.get_backend(process_group) == "nccl") if capture_collectives is None else bool(capture_collectives)
         if self.sync_bn and precision != "bf16":
             raise ValueError("sync_bn is implemented on the bf16 tensor-core generator path (precision='bf16')")
         self.tc = None
@@ -248,7 +251,8 @@ class MMGANTrainer:
     def _capture(self, fn, *args):
         g = torch.cuda.CUDAGraph()
         l0 = N.lib().mmg_launch_count()
-        with torch.cuda.graph(g):
+        # thread-local capture mode: other threads (NCCL's watchdog polling events, the bench's clock sampler) may call CUDA meanwhile
+        with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
             fn(*args)
         self.graph_launches += N.lib().mmg_launch_count() - l0
         return g
@@ -267,7 +271,7 @@ class MMGANTrainer:
             torch.cuda.synchronize()
             l0 = N.lib().mmg_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 fn()
             self._seg_graphs[key] = (g, N.lib().mmg_launch_count() - l0)
             g = self._seg_graphs[key]
@@ -282,7 +286,7 @@ class MMGANTrainer:
         B = noise1.shape[0]
         if inner is None:
             inner = self._draw_inner(B, "d")
-        sync = self.sync_bn                        # collectives between the layer kernels: not captured
+        sync = self.sync_bn and not self.capture_collectives      # host-side collectives between the layer kernels: not capturable
         if sync or self.tc is None:
             self._generators(noise1, noise2, beats, inner, out)
         else:
@@ -336,8 +340,8 @@ class MMGANTrainer:
                     self.graph_launches = 0
                     if self.world == 1:
                         graphs = (self._capture(lambda: (self._seg_d(*a_d), self._seg_g_gen(*a_g), self._seg_g(*a_g))),)
-                    else:       # sharded: graphs around the asynchronous D-gradient all-reduce; SyncBN generators (collectives between kernels) stay eager
-                        eager_gen = self.sync_bn
+                    else:       # sharded: graphs around the asynchronous D-gradient all-reduce; SyncBN generators are captured with their NCCL all-reduces (eager under gloo)
+                        eager_gen = self.sync_bn and not self.capture_collectives
                         graphs = (None if eager_gen else self._capture(self._seg_d_gen, *a_d), self._capture(self._seg_d_disc, *a_d),
                                   None if eager_gen else self._capture(self._seg_g_gen, *a_g), self._capture(self._seg_g, *a_g))
                     self._graphs[key] = graphs       # capture does not execute: fall through to the replay below

@@ -77,6 +77,8 @@ def _worker(rank, world, port, q, backend, ngpu):
                 dist.all_reduce(ls)
                 ls /= world
                 assert any(len(g) == 4 for g in tr._graphs.values()), "sharded iteration was not captured"
+                if backend == "nccl":                            # SyncBN generators replay from graphs too (NCCL all-reduces captured)
+                    assert all(x is not None for g in tr._graphs.values() for x in g), "SyncBN generator segments were not captured under NCCL"
             res[mode] = (ls.cpu(), [p.detach().clone() for p in m.discriminator.parameters()], m.generator1.gen[3][1].running_var.clone(), tr.g2_out.clone())
         out["loss"] = (res["dp"][0] - res["one"][0]).abs().max().item() / max(1.0, res["one"][0].abs().max().item())
         out["loss0"] = (res["dp"][0][0] - res["one"][0][0]).abs().max().item() / max(1.0, res["one"][0][0].abs().max().item())
