@@ -98,8 +98,12 @@ class Discriminator(nn.Module):
         require_cuda(input)
         x = torch.unsqueeze(input, 1)
         ops = self._ops
-        x = Fn.max_pool2(ops.conv2d(x, self.conv1.weight, self.conv1.bias, 1, 1, Fn.ACT_RELU))
-        x = Fn.max_pool2(ops.conv2d(x, self.conv2.weight, self.conv2.bias, 1, 1, Fn.ACT_RELU))
+        if ops is FnTC:       # conv + ReLU + pool as one autograd node: its backward undoes pooling and ReLU in one kernel
+            x = FnTC.conv2d_relu_pool(x, self.conv1.weight, self.conv1.bias, 1)
+            x = FnTC.conv2d_relu_pool(x, self.conv2.weight, self.conv2.bias, 1)
+        else:
+            x = Fn.max_pool2(Fn.conv2d(x, self.conv1.weight, self.conv1.bias, 1, 1, Fn.ACT_RELU))
+            x = Fn.max_pool2(Fn.conv2d(x, self.conv2.weight, self.conv2.bias, 1, 1, Fn.ACT_RELU))
         x = x.view(-1, 32 * 32 * 54)
         x = ops.linear(x, self.fc1.weight, self.fc1.bias, Fn.ACT_RELU)
         return ops.linear(x, self.fc2.weight, self.fc2.bias, Fn.ACT_SIGMOID)

@@ -155,6 +155,22 @@ def _gandes_leg(device):
         sec = _timed(it, 10, torch.cuda.synchronize) / 10
         res[name] = (sec, (N.lib().mmg_launch_count() - l0) // 10)
         del gen, disc, gen_opt, disc_opt
+    # the same iteration through GANDESTrainer: generate / d_step / g_step replayed from CUDA graphs (tensor-core path)
+    from .gandes_trainer import GANDESTrainer
+    gen, disc = SIMNN.Generator().to(device).enable_tensor_cores(), SIMNN.Discriminator().to(device).enable_tensor_cores()
+    gen.load_state_dict(gsd); disc.load_state_dict(dsd)
+    gtr = GANDESTrainer(gen, disc, lr=2e-5, betas=(0.5, 0.999))
+
+    def it_graph(i):
+        gtr.generate(noise)
+        gtr.d_step(real, fake)
+        gtr.g_step(fake)
+
+    for _ in range(4):
+        it_graph(0)
+    r0 = gtr.replayed_launches
+    sec_graph = _timed(it_graph, 10, torch.cuda.synchronize) / 10
+    res["tensor_cores_graph"] = (sec_graph, (gtr.replayed_launches - r0) // 10)
     adam = {}
     mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
     t0 = time.perf_counter()
@@ -163,7 +179,7 @@ def _gandes_leg(device):
         mo.gandes_iteration(gsd, dsd, adam, noise_h, real_h, fake_h)
         n += 1
     cs = (time.perf_counter() - t0) / n
-    sec, launches = res["tensor_cores"]
+    sec, launches = res["tensor_cores_graph"]
     # algorithmic HBM traffic of one iteration, fp32 tensors (the reference's): 3 D passes read a (B,128,216) batch and touch the conv1 / conv2
     # activations (written, read by the pool, re-read by the backward) + fc1's 28.3 MB weight (3 forward + 3 dgrad reads, 3 wgrad writes) + Adam
     # on 7.1 M parameters (28 B each)
@@ -171,7 +187,9 @@ def _gandes_leg(device):
     alg_bytes = 3 * (3 * act) + 9 * 128 * 55296 * 4 + 7.1e6 * 28
     peaks = _peaks()
     return {"spectrograms_per_sec": B / sec, "ms_per_step": sec * 1e3, "batch": B, "dtype": "bf16 operands, fp32 accumulation (tcgen05)",
-            "launches_per_step": launches,
+            "launches_per_step": launches, "api": "gandes_trainer.GANDESTrainer: generate / d_step / g_step, each replayed from its CUDA graph",
+            "module_loop": {"ms_per_step": res["tensor_cores"][0] * 1e3, "spectrograms_per_sec": B / res["tensor_cores"][0], "launches_per_step": res["tensor_cores"][1],
+                            "api": "the reference's loop written with the drop-in modules (enable_tensor_cores), FusedAdam and the fused BCE, eager launches"},
             "fp32_simt": {"ms_per_step": res["fp32_simt"][0] * 1e3, "spectrograms_per_sec": B / res["fp32_simt"][0], "launches_per_step": res["fp32_simt"][1]},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes": alg_bytes, "traffic": None, "peak_src": peaks["src"],

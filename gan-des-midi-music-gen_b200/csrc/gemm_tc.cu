@@ -270,6 +270,39 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __res
     }
 }
 
+// Backward of maxpool2(relu(z)) in one pass (SIMNN.py:138-139): dz[b][c][iy][ix] = dyp[b][c][iy/2][ix/2] where (iy, ix) is the window's argmax and
+// the pooled value is > 0 (the ReLU mask of the element that won), else 0; rows / columns beyond the pooled area (odd H / W) are zero.
+// Outputs (either may be null): dz fp32 NCHW, and dzt bf16 [C][B*H*W] with row pitch Pp = the K-major B operand of the weight-gradient GEMM.
+// One thread = 4 consecutive ix of one image row.
+__global__ void pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_t* __restrict__ idx, const float* __restrict__ yp, float* __restrict__ dz,
+                                     __nv_bfloat16* __restrict__ dzt, int B, int C, int H, int W, int OH, int OW, long long Pp) {
+    const unsigned WQ = (unsigned)(W + 3) >> 2;
+    const unsigned total = (unsigned)B * C * H * WQ;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned wq = i % WQ, t = i / WQ, iy = t % (unsigned)H, bc = t / (unsigned)H, c = bc % (unsigned)C, b = bc / (unsigned)C;
+        const unsigned oy = iy >> 1;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned ix = wq * 4 + e, ox = ix >> 1;
+            v[e] = 0.f;
+            if (ix < (unsigned)W && oy < (unsigned)OH && ox < (unsigned)OW) {
+                const size_t o = ((size_t)bc * OH + oy) * OW + ox;
+                if (idx[o] == ((iy & 1) * 2 + (ix & 1)) && yp[o] > 0.f) v[e] = dyp[o];
+            }
+        }
+        const size_t row = ((size_t)bc * H + iy) * W + wq * 4;
+        const size_t trow = (size_t)c * Pp + ((size_t)b * H + iy) * W + wq * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (wq * 4 + e < (unsigned)W) {
+                if (dz) dz[row + e] = v[e];
+                if (dzt) dzt[trow + e] = __float2bfloat16(v[e]);
+            }
+        }
+    }
+}
+
 // column sums of an fp32 [rows][cols] matrix (bias gradients): one warp per column group, fixed order
 __global__ void colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +417,17 @@ extern "C" int mmg_colsum_f32(const float* src, float* dst, int rows, int cols, 
 extern "C" int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int cols, int act, void* stream) {
     MMG_REQUIRE(y && rows > 0 && cols > 0, MMG_EINVAL, "bias_act_inplace_f32: bad argument");
     gemm_bias_act_kernel<<<mmg_grid(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, rows * cols, cols, act);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+extern "C" int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream) {
+    const int OH = H / 2, OW = W / 2;
+    MMG_REQUIRE(dyp && idx && yp && (dz || dzt) && B > 0 && C > 0 && OH > 0 && OW > 0, MMG_EINVAL, "pool_relu_bwd: bad argument");
+    MMG_REQUIRE(!dzt || Pp >= (long long)B * H * W, MMG_EINVAL, "pool_relu_bwd: pitch of the transposed output smaller than B*H*W");
+    const long long total = (long long)B * C * H * ((W + 3) / 4);
+    MMG_REQUIRE(total < (1LL << 31), MMG_EUNSUPPORTED, "pool_relu_bwd: tensor too large for 32-bit indexing");
+    pool_relu_bwd_kernel<<<mmg_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dyp, idx, yp, dz, (__nv_bfloat16*)dzt, B, C, H, W, OH, OW, Pp);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

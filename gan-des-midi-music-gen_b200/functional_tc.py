@@ -9,7 +9,7 @@ added inside the forward GEMM and its gradient is the extra row of the weight-gr
 import torch
 
 from . import _native as N
-from .functional import ACT_NONE, _f32c
+from .functional import ACT_NONE, ACT_RELU, _f32c
 
 _BF = torch.bfloat16
 _epoch = 0
@@ -175,6 +175,72 @@ class Conv2dActTC(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
+class Conv2dReluPoolTC(torch.autograd.Function):
+    """maxpool2(relu(conv2d(x, w, b, 1, padding))) -- one block of the GAN-DES discriminator (SIMNN.py:138-139).  Forward: im2col + GEMM (bias,
+    ReLU, NCHW store in the epilogue) + the pooling kernel; only the pooled output and the argmax codes are kept.  Backward: ONE kernel
+    undoes pooling and ReLU and writes the gradient both as fp32 NCHW (for the data-gradient GEMM) and as bf16 [oc][b*p] rows (the K-major B
+    operand of the weight-gradient GEMM) -- the pre-pool activation is never read again."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pad):
+        x, w = _f32c(x), _f32c(w)
+        b = _f32c(b) if b is not None else None
+        Nn, Ci, H, W = x.shape
+        Co, _, kh, kw = w.shape
+        OH, OW = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+        K = Ci * kh * kw
+        Kp = _r8(K + 1)
+
+        def make_w():
+            ext = torch.zeros(Co, Kp, device=w.device)
+            ext[:, :K] = w.reshape(Co, K)
+            if b is not None:
+                ext[:, K] = b
+            return ext.to(_BF)
+        wp = _cached(w, ("conv", None if b is None else (b.data_ptr(), b._version)), make_w)
+        P = Nn * OH * OW
+        col = torch.empty(P, Kp, device=x.device, dtype=_BF)
+        N.call("mmg_im2col_bf16", N.ptr(x), N.ptr(col), Nn, Ci, H, W, kh, kw, 1, pad, Kp, 1, N.stream())
+        y = torch.empty(Nn, Co, OH, OW, device=x.device)
+        _gemm(col, 0, Kp, wp, 0, Kp, y, Co, P, Co, K + 1, trans_out=True, inner=OH * OW, act=ACT_RELU)
+        yp = torch.empty(Nn, Co, OH // 2, OW // 2, device=x.device)
+        idx = torch.empty(Nn, Co, OH // 2, OW // 2, device=x.device, dtype=torch.uint8)
+        N.call("mmg_maxpool2_fwd_f32", N.ptr(y), N.ptr(yp), N.ptr(idx), Nn * Co, OH, OW, N.stream())
+        ctx.save_for_backward(col, w, yp, idx)
+        ctx.cfg = (Nn, Ci, H, W, Co, kh, kw, pad, OH, OW, K, Kp)
+        ctx.has_b = b is not None
+        return yp
+
+    @staticmethod
+    def backward(ctx, dyp):
+        col, w, yp, idx = ctx.saved_tensors
+        Nn, Ci, H, W, Co, kh, kw, pad, OH, OW, K, Kp = ctx.cfg
+        dyp = _f32c(dyp)
+        P = Nn * OH * OW
+        Pp = _r8(P)
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2])
+        dz = torch.empty(Nn, Co, OH, OW, device=dyp.device) if need_dx else None
+        dzt = torch.empty(Co, Pp, device=dyp.device, dtype=_BF) if need_dw else None
+        N.call("mmg_pool_relu_bwd", N.ptr(dyp), N.ptr(idx), N.ptr(yp), N.ptr(dz), N.ptr(dzt), Nn, Co, OH, OW, Pp, N.stream())
+        dx = dw = db = None
+        if need_dx:
+            K2 = Co * kh * kw
+            K2p = _r8(K2)
+            wf = _cached(w, "convT", lambda: w.flip(2, 3).permute(1, 0, 2, 3).reshape(Ci, K2).contiguous())
+            wfp = _cached(w, "convTp", lambda: _pack(wf, (1, Ci, K2), (0, 1, 2), K2p))
+            col2 = torch.empty(Nn * H * W, K2p, device=dz.device, dtype=_BF)
+            N.call("mmg_im2col_bf16", N.ptr(dz), N.ptr(col2), Nn, Co, OH, OW, kh, kw, 1, kh - 1 - pad, K2p, 0, N.stream())
+            dx = torch.empty(Nn, Ci, H, W, device=dz.device)
+            _gemm(col2, 0, K2p, wfp, 0, K2p, dx, Ci, Nn * H * W, Ci, K2, trans_out=True, inner=H * W)
+        if need_dw:
+            buf = torch.zeros(Co, K + 1, device=dyp.device)
+            _gemm(col, 1, Kp, dzt, 0, Pp, buf, K + 1, K + 1, Co, P, split_k=_split(P, (K + 128) // 128), trans_out=True, inner=K + 1, atomic=True)
+            dw = buf[:, :K].reshape(w.shape).contiguous()
+            db = buf[:, K].contiguous() if ctx.has_b else None
+        return dx, dw, db, None
+
+
 class ConvTranspose2dActTC(torch.autograd.Function):
     """y = act(conv_transpose2d(x, w, None, stride, padding)), w (Cin, Cout, kh, kw), bias-free (SIMNN.py:70-84): GEMM over the input
     channels into per-input-pixel tap columns, then col2im.  Backward: dx = conv2d(dz, w) and dW = x^T col(dz), both GEMMs."""
@@ -226,3 +292,7 @@ def conv2d(x, w, b=None, stride=1, padding=0, act=ACT_NONE):
 
 def conv_transpose2d(x, w, stride=1, padding=0, act=ACT_NONE):
     return ConvTranspose2dActTC.apply(x, w, stride, padding, act)
+
+
+def conv2d_relu_pool(x, w, b=None, padding=0):
+    return Conv2dReluPoolTC.apply(x, w, b, padding)

@@ -1,0 +1,112 @@
+"""The GAN-DES loop body (/root/reference/GAN_DES/SIMNN.py:275-334) as replayable segments around the host bridge.
+
+The reference loop is ``real -> disc`` / ``gen(noise) -> matrix_to_wav (host DES + FluidSynth) -> disc(fake)`` / backward / ``disc_opt.step()``,
+then ``disc(fake)`` against ones / backward / ``gen_opt.step()`` (a no-op: the fake spectrograms come back from the host, no generator parameter
+has a gradient).  ``GANDESTrainer`` keeps that order and cuts it where the host takes over:
+
+    fake_matrices = tr.generate(noise)            # SIMNN.py:291-294   (eval of the generator under no_grad, as the loop detaches it at once)
+    fake = matrix_to_wav(fake_matrices ...)       # host, unchanged
+    d_loss = tr.d_step(real, fake)                # SIMNN.py:279-316
+    g_loss = tr.g_step(fake)                      # SIMNN.py:321-331
+
+Each segment runs eagerly the first time it sees a set of input buffers, is captured into a CUDA graph the second time (forward, autograd
+backward and the Adam update: ~60 launches) and replayed afterwards.  Adam's step count and hyper-parameters live in device memory
+(``mmg_adam_multi_tensor_dev_f32``) so the replayed update is the right one.  Works with the fp32 kernels and with ``enable_tensor_cores()``.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+from . import functional_tc as FnTC
+from .optim import BCEWithLogitsLoss
+
+
+class GANDESTrainer:
+    def __init__(self, gen, disc, lr=2e-5, betas=(0.5, 0.999), eps=1e-8, use_graph=True):
+        self.gen, self.disc = gen, disc
+        self.crit = BCEWithLogitsLoss()
+        self.d_params = list(disc.parameters())
+        dev = self.d_params[0].device
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=dev)       # updates applied so far (device side: graph replays advance it)
+        self.exp_avg = [torch.zeros_like(p) for p in self.d_params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.d_params]
+        self.use_graph = bool(use_graph)
+        self._graphs, self._seen, self._labels = {}, {}, {}
+        self.replayed_launches = 0
+
+    # ------------------------------------------------------------------ pieces
+    def _label(self, B, v):
+        t = self._labels.get((B, v))
+        if t is None:
+            t = self._labels[(B, v)] = torch.full((B,), v, device=self.hyper.device)
+        return t
+
+    def _adam(self):
+        ps = self.d_params
+        ts = [p.data for p in ps] + [p.grad for p in ps] + self.exp_avg + self.exp_avg_sq
+        ptrs = (ctypes.c_void_p * (4 * len(ps)))(*[N.ptr(t) for t in ts])
+        sizes = (ctypes.c_int64 * len(ps))(*[p.numel() for p in ps])
+        N.call("mmg_adam_multi_tensor_dev_f32", len(ps), ptrs, sizes, N.ptr(self.hyper), N.ptr(self.adam_step), 1.0, N.stream())
+        FnTC.invalidate_weight_cache()
+
+    def _d_body(self, real, fake):
+        B = real.shape[0]
+        for p in self.d_params:
+            p.grad = None
+        l_real = self.crit(self.disc(real).reshape(-1), self._label(B, 0.9))
+        l_fake = self.crit(self.disc(fake.detach()).reshape(-1), self._label(B, 0.1))
+        loss = l_fake + l_real
+        loss.backward()
+        for p in self.d_params:
+            if p.grad is None or not p.grad.is_contiguous():
+                raise RuntimeError("GANDESTrainer: every discriminator parameter needs a contiguous gradient")
+        self._adam()
+        return loss.detach()
+
+    def _g_body(self, fake):
+        B = fake.shape[0]
+        for p in self.d_params:            # gen_opt.zero_grad() leaves the discriminator's gradients; they are recomputed here and never applied
+            p.grad = None
+        loss = self.crit(self.disc(fake).squeeze(), self._label(B, 1.0))
+        loss.backward()
+        return loss.detach()
+
+    def _segment(self, name, fn, tensors):
+        """eager on first sight of these buffers, captured on the second call, replayed afterwards"""
+        if not self.use_graph:
+            return fn()
+        key = (name,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors)
+        g = self._graphs.get(key)
+        if g is None:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] == 1:
+                return fn()
+            torch.cuda.synchronize()
+            FnTC.invalidate_weight_cache()                 # every packed weight must be (re)built INSIDE the graph
+            l0 = N.lib().mmg_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn()
+            FnTC.invalidate_weight_cache()                 # the cache now points into the graph's private pool: eager code must not trust it
+            g = self._graphs[key] = (graph, out, N.lib().mmg_launch_count() - l0)
+        g[0].replay()
+        self.replayed_launches += g[2]
+        return g[1]
+
+    # ------------------------------------------------------------------ public segments
+    def generate(self, noise):
+        """SIMNN.py:291-297: the generator's forward for the host bridge (train-mode BatchNorm, running statistics advance); no autograd tape."""
+        def body():
+            with torch.no_grad():
+                return self.gen(noise)
+        return self._segment("gen", body, (noise,))
+
+    def d_step(self, real, fake):
+        """SIMNN.py:279-316.  Returns the discriminator loss (device scalar; under graph replay the same tensor every call)."""
+        return self._segment("d", lambda: self._d_body(real, fake), (real, fake))
+
+    def g_step(self, fake):
+        """SIMNN.py:321-331."""
+        return self._segment("g", lambda: self._g_body(fake), (fake,))

@@ -116,6 +116,9 @@ int mmg_col2im_f32(const float* col, float* y, int B, int Co, int Hin, int Win, 
 int mmg_transpose_f32(const float* src, float* dst, int rows, int cols, long long lds, void* stream);
 int mmg_colsum_f32(const float* src, float* dst, int rows, int cols, void* stream);                 /* dst[c] = sum_r src[r][c] */
 int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int cols, int act, void* stream);
+/* backward of MaxPool2d(2,2)(ReLU(z)) in one pass (SIMNN.py:138-139): dyp / idx / yp are the pooled gradient, the argmax codes of
+ * mmg_maxpool2_fwd_f32 and the pooled output; writes dz fp32 NCHW (B,C,H,W) and / or dzt bf16 [C][Pp >= B*H*W] (either may be NULL) */
+int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream);
 
 /* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
  * Activations live in padded space-to-depth layouts (see csrc/disc_tc.cu): XS (B*1690, 8) is the input, P1 (B*429, 64)

@@ -141,6 +141,30 @@ def test_conv2d_tc_vs_torch(B, Ci, H, W, Co, k, pad, act):
             assert _rel(a, c) < 1.5e-2, (n, _rel(a, c))
 
 
+@pytest.mark.parametrize("B,Ci,H,W,Co,k,pad", [(2, 1, 128, 216, 16, 2, 1), (3, 16, 64, 108, 32, 3, 1), (2, 3, 9, 7, 5, 3, 1)])
+def test_conv2d_relu_pool_tc_vs_torch(B, Ci, H, W, Co, k, pad):
+    """conv + ReLU + maxpool as one node (forward through the GEMM, backward through the fused pool / ReLU kernel), odd pre-pool sizes included"""
+    from gan_des_midi_music_gen_b200 import functional_tc as T
+    g = torch.Generator(device="cpu").manual_seed(Ci + H + W)
+    x = torch.randn(B, Ci, H, W, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(Co, generator=g).to(DEV).requires_grad_(True)
+    want = F.max_pool2d(torch.relu(F.conv2d(rb(x), rb(w), rb(b), 1, pad)), 2)
+    gy = torch.randn(want.shape, generator=g).to(DEV)
+    gw = torch.autograd.grad(want, (x, w, b), gy)
+    got = T.conv2d_relu_pool(x, w, b, pad)
+    assert got.shape == want.shape
+    gg = torch.autograd.grad(got, (x, w, b), gy)
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()
+    for a, c, n in zip(gg, gw, ("dx", "dw", "db")):
+        assert _rel(a, c) < 1e-2, (n, _rel(a, c))
+    # without a data gradient (the discriminator's first block) only the bf16 transposed gradient is produced
+    got2 = T.conv2d_relu_pool(x.detach(), w, b, pad)
+    g2 = torch.autograd.grad(got2, (w, b), gy)
+    for a, c, n in zip(g2, gw[1:], ("dw", "db")):
+        assert _rel(a, c) < 1e-2, (n, _rel(a, c))
+
+
 @pytest.mark.parametrize("B,Ci,Hin,Co,k,s,pad,act", [(30, 100, 1, 128, 4, 1, 0, 0), (30, 128, 4, 64, 4, 2, 1, 0), (3, 64, 8, 32, 4, 2, 1, 0), (3, 32, 16, 1, 5, 1, 0, 3)])
 def test_conv_transpose2d_tc_vs_torch(B, Ci, Hin, Co, k, s, pad, act):
     from gan_des_midi_music_gen_b200 import functional_tc as T
@@ -235,3 +259,53 @@ def test_gandes_loop_body_on_tensor_cores(golden_dir):
     rep = {k: _rel(p.grad, eg[k]) for k, p in gen.named_parameters()}
     print("GAN-DES generator gradient rel-L2, kernels vs bf16 restatement:", {k: f"{v:.1e}" for k, v in rep.items()})
     assert max(rep.values()) < 1.5e-2, rep
+
+
+@pytest.mark.parametrize("tcores", [False, True])
+def test_gandes_trainer_graph_replay_matches_module_loop(tcores):
+    """GANDESTrainer (segments of SIMNN.py:275-334, captured into CUDA graphs on the second call) against the same loop written with the
+    modules, FusedAdam and the fused BCE: identical kernels, so losses agree to fp32 atomics noise and the weights follow the same trajectory."""
+    from gan_des_midi_music_gen_b200.GAN_DES import SIMNN
+    from gan_des_midi_music_gen_b200 import optim as fo
+    from gan_des_midi_music_gen_b200.gandes_trainer import GANDESTrainer
+    B = 4
+    gshapes, dshapes = mo.gandes_shapes()
+    g = torch.Generator().manual_seed(21)
+    noise, real, fake = (torch.randn(B, 100, 1, 1, generator=g).to(DEV), torch.randn(B, 128, 216, generator=g).to(DEV),
+                         torch.randn(B, 128, 216, generator=g).to(DEV))
+    out = {}
+    for mode in ("loop", "trainer"):
+        gen, disc = SIMNN.Generator().to(DEV).enable_tensor_cores(tcores), SIMNN.Discriminator().to(DEV).enable_tensor_cores(tcores)
+        gen.load_state_dict(mo.synth_state(gshapes, seed=11)); disc.load_state_dict(mo.synth_state(dshapes, seed=12))
+        losses = []
+        if mode == "loop":
+            crit = fo.BCEWithLogitsLoss()
+            disc_opt = fo.FusedAdam(disc.parameters(), lr=2e-4, betas=(0.5, 0.999))
+            for it in range(5):
+                disc_opt.zero_grad()
+                l_real = crit(disc(real).reshape(-1), torch.full((B,), 0.9, device=DEV))
+                with torch.no_grad():
+                    gm = gen(noise)
+                l_fake = crit(disc(fake.detach()).reshape(-1), torch.full((B,), 0.1, device=DEV))
+                dl = l_fake + l_real
+                dl.backward()
+                disc_opt.step()
+                gl = crit(disc(fake).squeeze(), torch.ones(B, device=DEV))
+                losses.append((dl.item(), gl.item()))
+        else:
+            tr = GANDESTrainer(gen, disc, lr=2e-4, betas=(0.5, 0.999))
+            for it in range(5):
+                gm = tr.generate(noise)
+                dl = tr.d_step(real, fake)
+                gl = tr.g_step(fake)
+                losses.append((dl.item(), gl.item()))
+            assert {k[0] for k in tr._graphs} == {"gen", "d", "g"} and tr.replayed_launches > 0
+            assert int(tr.adam_step) == 5
+        out[mode] = (losses, [p.detach().clone() for p in disc.parameters()], gm.clone(), int(gen.batch_norm1.num_batches_tracked))
+    (l0, p0, g0, n0), (l1, p1, g1, n1) = out["loop"], out["trainer"]
+    assert n0 == n1 == 5 and (g0 - g1).abs().max().item() < 1e-5
+    for a, b in zip(l0, l1):
+        assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0]) and abs(a[1] - b[1]) <= 1e-3 * abs(a[1]), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert (a - b).abs().max().item() <= 5 * 2e-4 * 0.5 + 1e-7           # Adam: a sign flip of a ~0 gradient element moves a weight by <= lr per step
+        assert _rel(a, b) < 2e-2
