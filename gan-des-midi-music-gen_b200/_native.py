@@ -45,6 +45,7 @@ SIGNATURES = {
     "mmg_transpose_f32": (_I, [_P, _P, _I, _I, _L, _P]),
     "mmg_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
     "mmg_bias_act_inplace_f32": (_I, [_P, _P, _L, _I, _I, _P]),
+    "mmg_conv_small_relu_pool_f32": (_I, [_P, _P, _P, _P, _P] + [_I] * 8 + [_P]),
     "mmg_pool_relu_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _P]),
     "mmg_maxpool2_fwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "mmg_maxpool2_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),

@@ -236,6 +236,44 @@ __global__ void im2col_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* _
     }
 }
 
+// The same rows with the lanes of a warp on CONSECUTIVE PIXELS of one column group: every load instruction reads 32 consecutive floats of an
+// image row (the version above gathers 4-byte elements from Ci * kh different rows per instruction), and a thread stores G = 16 columns =
+// one full 32-byte sector (G = 8 when the pitch is not a multiple of 16).
+template <int G>
+__global__ void im2col_bf16_px_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int Ci, int H, int W, int kh, int kw, int stride, int pad,
+                                      int OH, int OW, int pitch, int ones_col) {
+    const int K = Ci * kh * kw;
+    const unsigned P = (unsigned)B * OH * OW, groups = (unsigned)pitch / G;
+    const unsigned total = P * groups;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned p = i % P, gq = i / P;
+        const int ox = (int)(p % (unsigned)OW), t = (int)(p / (unsigned)OW), oy = t % OH, b = t / OH;
+        int k = (int)gq * G;
+        int kx = k % kw, t2 = k / kw, ky = t2 % kh, c = t2 / kh;
+        const float* xb = x + (long long)b * Ci * H * W;
+        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+        float v[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e, ++k) {
+            float val = (ones_col && k == K) ? 1.f : 0.f;
+            if (k < K) {
+                const int iy = iy0 + ky, ix = ix0 + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = xb[((long long)c * H + iy) * W + ix];
+            }
+            v[e] = val;
+            if (++kx == kw) { kx = 0; if (++ky == kh) { ky = 0; ++c; } }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(col + (long long)p * pitch + gq * G);
+#pragma unroll
+        for (int q = 0; q < G / 8; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            dst[q] = o;
+        }
+    }
+}
+
 // col2im (gather form, no atomics) of the transposed convolution: col fp32 [b * Hin * Win][Co * kh * kw (pitch ldc)] -> y NCHW [b][Co][Hout][Wout],
 // y[b][co][oy][ox] = act( sum over (ky, kx) with (oy + pad - ky) % stride == 0 ... of col[b, iy, ix][co, ky, kx] )
 __global__ void col2im_f32_kernel(const float* __restrict__ col, float* __restrict__ y, int B, int Co, int Hin, int Win, int kh, int kw, int stride, int pad,
@@ -299,6 +337,55 @@ __global__ void pool_relu_bwd_kernel(const float* __restrict__ dyp, const uint8_
                 if (dz) dz[row + e] = v[e];
                 if (dzt) dzt[trow + e] = __float2bfloat16(v[e]);
             }
+        }
+    }
+}
+
+// maxpool2(relu(conv2d(x, w, b, stride 1, pad))) for a tiny stencil (SIMNN.py:123,138: Conv2d(1, 16, kernel 2) -- K = 4 is a stencil, not a
+// GEMM): one thread = one pooled pixel, all output channels; the pre-pool activation never exists in memory.  Same tie-breaking and NaN
+// rule as maxpool2_fwd_kernel (first maximum in (0,0), (0,1), (1,0), (1,1) order; NaN wins).
+template <int CI, int KH, int KW>
+__global__ void conv_small_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ yp,
+                                            uint8_t* __restrict__ idx, int B, int H, int W, int Co, int pad, int OH2, int OW2) {
+    constexpr int K = CI * KH * KW;
+    __shared__ float ws[32 * K + 32];
+    for (int i = threadIdx.x; i < Co * K; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < Co; i += blockDim.x) ws[32 * K + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const unsigned total = (unsigned)B * OH2 * OW2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ox2 = (int)(i % (unsigned)OW2), t = (int)(i / (unsigned)OW2), oy2 = t % OH2, b = t / OH2;
+        float patch[CI][KH + 1][KW + 1];
+#pragma unroll
+        for (int c = 0; c < CI; ++c)
+#pragma unroll
+            for (int r = 0; r <= KH; ++r)
+#pragma unroll
+                for (int q = 0; q <= KW; ++q) {
+                    const int iy = 2 * oy2 - pad + r, ix = 2 * ox2 - pad + q;
+                    patch[c][r][q] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((size_t)b * CI + c) * H + iy) * W + ix] : 0.f;
+                }
+        for (int co = 0; co < Co; ++co) {
+            float v[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                float acc = ws[32 * K + co];
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+#pragma unroll
+                    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < KW; ++kx) acc = fmaf(ws[co * K + (c * KH + ky) * KW + kx], patch[c][(d >> 1) + ky][(d & 1) + kx], acc);
+                v[d] = acc > 0.f ? acc : (acc != acc ? acc : 0.f);         // ReLU (NaN propagates, as torch.relu does)
+            }
+            float best = v[0];
+            int bi = 0;
+            if (v[1] > best || v[1] != v[1]) { best = v[1]; bi = 1; }
+            if (v[2] > best || v[2] != v[2]) { best = v[2]; bi = 2; }
+            if (v[3] > best || v[3] != v[3]) { best = v[3]; bi = 3; }
+            const size_t o = (((size_t)b * Co + co) * OH2 + oy2) * OW2 + ox2;
+            yp[o] = best;
+            idx[o] = (uint8_t)bi;
         }
     }
 }
@@ -385,6 +472,16 @@ extern "C" int mmg_im2col_bf16(const float* x, void* col, int B, int Ci, int H, 
     MMG_REQUIRE(OH > 0 && OW > 0 && pitch >= Ci * kh * kw + (ones_col ? 1 : 0) && pitch % 8 == 0, MMG_EINVAL,
                 "im2col_bf16: pitch must cover Ci*kh*kw (+1 with a ones column) and be a multiple of 8");
     MMG_REQUIRE((long long)B * OH * OW * (pitch / 8) < (1LL << 31), MMG_EUNSUPPORTED, "im2col_bf16: tensor too large for 32-bit indexing");
+    if (OW >= 32) {                                         // wide images: lanes on consecutive pixels (coalesced row reads, full-sector stores)
+        if (pitch % 16 == 0)
+            im2col_bf16_px_kernel<16><<<mmg_grid((long long)B * OH * OW * (pitch / 16), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw,
+                                                                                                                                    stride, pad, OH, OW, pitch, ones_col);
+        else
+            im2col_bf16_px_kernel<8><<<mmg_grid((long long)B * OH * OW * (pitch / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw,
+                                                                                                                                  stride, pad, OH, OW, pitch, ones_col);
+        MMG_LAUNCH_CHECK();
+        return MMG_OK;
+    }
     im2col_bf16_kernel<<<mmg_grid((long long)B * OH * OW * (pitch / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, Ci, H, W, kh, kw, stride, pad, OH, OW, pitch,
                                                                                                          ones_col);
     MMG_LAUNCH_CHECK();
@@ -428,6 +525,19 @@ extern "C" int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const flo
     const long long total = (long long)B * C * H * ((W + 3) / 4);
     MMG_REQUIRE(total < (1LL << 31), MMG_EUNSUPPORTED, "pool_relu_bwd: tensor too large for 32-bit indexing");
     pool_relu_bwd_kernel<<<mmg_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dyp, idx, yp, dz, (__nv_bfloat16*)dzt, B, C, H, W, OH, OW, Pp);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+/* stride-1 convolution with a tiny stencil + bias + ReLU + MaxPool2d(2,2) in one kernel; supported stencil: Ci = 1, 2 x 2 (the GAN-DES
+ * discriminator's first block), Co <= 32.  yp / idx: (B, Co, OH/2, OW/2) with OH = H + 2 pad - 1. */
+extern "C" int mmg_conv_small_relu_pool_f32(const float* x, const float* w, const float* bias, float* yp, uint8_t* idx, int B, int Ci, int H, int W, int Co, int kh, int kw,
+                                            int pad, void* stream) {
+    MMG_REQUIRE(x && w && yp && idx && B > 0 && H > 0 && W > 0 && Co > 0 && pad >= 0, MMG_EINVAL, "conv_small_relu_pool: bad argument");
+    MMG_REQUIRE(Ci == 1 && kh == 2 && kw == 2 && Co <= 32, MMG_EUNSUPPORTED, "conv_small_relu_pool: only the 1 -> Co (<= 32), 2 x 2 stencil is built");
+    const int OH2 = (H + 2 * pad - kh + 1) / 2, OW2 = (W + 2 * pad - kw + 1) / 2;
+    MMG_REQUIRE(OH2 > 0 && OW2 > 0 && (long long)B * OH2 * OW2 < (1LL << 31), MMG_EINVAL, "conv_small_relu_pool: bad geometry");
+    conv_small_relu_pool_kernel<1, 2, 2><<<mmg_grid((long long)B * OH2 * OW2, 128, 16), 128, 0, (cudaStream_t)stream>>>(x, w, bias, yp, idx, B, H, W, Co, pad, OH2, OW2);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

@@ -40,6 +40,11 @@ def _r8(n):
     return (n + 7) // 8 * 8
 
 
+def _r16(n):
+    """im2col row pitch: a multiple of 16 elements (the im2col kernel then stores whole 32-byte sectors), except for tiny K"""
+    return (n + 15) // 16 * 16 if n > 8 else 8
+
+
 def _pack(src, dims, perm, pitch, out=None, a_stride=0):
     """fp32 tensor viewed as (d0,d1,d2) -> bf16 [n_pa * n_pb][pitch] (zero padded), or into ``out`` with ``a_stride`` elements between the pa blocks."""
     if out is None:
@@ -126,7 +131,7 @@ class Conv2dActTC(torch.autograd.Function):
         Co, _, kh, kw = w.shape
         OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
         K = Ci * kh * kw
-        Kp = _r8(K + 1)
+        Kp = _r16(K + 1)
 
         def make_w():
             ext = torch.zeros(Co, Kp, device=w.device)
@@ -158,7 +163,7 @@ class Conv2dActTC(torch.autograd.Function):
                 N.call("mmg_conv2d_bwd_data_f32", N.ptr(dz), N.ptr(w), None, N.ptr(dx), Nn, Ci, H, W, Co, kh, kw, stride, pad, ACT_NONE, N.stream())
             else:
                 K2 = Co * kh * kw
-                K2p = _r8(K2)
+                K2p = _r16(K2)
                 wf = _cached(w, "convT", lambda: w.flip(2, 3).permute(1, 0, 2, 3).reshape(Ci, K2).contiguous())
                 wfp = _cached(w, "convTp", lambda: _pack(wf, (1, Ci, K2), (0, 1, 2), K2p))
                 col2 = torch.empty(Nn * H * W, K2p, device=dz.device, dtype=_BF)
@@ -189,7 +194,7 @@ class Conv2dReluPoolTC(torch.autograd.Function):
         Co, _, kh, kw = w.shape
         OH, OW = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
         K = Ci * kh * kw
-        Kp = _r8(K + 1)
+        Kp = _r16(K + 1)
 
         def make_w():
             ext = torch.zeros(Co, Kp, device=w.device)
@@ -197,18 +202,25 @@ class Conv2dReluPoolTC(torch.autograd.Function):
             if b is not None:
                 ext[:, K] = b
             return ext.to(_BF)
-        wp = _cached(w, ("conv", None if b is None else (b.data_ptr(), b._version)), make_w)
         P = Nn * OH * OW
-        col = torch.empty(P, Kp, device=x.device, dtype=_BF)
-        N.call("mmg_im2col_bf16", N.ptr(x), N.ptr(col), Nn, Ci, H, W, kh, kw, 1, pad, Kp, 1, N.stream())
-        y = torch.empty(Nn, Co, OH, OW, device=x.device)
-        _gemm(col, 0, Kp, wp, 0, Kp, y, Co, P, Co, K + 1, trans_out=True, inner=OH * OW, act=ACT_RELU)
         yp = torch.empty(Nn, Co, OH // 2, OW // 2, device=x.device)
         idx = torch.empty(Nn, Co, OH // 2, OW // 2, device=x.device, dtype=torch.uint8)
-        N.call("mmg_maxpool2_fwd_f32", N.ptr(y), N.ptr(yp), N.ptr(idx), Nn * Co, OH, OW, N.stream())
-        ctx.save_for_backward(col, w, yp, idx)
+        stencil = (Ci, kh, kw) == (1, 2, 2) and Co <= 32
+        if stencil:
+            # K = 4 is a stencil, not a GEMM: conv + bias + ReLU + pool in one fp32 kernel, the (B,Co,OH,OW) activation never exists; the
+            # backward (a reduction over all pixels: a GEMM again) rebuilds the im2col rows of x
+            N.call("mmg_conv_small_relu_pool_f32", N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(yp), N.ptr(idx), Nn, Ci, H, W, Co, kh, kw, pad, N.stream())
+            ctx.save_for_backward(x, w, yp, idx)
+        else:
+            wp = _cached(w, ("conv", None if b is None else (b.data_ptr(), b._version)), make_w)
+            col = torch.empty(P, Kp, device=x.device, dtype=_BF)
+            N.call("mmg_im2col_bf16", N.ptr(x), N.ptr(col), Nn, Ci, H, W, kh, kw, 1, pad, Kp, 1, N.stream())
+            y = torch.empty(Nn, Co, OH, OW, device=x.device)
+            _gemm(col, 0, Kp, wp, 0, Kp, y, Co, P, Co, K + 1, trans_out=True, inner=OH * OW, act=ACT_RELU)
+            N.call("mmg_maxpool2_fwd_f32", N.ptr(y), N.ptr(yp), N.ptr(idx), Nn * Co, OH, OW, N.stream())
+            ctx.save_for_backward(col, w, yp, idx)
         ctx.cfg = (Nn, Ci, H, W, Co, kh, kw, pad, OH, OW, K, Kp)
-        ctx.has_b = b is not None
+        ctx.has_b, ctx.stencil = b is not None, stencil
         return yp
 
     @staticmethod
@@ -218,6 +230,9 @@ class Conv2dReluPoolTC(torch.autograd.Function):
         dyp = _f32c(dyp)
         P = Nn * OH * OW
         Pp = _r8(P)
+        if ctx.stencil and (ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2])):
+            x, col = col, torch.empty(P, Kp, device=dyp.device, dtype=_BF)
+            N.call("mmg_im2col_bf16", N.ptr(x), N.ptr(col), Nn, Ci, H, W, kh, kw, 1, pad, Kp, 1, N.stream())
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2])
         dz = torch.empty(Nn, Co, OH, OW, device=dyp.device) if need_dx else None
@@ -226,7 +241,7 @@ class Conv2dReluPoolTC(torch.autograd.Function):
         dx = dw = db = None
         if need_dx:
             K2 = Co * kh * kw
-            K2p = _r8(K2)
+            K2p = _r16(K2)
             wf = _cached(w, "convT", lambda: w.flip(2, 3).permute(1, 0, 2, 3).reshape(Ci, K2).contiguous())
             wfp = _cached(w, "convTp", lambda: _pack(wf, (1, Ci, K2), (0, 1, 2), K2p))
             col2 = torch.empty(Nn * H * W, K2p, device=dz.device, dtype=_BF)

@@ -118,6 +118,11 @@ int mmg_colsum_f32(const float* src, float* dst, int rows, int cols, void* strea
 int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int cols, int act, void* stream);
 /* backward of MaxPool2d(2,2)(ReLU(z)) in one pass (SIMNN.py:138-139): dyp / idx / yp are the pooled gradient, the argmax codes of
  * mmg_maxpool2_fwd_f32 and the pooled output; writes dz fp32 NCHW (B,C,H,W) and / or dzt bf16 [C][Pp >= B*H*W] (either may be NULL) */
+/* MaxPool2d(2,2)(ReLU(conv2d(x, w, b, stride 1, pad))) for a tiny stencil in ONE kernel (SIMNN.py:123,138: Conv2d(1, 16, kernel_size=2) has
+ * K = 4: a stencil, not a GEMM).  Built for Ci = 1, 2 x 2, Co <= 32; anything else returns MMG_EUNSUPPORTED (use mmg_im2col_bf16 + mmg_gemm_tc).
+ * yp / idx: (B, Co, OH/2, OW/2) pooled output and argmax codes (as mmg_maxpool2_fwd_f32), OH = H + 2 pad - kh + 1. */
+int mmg_conv_small_relu_pool_f32(const float* x, const float* w, const float* bias, float* yp, uint8_t* idx, int B, int Ci, int H, int W, int Co, int kh,
+                                 int kw, int pad, void* stream);
 int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream);
 
 /* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
