@@ -125,6 +125,14 @@ int mmg_conv_small_relu_pool_f32(const float* x, const float* w, const float* bi
                                  int kw, int pad, void* stream);
 int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream);
 
+/* ---- GAN-DES mel front end (GAN_DES/util.py:37-61: torchaudio MelSpectrogram + AmplitudeToDB) ----
+ * mmg_stft_power_f32: wave (B, L) fp32 (row pitch wave_pitch) -> power [B*T][pitch >= 1025] fp32, T = 1 + L / hop: centred frames with
+ * reflect padding, periodic Hann window, 2048-point FFT, |X|^2.  Only n_fft = 2048.  The mel projection is mmg_gemm_tc (dtype 1, tf32) with
+ * the transposed filter bank as B and trans_out / inner = T; mmg_power_to_db_f32 then gives 10 log10(max(x, 1e-10)) floored at the
+ * spectrogram's maximum - top_db (top_db < 0: no floor) for n_spectrograms blocks of n values. */
+int mmg_stft_power_f32(const float* wave, int B, long long L, long long wave_pitch, int n_fft, int hop, float* power, int pitch, void* stream);
+int mmg_power_to_db_f32(const float* x, float* out, int n_spectrograms, long long n, float top_db, void* stream);
+
 /* ---- bf16 tensor-core discriminator (DiscriminatorCNN, network_tests.py:147-160 and its autograd backward) ----
  * Activations live in padded space-to-depth layouts (see csrc/disc_tc.cu): XS (B*1690, 8) is the input, P1 (B*429, 64)
  * the conv1 activations, A2 / DZ2 (B*429, 32) the conv2 activations / their gradient, DZ1C (B*1690, 16) the conv1

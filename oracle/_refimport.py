@@ -205,3 +205,16 @@ def import_gandes():
     finally:
         os.chdir(cwd)
     return m
+
+
+def import_gandes_util():
+    """Returns the UNMODIFIED GAN_DES/util.py (mel-spectrogram helpers): librosa is stubbed (only the two librosa-based helpers need it), the
+    REAL torchaudio of this image computes ``get_melspectrogram_db_tensor`` (util.py:37-61).  Run in a separate process from the other imports."""
+    if not os.path.isdir(REF_ROOT):
+        raise RuntimeError(f"reference not present at {REF_ROOT}")
+    sys.modules.setdefault("librosa", _Stub("librosa"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_gandes_util", os.path.join(REF_ROOT, "GAN_DES", "util.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m

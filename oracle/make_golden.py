@@ -446,6 +446,23 @@ def make_midi():
     print("midi goldens:", len(files), "files,", sum(len(gold[f"s{i}.dt"]) for i in range(len(files))), "messages")
 
 
+def make_mel():
+    """GAN_DES/util.py:37-87 UNMODIFIED (torchaudio of this image) on deterministic test signals (mel_oracle.synth_wave: regenerated from the
+    seed by the tests, so only the outputs are stored): the three call shapes of the reference -- datasets.py:51 (110 250 samples at 22 050 Hz),
+    datasets.py:88 (a 5 s split at 44 100 Hz, default sr) and a short clip -- dB spectrograms, plus the power spectrogram `_maestro` returns."""
+    import mel_oracle as mel
+    u = R.import_gandes_util()
+    out = {"meta": np.array([[110250, 22050, 11], [220500, 44100, 12], [30000, 44100, 13], [2049 * 215 + 7, 44100, 14]], dtype=np.int64)}
+    for i, (L, sr, seed) in enumerate(out["meta"]):
+        w = torch.from_numpy(mel.synth_wave(int(L), int(seed)))
+        db = u.get_melspectrogram_db_tensor(w, int(sr))
+        out[f"db{i}"] = db.numpy().astype(np.float32)
+        if i == 1:
+            out["power1"] = u.get_melspectrogram_db_tensor_maestro(w, int(sr)).numpy().astype(np.float32)
+        print("mel case", i, tuple(db.shape), float(db.min()), float(db.max()))
+    np.savez_compressed(os.path.join(GOLD, "mel_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -463,7 +480,10 @@ if __name__ == "__main__":
         make_midi()
     if what == "artifacts_gandes":
         make_artifacts_gandes()
+    if what == "mel":
+        make_mel()
     if what == "all":
         import subprocess
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "artifacts_gandes"])
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "gandes"])
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "mel"])
