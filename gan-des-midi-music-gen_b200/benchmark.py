@@ -198,6 +198,33 @@ def _gandes_leg(device):
                              "sample": f"{n} iterations of batch {B} through oracle/mmgan_oracle.gandes_iteration"}}
 
 
+def _mel_leg(device, peaks):
+    """the GAN-DES mel front end (GAN_DES/util.py:37-61) for one batch of real windows: 30 five-second windows at 44.1 kHz
+    (datasets.py:85-90, SIMNN.py:236) -> (30, 128, 216) dB spectrograms; waveforms resident on the device."""
+    import mel_oracle as mel                # cpu_baseline sample only
+    from .GAN_DES import util
+    B, L = 30, 220500
+    waves_h = np.stack([mel.synth_wave(L, 100 + b) for b in range(B)])
+    waves = torch.from_numpy(waves_h).to(device)
+    fn = lambda i: util.get_melspectrogram_db_tensor(waves)
+    out = fn(0)
+    for _ in range(3):
+        fn(0)
+    l0 = N.lib().mmg_launch_count()
+    sec = _timed(fn, 20, torch.cuda.synchronize) / 20
+    launches = (N.lib().mmg_launch_count() - l0) // 20
+    t0 = time.perf_counter()
+    want = mel.get_melspectrogram_db_tensor(waves_h[0])
+    cs = time.perf_counter() - t0
+    err = float(np.abs(out[0].cpu().numpy() - want).max())
+    alg_bytes = B * L * 4.0 + B * 128 * 216 * 4.0
+    return {"windows_per_sec": B / sec, "us": sec * 1e6, "batch": B, "samples_per_window": L, "launches": launches, "max_abs_db_error_vs_oracle": err,
+            "dtype": "f32 FFT, tf32 mel projection",
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"],
+                         "algorithmic_bytes": alg_bytes, "traffic": None, "peak_src": peaks["src"]},
+            "cpu_baseline": {"value": 1.0 / cs, "unit": "windows/s", "cores": 1, "kind": "port", "sample": "1 window through oracle/mel_oracle.py (numpy float64)"}}
+
+
 def _inference_leg(mmgan, device):
     """BASELINE config 5: eval-mode G1 + G2 (running-stat BatchNorm folded into the tcgen05 prologue / epilogue) for B = 1 .. 16384, outputs
     (B,1,64,64) + (B,20) fp32 delivered to pinned host memory -- what matrix_to_midi consumes (matrix_sim_process.py:28-29)."""
@@ -407,6 +434,7 @@ def run(args):
             mmgan.eval()
             line["inference_sweep"] = _inference_leg(mmgan, device)
             line["gandes"] = _gandes_leg(device)
+            line["gandes_mel"] = _mel_leg(device, peaks)
     if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()
