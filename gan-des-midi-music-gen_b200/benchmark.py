@@ -388,6 +388,15 @@ def run(args):
                 "other_kernels": {k.split(" ")[0]: {"us": v[0] * 1e6, "tflops": v[1] / v[0] / 1e12} for k, v in timed.items() if k != kname},
                 "step_achieved_tflops_per_gpu": FLOP_PER_ROLL * B * args.steps / sec / 1e12,
                 "step_frac_of_bf16_peak": FLOP_PER_ROLL * B * args.steps / sec / 1e12 / peaks["bf16_tflops_sustained"]}
+    if kname.startswith("disc_pass_fused_kernel"):
+        # what actually bounds this kernel: the tensor cores read their operands from shared memory at 128 B per clock and SM
+        # (ncu l1tex__data_pipe_tc_wavefronts_mem_shared); the MMA program of one sample reads 42 x 4608 + 68 x 5120 + 89 x 6144 bytes
+        op_bytes = (42 * 4608 + 68 * 5120 + 89 * 6144) * float(Bk)
+        sm_clock = 1.965e9 if not clocks.summary().get("sm_mhz") else clocks.summary()["sm_mhz"] * 1e6
+        feed_peak = 148 * 128 * sm_clock
+        roofline["operand_feed"] = {"bound": "shared memory -> tensor core operand reads", "achieved_tbs": op_bytes / ksec / 1e12, "peak_tbs": feed_peak / 1e12,
+                                    "frac": op_bytes / ksec / feed_peak, "operand_bytes_per_roll": op_bytes / Bk,
+                                    "note": "N = 16 / 32 / 64 MMAs: the A tile (4 KB per M128 x K16 MMA) is re-read once per tap; ncu: 61-66 % of the pipe's peak"}
 
     line = {"metric": METRIC, "value": value, "unit": "rolls/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
