@@ -645,7 +645,22 @@ __global__ void __launch_bounds__(K2_THREADS) raster_rows_kernel(const uint32_t*
                 c1 = c1 < a_next_off ? c1 : a_next_off;
                 c1 = c1 < hi ? c1 : hi;
                 const unsigned v = (unsigned)(s - a);
-                for (int c = a > lo ? a : lo; c < c1; ++c) put_d(c, v);
+                int c = a > lo ? a : lo;
+                if (rowbuf) {
+                    // this lane's cells [c, c1) of the shared-memory row: head to 8-byte alignment, 4 cells per store, tail (the per-lane spans
+                    // differ, so the loop runs as long as the longest one: 4x fewer trips)
+                    int j = c - lo;
+                    const int j1 = c1 - lo;
+                    const uint16_t v16 = (uint16_t)v;
+                    const uint32_t v32 = (uint32_t)v16 * 0x10001u;
+                    if ((j & 1) && j < j1) row_d[j++] = v16;
+                    if ((j & 2) && j + 2 <= j1) { *reinterpret_cast<uint32_t*>(row_d + j) = v32; j += 2; }
+                    for (; j + 4 <= j1; j += 4) *reinterpret_cast<uint2*>(row_d + j) = make_uint2(v32, v32);
+                    if (j + 2 <= j1) { *reinterpret_cast<uint32_t*>(row_d + j) = v32; j += 2; }
+                    if (j < j1) row_d[j] = v16;
+                } else {
+                    for (; c < c1; ++c) put_d(c, v);
+                }
             }
             if (onm) {
                 const int last = 31 - __clz(onm);
