@@ -90,3 +90,23 @@ def test_gram_stats_arg_checks_without_gpu():
     assert rc == -1 and b"Expected more than 1 value per channel" in lib.mmg_last_error()
     rc = lib.mmg_gen_layer_stats_gram(one, 4, 64, one, 0, one, one, 1e-5, one, one, 4096, one, one, 16, None)
     assert rc < 0 and b"workspace too small" in lib.mmg_last_error()
+
+
+def test_gandes_entry_point_arg_checks_without_gpu():
+    """argument errors of the GAN-DES entry points are reported before any CUDA call (codes: -1 invalid, -2 unsupported)"""
+    from gan_des_midi_music_gen_b200 import _native as N
+    lib = N.lib()
+    p = ctypes.c_void_p(4096)                                   # a well-aligned non-null address that is never dereferenced on these paths
+    gemm = lambda *a: lib.mmg_gemm_tc(*a)
+    assert gemm(None, 0, 64, p, 0, 64, p, 32, 128, 32, 64, 0, 1, 0, 0, 0, None, 0, 0, None) == -1
+    assert gemm(p, 1, 64, p, 0, 64, p, 32, 128, 32, 64, 1, 1, 0, 0, 0, None, 0, 0, None) == -2 and b"tf32" in lib.mmg_last_error()
+    assert gemm(p, 0, 60, p, 0, 64, p, 32, 128, 32, 60, 0, 1, 0, 0, 0, None, 0, 0, None) == -1 and b"16-byte" in lib.mmg_last_error()
+    assert gemm(p, 0, 64, p, 0, 64, p, 32, 128, 32, 640, 0, 4, 0, 0, 0, None, 0, 0, None) == -1 and b"split_k" in lib.mmg_last_error()
+    assert gemm(p, 0, 64, p, 0, 64, p, 32, 128, 32, 64, 0, 1, 1, 0, 0, None, 0, 0, None) == -1 and b"inner" in lib.mmg_last_error()
+    assert lib.mmg_im2col_bf16(p, p, 2, 16, 8, 8, 3, 3, 1, 1, 144, 1, None) == -1 and b"pitch" in lib.mmg_last_error()      # no room for the ones column
+    assert lib.mmg_im2col_bf16(p, p, 2, 16, 8, 8, 3, 3, 1, 1, 150, 0, None) == -1                                            # pitch not a multiple of 8
+    assert lib.mmg_pack_bf16(p, p, 2, 3, 4, 0, 0, 2, 8, 0, None) == -1 and b"permutation" in lib.mmg_last_error()
+    assert lib.mmg_conv_small_relu_pool_f32(p, p, p, p, p, 2, 3, 16, 16, 8, 2, 2, 1, None) == -2
+    assert lib.mmg_stft_power_f32(p, 2, 40000, 40000, 1024, 186, p, 1028, None) == -2 and b"2048" in lib.mmg_last_error()
+    assert lib.mmg_stft_power_f32(p, 2, 900, 900, 2048, 4, p, 1028, None) == -1 and b"reflect" in lib.mmg_last_error()
+    assert lib.mmg_pool_relu_bwd(p, p, p, None, None, 2, 4, 8, 8, 0, None) == -1
