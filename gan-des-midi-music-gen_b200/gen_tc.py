@@ -19,7 +19,7 @@ from . import _native as N
 
 
 class GenTC:
-    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=True):
+    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=True, sum_views=None):
         self.g = gen
         dist = torch.distributed
         self.pg = process_group
@@ -40,8 +40,12 @@ class GenTC:
         for w in self.widths:
             offs.append(o)
             o += 2 * w
-        self.sums = torch.zeros(o, dtype=torch.float64, device=dev)     # [layer][sum | sumsq][width]
-        self.sum_views = [self.sums[a:a + 2 * w] for a, w in zip(offs, self.widths)]
+        if sum_views is None:
+            self.sums = torch.zeros(o, dtype=torch.float64, device=dev)     # [layer][sum | sumsq][width]
+            self.sum_views = [self.sums[a:a + 2 * w] for a, w in zip(offs, self.widths)]
+        else:           # storage owned by the caller (trainer.py: the two generators' layer-i sums sit side by side: one all-reduce for both)
+            assert len(sum_views) == len(self.widths) and all(v.numel() == 2 * w and v.dtype == torch.float64 for v, w in zip(sum_views, self.widths))
+            self.sums, self.sum_views = None, list(sum_views)
         # the wide output layer's batch statistics come from the 64 x 64 Gram matrix of its input instead of a GEMM pass (csrc/gen_tc.cu)
         last = self.blocks[-1][0]
         self.gram_stats = bool(gram_stats) and last.in_features <= 64 and last.in_features % 8 == 0 and last.out_features >= 512
@@ -64,6 +68,18 @@ class GenTC:
 
     def forward(self, noise, input_tensor, training=None, out=None):
         """noise (B,z) and input_tensor (B,input_dim) fp32 CUDA tensors -> (B, out_features) fp32 (caller reshapes)."""
+        steps = self.forward_steps(noise, input_tensor, training, out)
+        while True:
+            try:
+                i = next(steps)
+            except StopIteration as done:
+                return done.value
+            self._sync(i)
+
+    def forward_steps(self, noise, input_tensor, training=None, out=None):
+        """The forward as a Python generator: yields the index of a layer whose batch sums are complete on this rank and must be summed over
+        the ranks (SyncBN) before the next kernel is enqueued; returns the output.  ``forward`` all-reduces each one on its own; the trainer
+        drives both generators in lock step and reduces their layer-i sums with ONE collective."""
         N.require_cuda(noise, input_tensor)
         training = self.g.training if training is None else training
         B = noise.shape[0]
@@ -75,7 +91,11 @@ class GenTC:
         self.pack(force=False)
         s = N.stream()
         if training:
-            N.call("mmg_zero", N.ptr(self.sums), self.sums.numel() * 8, s)
+            if self.sums is not None:
+                N.call("mmg_zero", N.ptr(self.sums), self.sums.numel() * 8, s)
+            else:
+                for v in self.sum_views:
+                    N.call("mmg_zero", N.ptr(v), v.numel() * 8, s)
         y = out if out is not None else torch.empty(B, self.widths[-1], device=self.dev)
         mode = 1 if training else 2
         last = len(self.blocks) - 1
@@ -98,8 +118,8 @@ class GenTC:
                 a.z_out = N.ptr(self.z[i])
                 a.out_sums = N.ptr(self.sum_views[i]) if training else None
                 N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
-                if training:
-                    self._sync(i)
+                if training and self.sync_bn:
+                    yield i
             else:
                 a.out_gamma, a.out_beta = N.ptr(bn.weight.data), N.ptr(bn.bias.data)
                 a.out_run_mean, a.out_run_var = N.ptr(bn.running_mean), N.ptr(bn.running_var)
@@ -108,11 +128,13 @@ class GenTC:
                     N.call("mmg_gen_layer_stats_gram", N.ptr(self.z[i - 1]), B, self.widths[i - 1], N.ptr(self.sum_views[i - 1]), B * self.world,
                            N.ptr(pbn.weight.data), N.ptr(pbn.bias.data), pbn.eps, N.ptr(lin.weight.data), N.ptr(lin.bias.data), lin.out_features,
                            N.ptr(self.sum_views[i]), N.ptr(self.gram_ws), self.gram_ws.numel(), s)
-                    self._sync(i)                  # (the single pass below also makes the one update of the previous layer's running stats)
+                    if self.sync_bn:
+                        yield i                    # (the single pass below also makes the one update of the previous layer's running stats)
                 elif training:                     # pass 1: batch sums only (also the one update of the previous layer's running stats)
                     a.out_sums = N.ptr(self.sum_views[i])
                     N.call("mmg_gen_layer_fwd", ctypes.byref(a), s)
-                    self._sync(i)
+                    if self.sync_bn:
+                        yield i
                     a.out_sums = None
                     a.in_run_mean = a.in_run_var = None      # already updated by pass 1
                 a.y_out, a.out_mode = N.ptr(y), mode

@@ -92,8 +92,25 @@ class MMGANTrainer:
             from .disc_tc import DiscTC
             from .gen_tc import GenTC
             self.tc = DiscTC(D, max_batch)
-            self.gtc1 = GenTC(mmgan.generator1, max_batch, process_group, self.sync_bn)
-            self.gtc2 = GenTC(mmgan.generator2, max_batch, process_group, self.sync_bn)
+            sv1 = sv2 = None
+            if self.sync_bn:
+                # SyncBN: the layer-i batch sums of the two generators sit side by side in one buffer, so ONE all-reduce per layer index serves
+                # both (5 collectives per pair of forwards instead of 9)
+                w1 = [blk[0].out_features for blk in mmgan.generator1.gen]
+                w2 = [blk[0].out_features for blk in mmgan.generator2.gen]
+                nl = max(len(w1), len(w2))
+                tot = sum(2 * (w1[i] if i < len(w1) else 0) + 2 * (w2[i] if i < len(w2) else 0) for i in range(nl))
+                self._sync_sums = torch.zeros(tot, dtype=torch.float64, device=self.flat_grad.device)
+                sv1, sv2, self._sync_pairs, o = [], [], [], 0
+                for i in range(nl):
+                    a = o
+                    if i < len(w1):
+                        sv1.append(self._sync_sums[o:o + 2 * w1[i]]); o += 2 * w1[i]
+                    if i < len(w2):
+                        sv2.append(self._sync_sums[o:o + 2 * w2[i]]); o += 2 * w2[i]
+                    self._sync_pairs.append(self._sync_sums[a:o])
+            self.gtc1 = GenTC(mmgan.generator1, max_batch, process_group, self.sync_bn, sum_views=sv1)
+            self.gtc2 = GenTC(mmgan.generator2, max_batch, process_group, self.sync_bn, sum_views=sv2)
         dev = self.flat_grad.device
         if inner_rng not in ("reference", "device"):
             raise ValueError("inner_rng must be 'reference' or 'device'")
@@ -167,9 +184,32 @@ class MMGANTrainer:
                 self._g_out_owned = out is None
                 a = m.generator1.adj_size
                 if self.sync_bn:
-                    # SyncBN: the statistics all-reduces sit between the layer kernels; both generators on this stream (one collective order)
-                    self.g2_out = self.gtc2.forward(noise2, beats, out=self._g_out[1])
-                    self.g1_out = self.gtc1.forward(noise1, inner, out=self._g_out[0]).view(B, -1, a[0], a[1])
+                    # SyncBN: the statistics all-reduces sit between the layer kernels.  Both generators advance in lock step on this stream
+                    # and their layer-i sums (adjacent in self._sync_sums) are reduced by one collective.
+                    st1 = self.gtc1.forward_steps(noise1, inner, out=self._g_out[0])
+                    st2 = self.gtc2.forward_steps(noise2, beats, out=self._g_out[1])
+                    y1 = y2 = None
+                    i1 = i2 = -1
+                    while y1 is None or y2 is None:
+                        if y1 is None:
+                            try:
+                                i1 = next(st1)
+                            except StopIteration as fin:
+                                y1, i1 = fin.value, None
+                        if y2 is None:
+                            try:
+                                i2 = next(st2)
+                            except StopIteration as fin:
+                                y2, i2 = fin.value, None
+                        if i1 is not None and i2 is not None:
+                            assert i1 == i2, "the generators' SyncBN points went out of step"
+                            torch.distributed.all_reduce(self._sync_pairs[i1], group=self.pg)
+                        elif i1 is not None:
+                            torch.distributed.all_reduce(self.gtc1.sum_views[i1], group=self.pg)
+                        elif i2 is not None:
+                            torch.distributed.all_reduce(self.gtc2.sum_views[i2], group=self.pg)
+                    self.g2_out = y2
+                    self.g1_out = y1.view(B, -1, a[0], a[1])
                 else:
                     # the two generators are independent: the beat generator runs on a side stream (fork / join, also under graph capture)
                     cur = torch.cuda.current_stream()
