@@ -12,6 +12,12 @@ has a gradient).  ``GANDESTrainer`` keeps that order and cuts it where the host 
 Each segment runs eagerly the first time it sees a set of input buffers, is captured into a CUDA graph the second time (forward, autograd
 backward and the Adam update: ~60 launches) and replayed afterwards.  Adam's step count and hyper-parameters live in device memory
 (``mmg_adam_multi_tensor_dev_f32``) so the replayed update is the right one.  Works with the fp32 kernels and with ``enable_tensor_cores()``.
+
+Data parallel: with an initialised process group every rank runs the segments on its shard of the batch.  The discriminator has no
+BatchNorm, so the mean-loss gradient of the global batch is the average of the shard gradients: each parameter's gradient is all-reduced as
+soon as autograd has produced it (fc2 / fc1 -- 28 MB -- first, underneath the convolution backward), the 1/world goes into the Adam kernel,
+and with NCCL the collectives are captured into the D-step graph.  The G step's discriminator gradients are never applied by the reference and
+are not reduced.  ``generate`` uses per-replica BatchNorm statistics; the returned losses are the means over this rank's shard.
 """
 import ctypes
 
@@ -23,8 +29,14 @@ from .optim import BCEWithLogitsLoss
 
 
 class GANDESTrainer:
-    def __init__(self, gen, disc, lr=2e-5, betas=(0.5, 0.999), eps=1e-8, use_graph=True):
+    def __init__(self, gen, disc, lr=2e-5, betas=(0.5, 0.999), eps=1e-8, use_graph=True, process_group=None, data_parallel=None):
+        """``data_parallel``: None = shard over ``process_group`` when torch.distributed is initialised, False = this process alone."""
         self.gen, self.disc = gen, disc
+        dist = torch.distributed
+        self.pg = process_group
+        on = dist.is_available() and dist.is_initialized() and data_parallel is not False
+        self.world = dist.get_world_size(process_group) if on else 1
+        self._reduce_now, self._forked = False, False
         self.crit = BCEWithLogitsLoss()
         self.d_params = list(disc.parameters())
         dev = self.d_params[0].device
@@ -35,6 +47,23 @@ class GANDESTrainer:
         self.use_graph = bool(use_graph)
         self._graphs, self._seen, self._labels = {}, {}, {}
         self.replayed_launches = 0
+        if self.world > 1:
+            if self.use_graph and dist.get_backend(process_group) != "nccl":
+                self.use_graph = False                        # host-side collectives (gloo) cannot be captured
+            self._side = torch.cuda.Stream(device=dev)
+            for p in self.d_params:
+                p.register_post_accumulate_grad_hook(self._grad_ready)
+
+    def _grad_ready(self, p):
+        """autograd has finished this parameter's gradient: its all-reduce (D step only) goes to a side stream, so the rest of the backward
+        runs underneath it (fork here, join before Adam: the same pattern eagerly and under graph capture; no asynchronous work handles,
+        which the NCCL watchdog would keep waiting for after a capture)"""
+        if self._reduce_now:
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                torch.distributed.all_reduce(p.grad, group=self.pg)
+            self._forked = True
 
     # ------------------------------------------------------------------ pieces
     def _label(self, B, v):
@@ -48,7 +77,7 @@ class GANDESTrainer:
         ts = [p.data for p in ps] + [p.grad for p in ps] + self.exp_avg + self.exp_avg_sq
         ptrs = (ctypes.c_void_p * (4 * len(ps)))(*[N.ptr(t) for t in ts])
         sizes = (ctypes.c_int64 * len(ps))(*[p.numel() for p in ps])
-        N.call("mmg_adam_multi_tensor_dev_f32", len(ps), ptrs, sizes, N.ptr(self.hyper), N.ptr(self.adam_step), 1.0, N.stream())
+        N.call("mmg_adam_multi_tensor_dev_f32", len(ps), ptrs, sizes, N.ptr(self.hyper), N.ptr(self.adam_step), 1.0 / self.world, N.stream())
         FnTC.invalidate_weight_cache()
 
     def _d_body(self, real, fake):
@@ -58,7 +87,14 @@ class GANDESTrainer:
         l_real = self.crit(self.disc(real).reshape(-1), self._label(B, 0.9))
         l_fake = self.crit(self.disc(fake.detach()).reshape(-1), self._label(B, 0.1))
         loss = l_fake + l_real
-        loss.backward()
+        self._reduce_now = self.world > 1
+        try:
+            loss.backward()
+        finally:
+            self._reduce_now = False
+        if self._forked:                                       # sums over the ranks are complete before Adam; the 1/world is applied inside its kernel
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._forked = False
         for p in self.d_params:
             if p.grad is None or not p.grad.is_contiguous():
                 raise RuntimeError("GANDESTrainer: every discriminator parameter needs a contiguous gradient")
@@ -87,7 +123,7 @@ class GANDESTrainer:
             FnTC.invalidate_weight_cache()                 # every packed weight must be (re)built INSIDE the graph
             l0 = N.lib().mmg_launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 out = fn()
             FnTC.invalidate_weight_cache()                 # the cache now points into the graph's private pool: eager code must not trust it
             g = self._graphs[key] = (graph, out, N.lib().mmg_launch_count() - l0)

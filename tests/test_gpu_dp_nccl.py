@@ -28,6 +28,20 @@ def _mk(device, seed=4):
     return m.train()
 
 
+def _teardown():
+    """The results are in the queue: the communicator teardown must never keep the worker (and with it pytest) alive -- a timer ends the
+    process if destroy_process_group stalls (CUDA graphs that hold NCCL kernels are still alive at this point)."""
+    import gc
+    import threading
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    killer.cancel()
+
+
 def _worker(rank, world, port, q, backend, ngpu):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -90,7 +104,79 @@ def _worker(rank, world, port, q, backend, ngpu):
         import traceback
         q.put((rank, None, traceback.format_exc()))
     finally:
-        dist.destroy_process_group()
+        _teardown()
+
+
+def _worker_gandes(rank, world, port, q, backend, ngpu):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank % ngpu)
+    dev = torch.device("cuda", rank % ngpu)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gan_des_midi_music_gen_b200.GAN_DES import SIMNN
+        from gan_des_midi_music_gen_b200.gandes_trainer import GANDESTrainer
+        from gan_des_midi_music_gen_b200.trainer import shard_batch
+        Bg = 4
+        gshapes, dshapes = mo.gandes_shapes()
+        g = torch.Generator().manual_seed(31)
+        noise, real, fake = (torch.randn(Bg, 100, 1, 1, generator=g).to(dev), torch.randn(Bg, 128, 216, generator=g).to(dev),
+                             torch.randn(Bg, 128, 216, generator=g).to(dev))
+        res = {}
+        for mode in ("dp", "one"):
+            gen, disc = SIMNN.Generator().to(dev).enable_tensor_cores(), SIMNN.Discriminator().to(dev).enable_tensor_cores()
+            gen.load_state_dict(mo.synth_state(gshapes, seed=11)); disc.load_state_dict(mo.synth_state(dshapes, seed=12))
+            tr = GANDESTrainer(gen, disc, lr=2e-4, betas=(0.5, 0.999), data_parallel=(mode == "dp") and None)
+            assert tr.world == (world if mode == "dp" else 1)
+            r, f = (real, fake) if mode == "one" else (shard_batch(real, rank, world).contiguous(), shard_batch(fake, rank, world).contiguous())
+            losses = []
+            for it in range(4):
+                dl = tr.d_step(r, f)
+                gl = tr.g_step(f)
+                losses.append(torch.stack([dl, gl]).clone())
+            torch.cuda.synchronize()
+            ls = torch.stack(losses)
+            if mode == "dp":
+                dist.all_reduce(ls)
+                ls /= world
+                if backend == "nccl":
+                    assert {k[0] for k in tr._graphs} == {"d", "g"}, "the sharded D step (with its all-reduces) was not captured"
+            res[mode] = (ls.cpu(), [p.detach().clone() for p in disc.parameters()])
+        out = {"loss0": (res["dp"][0][0] - res["one"][0][0]).abs().max().item() / res["one"][0][0].abs().max().item(),
+               "loss": (res["dp"][0] - res["one"][0]).abs().max().item() / res["one"][0].abs().max().item(),
+               "par": max((a - b).abs().max().item() for a, b in zip(res["dp"][1], res["one"][1]))}
+        q.put((rank, out, None))
+    except Exception:       # pragma: no cover
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    finally:
+        _teardown()
+
+
+def test_gandes_trainer_sharded_matches_global_batch():
+    """GANDESTrainer over 2 ranks (every gradient all-reduced as autograd produces it, 1/world in the Adam kernel, the collectives captured into the
+    D-step graph under NCCL) against the same iterations on the global batch in one process (the discriminator has no BatchNorm)."""
+    ngpu = torch.cuda.device_count()
+    backend = "nccl" if ngpu >= 2 else "gloo"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_gandes, args=(r, 2, port, q, backend, max(1, min(ngpu, 2)))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        if p.is_alive():          # (a stalled communicator teardown: the results are already here)
+            p.kill()
+    for rank, out, err in res:
+        assert err is None, err
+        assert out["loss0"] < 1e-4, out                    # first iteration: identical weights on both sides
+        assert out["loss"] < 5e-3, out
+        assert out["par"] <= 4 * 2e-4 * 1.01 + 1e-7, out   # Adam moves a weight by at most lr per step; sign flips of ~0 gradient elements
 
 
 def test_sync_bn_and_sharded_iteration_match_global_batch():
@@ -105,6 +191,8 @@ def test_sync_bn_and_sharded_iteration_match_global_batch():
     res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():          # (a stalled communicator teardown: the results are already here)
+            p.kill()
     for rank, out, err in res:
         assert err is None, err
         assert out["gen_out"] < 2e-3, out                  # same bf16 operands; fp32/fp64 summation order only
