@@ -46,7 +46,8 @@ SIGNATURES = {
     "mmg_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
     "mmg_bias_act_inplace_f32": (_I, [_P, _P, _L, _I, _I, _P]),
     "mmg_conv_small_relu_pool_f32": (_I, [_P, _P, _P, _P, _P] + [_I] * 8 + [_P]),
-    "mmg_pool_relu_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _P]),
+    "mmg_pool_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _P]),
+    "mmg_conv_dgrad_gather": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P]),
     "mmg_stft_power_f32": (_I, [_P, _I, _L, _L, _I, _I, _P, _I, _P]),
     "mmg_power_to_db_f32": (_I, [_P, _P, _I, _L, _F, _P]),
     "mmg_maxpool2_fwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P]),

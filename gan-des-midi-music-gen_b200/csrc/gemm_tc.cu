@@ -37,6 +37,7 @@ struct GemmArgs {
     int trans_out;                         // element (m, n) -> C[(m / inner) * N * inner + n * inner + m % inner]   (NCHW: inner = pixels per image)
     long long inner;
     int atomic;                            // fp32 atomicAdd (split-K); bias / act are then left to the caller
+    int out_bf16;                          // C is a bf16 row-major matrix (plain stores only)
     const float* bias;
     int bias_on_m;
     int act;
@@ -132,7 +133,25 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_consta
             uint32_t r[32];
             tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             tc::tmem_ld_wait();
-            if (m < a.M && !a.trans_out && !a.atomic && n0 + c + 32 <= a.N && (a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0 && ((n0 + c) & 3) == 0) {
+            if (a.out_bf16) {
+                // bf16 row-major output (the tap columns of a convolution data gradient): 32 columns = four 16-byte stores
+                if (m < a.M) {
+                    __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(a.C) + (long long)m * a.ldc + n0 + c;
+                    if (n0 + c + 32 <= a.N && (a.ldc & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 o;
+                            o.x = pack_bf16x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])); o.y = pack_bf16x2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            o.z = pack_bf16x2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])); o.w = pack_bf16x2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+                            *reinterpret_cast<uint4*>(cb + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c + j < a.N) cb[j] = __float2bfloat16(__uint_as_float(r[j]));
+                    }
+                }
+            } else if (m < a.M && !a.trans_out && !a.atomic && n0 + c + 32 <= a.N && (a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0 && ((n0 + c) & 3) == 0) {
                 // plain row-major store of 32 consecutive columns: eight 16-byte stores
                 float4* dst = reinterpret_cast<float4*>(a.C + mo + n0 + c);
 #pragma unroll
@@ -390,6 +409,66 @@ __global__ void conv_small_relu_pool_kernel(const float* __restrict__ x, const f
     }
 }
 
+// Data gradient of a stride-1 convolution, second half: dcol[b * OH * OW + p][(ky * kw + kx) * Ci + ci] (bf16, the tap columns the GEMM
+// dz[p][oc] x W[oc][(ky,kx,ci)] produced) -> dx[b][ci][y][x] = sum over taps of dcol[(b, y + pad - ky, x + pad - kx)][tap][ci]   (gather, no atomics).
+// One thread = one input pixel: per tap one contiguous run of Ci bf16; the stores of a warp are contiguous per channel plane.
+template <int CI>
+__global__ void conv_dgrad_gather_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int B, int H, int W, int OH, int OW, int kh, int kw, int pad,
+                                         long long ldc) {
+    const unsigned total = (unsigned)B * H * W;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int x = (int)(i % (unsigned)W), t = (int)(i / (unsigned)W), y = t % H, b = t / H;
+        float acc[CI];
+#pragma unroll
+        for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int oy = y + pad - ky;
+            if (oy < 0 || oy >= OH) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int ox = x + pad - kx;
+                if (ox < 0 || ox >= OW) continue;
+                const uint4* src = reinterpret_cast<const uint4*>(dcol + (((long long)b * OH + oy) * OW + ox) * ldc + (ky * kw + kx) * CI);
+#pragma unroll
+                for (int q = 0; q < CI / 8; ++q) {
+                    const uint4 v = src[q];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc[8 * q + 2 * e] += __uint_as_float(w4[e] << 16);
+                        acc[8 * q + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CI; ++c) dx[(((size_t)b * CI + c) * H + y) * W + x] = acc[c];
+    }
+}
+
+// the same gradient as bf16 NHWC rows [b * H * W][C] (the K-major A operand of the data-gradient GEMM): one thread = one pixel and 8 channels =
+// one 16-byte store; the C / 8 threads of a pixel are neighbours, so a warp writes whole contiguous rows
+__global__ void pool_relu_bwd_nhwc_kernel(const float* __restrict__ dyp, const uint8_t* __restrict__ idx, const float* __restrict__ yp, __nv_bfloat16* __restrict__ dzn,
+                                          int B, int C, int H, int W, int OH, int OW) {
+    const unsigned CG = (unsigned)C >> 3;
+    const unsigned total = (unsigned)B * H * W * CG;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned cg = i % CG, p = i / CG, ix = p % (unsigned)W, t = p / (unsigned)W, iy = t % (unsigned)H, b = t / (unsigned)H;
+        const unsigned oy = iy >> 1, ox = ix >> 1, code = (iy & 1) * 2 + (ix & 1);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            v[e] = 0.f;
+            if (oy < (unsigned)OH && ox < (unsigned)OW) {
+                const size_t o = (((size_t)b * C + cg * 8 + e) * OH + oy) * OW + ox;
+                if (idx[o] == code && yp[o] > 0.f) v[e] = dyp[o];
+            }
+        }
+        uint4 q;
+        q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dzn + (size_t)p * C + cg * 8) = q;
+    }
+}
+
 // column sums of an fp32 [rows][cols] matrix (bias gradients): one warp per column group, fixed order
 __global__ void colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,7 +494,7 @@ extern "C" int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B
     const int esz = dtype ? 4 : 2, kelems = 128 / esz;
     MMG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && (lda * esz) % 16 == 0 && (ldb * esz) % 16 == 0, MMG_EINVAL,
                 "gemm_tc: operands need 16-byte aligned bases and row pitches");
-    MMG_REQUIRE(!trans_out || inner > 0, MMG_EINVAL, "gemm_tc: trans_out needs inner > 0");
+    MMG_REQUIRE(trans_out != 1 || inner > 0, MMG_EINVAL, "gemm_tc: trans_out needs inner > 0");
     MMG_REQUIRE(!(atomic && (bias || act)), MMG_EINVAL, "gemm_tc: bias / activation cannot be fused into a split-K accumulation");
     GemmArgs a{};
     a.M = M; a.N = N;
@@ -427,6 +506,9 @@ extern "C" int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B
     if (split_k > a.chunks) split_k = a.chunks;
     MMG_REQUIRE(split_k == 1 || atomic, MMG_EINVAL, "gemm_tc: split_k > 1 needs atomic accumulation into a zeroed C");
     a.chunks_per_split = (a.chunks + split_k - 1) / split_k;
+    a.out_bf16 = trans_out == 2 ? 1 : 0;                       // trans_out: 0 = fp32 row-major, 1 = fp32 transposed / NCHW, 2 = bf16 row-major
+    MMG_REQUIRE(!(a.out_bf16 && (atomic || bias || act)), MMG_EINVAL, "gemm_tc: the bf16 output takes plain stores only");
+    if (a.out_bf16) trans_out = 0;
     a.C = C; a.ldc = ldc; a.trans_out = trans_out; a.inner = inner; a.atomic = atomic; a.bias = bias; a.bias_on_m = bias_on_m; a.act = act;
     CUtensorMap map_a, map_b;
     const CUtensorMapDataType dt = dtype ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -518,14 +600,22 @@ extern "C" int mmg_bias_act_inplace_f32(float* y, const float* bias, long long r
     return MMG_OK;
 }
 
-extern "C" int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream) {
+extern "C" int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, void* dzn, int B, int C, int H, int W, long long Pp,
+                                 void* stream) {
     const int OH = H / 2, OW = W / 2;
-    MMG_REQUIRE(dyp && idx && yp && (dz || dzt) && B > 0 && C > 0 && OH > 0 && OW > 0, MMG_EINVAL, "pool_relu_bwd: bad argument");
+    MMG_REQUIRE(dyp && idx && yp && (dz || dzt || dzn) && B > 0 && C > 0 && OH > 0 && OW > 0, MMG_EINVAL, "pool_relu_bwd: bad argument");
     MMG_REQUIRE(!dzt || Pp >= (long long)B * H * W, MMG_EINVAL, "pool_relu_bwd: pitch of the transposed output smaller than B*H*W");
     const long long total = (long long)B * C * H * ((W + 3) / 4);
     MMG_REQUIRE(total < (1LL << 31), MMG_EUNSUPPORTED, "pool_relu_bwd: tensor too large for 32-bit indexing");
-    pool_relu_bwd_kernel<<<mmg_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dyp, idx, yp, dz, (__nv_bfloat16*)dzt, B, C, H, W, OH, OW, Pp);
-    MMG_LAUNCH_CHECK();
+    if (dz || dzt) {
+        pool_relu_bwd_kernel<<<mmg_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(dyp, idx, yp, dz, (__nv_bfloat16*)dzt, B, C, H, W, OH, OW, Pp);
+        MMG_LAUNCH_CHECK();
+    }
+    if (dzn) {
+        MMG_REQUIRE(C % 8 == 0 && ((uintptr_t)dzn & 15) == 0 && (long long)B * H * W * (C / 8) < (1LL << 31), MMG_EINVAL, "pool_relu_bwd: the NHWC output needs C % 8 == 0");
+        pool_relu_bwd_nhwc_kernel<<<mmg_grid((long long)B * H * W * (C / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(dyp, idx, yp, (__nv_bfloat16*)dzn, B, C, H, W, OH, OW);
+        MMG_LAUNCH_CHECK();
+    }
     return MMG_OK;
 }
 
@@ -538,6 +628,18 @@ extern "C" int mmg_conv_small_relu_pool_f32(const float* x, const float* w, cons
     const int OH2 = (H + 2 * pad - kh + 1) / 2, OW2 = (W + 2 * pad - kw + 1) / 2;
     MMG_REQUIRE(OH2 > 0 && OW2 > 0 && (long long)B * OH2 * OW2 < (1LL << 31), MMG_EINVAL, "conv_small_relu_pool: bad geometry");
     conv_small_relu_pool_kernel<1, 2, 2><<<mmg_grid((long long)B * OH2 * OW2, 128, 16), 128, 0, (cudaStream_t)stream>>>(x, w, bias, yp, idx, B, H, W, Co, pad, OH2, OW2);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+/* second half of the stride-1 convolution data gradient: tap columns (bf16, column (ky*kw + kx)*Ci + ci, row pitch ldc) -> dx fp32 NCHW */
+extern "C" int mmg_conv_dgrad_gather(const void* dcol, float* dx, int B, int Ci, int H, int W, int kh, int kw, int pad, long long ldc, void* stream) {
+    MMG_REQUIRE(dcol && dx && B > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && pad >= 0, MMG_EINVAL, "conv_dgrad_gather: bad argument");
+    MMG_REQUIRE(Ci == 16, MMG_EUNSUPPORTED, "conv_dgrad_gather: built for 16 input channels (GAN-DES conv2)");
+    const int OH = H + 2 * pad - kh + 1, OW = W + 2 * pad - kw + 1;
+    MMG_REQUIRE(OH > 0 && OW > 0 && ldc >= (long long)kh * kw * Ci && ldc % 8 == 0 && ((uintptr_t)dcol & 15) == 0 && (long long)B * H * W < (1LL << 31), MMG_EINVAL,
+                "conv_dgrad_gather: bad geometry");
+    conv_dgrad_gather_kernel<16><<<mmg_grid((long long)B * H * W, 128, 16), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, dx, B, H, W, OH, OW, kh, kw, pad, ldc);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }

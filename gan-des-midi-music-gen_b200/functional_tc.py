@@ -235,11 +235,23 @@ class Conv2dReluPoolTC(torch.autograd.Function):
             N.call("mmg_im2col_bf16", N.ptr(x), N.ptr(col), Nn, Ci, H, W, kh, kw, 1, pad, Kp, 1, N.stream())
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2])
-        dz = torch.empty(Nn, Co, OH, OW, device=dyp.device) if need_dx else None
+        gather = need_dx and Ci == 16 and Co % 8 == 0          # data gradient as GEMM + gather (below) instead of im2col(dz) + GEMM
+        dz = torch.empty(Nn, Co, OH, OW, device=dyp.device) if (need_dx and not gather) else None
         dzt = torch.empty(Co, Pp, device=dyp.device, dtype=_BF) if need_dw else None
-        N.call("mmg_pool_relu_bwd", N.ptr(dyp), N.ptr(idx), N.ptr(yp), N.ptr(dz), N.ptr(dzt), Nn, Co, OH, OW, Pp, N.stream())
+        dzn = torch.empty(P, Co, device=dyp.device, dtype=_BF) if gather else None
+        N.call("mmg_pool_relu_bwd", N.ptr(dyp), N.ptr(idx), N.ptr(yp), N.ptr(dz), N.ptr(dzt), N.ptr(dzn), Nn, Co, OH, OW, Pp, N.stream())
         dx = dw = db = None
-        if need_dx:
+        if gather:
+            # dx = sum over taps of (dz x W_tap) shifted back: ONE GEMM dz[p][oc] x W[(ky,kx,ci)][oc] writes the tap columns in bf16 (60 MB for
+            # the GAN-DES conv2 instead of the 119 MB im2col of dz written and read again), a gather kernel adds the nine shifted runs
+            T = kh * kw * Ci
+            wt = _cached(w, "dgradT", lambda: w.permute(2, 3, 1, 0).reshape(T, Co).contiguous())      # [(ky,kx,ci)][oc]
+            wtp = _cached(w, "dgradTp", lambda: _pack(wt, (1, T, Co), (0, 1, 2), Co))
+            dcol = torch.empty(P, T, device=dyp.device, dtype=_BF)
+            N.call("mmg_gemm_tc", N.ptr(dzn), 0, Co, N.ptr(wtp), 0, Co, N.ptr(dcol), T, P, T, Co, 0, 1, 2, 0, 0, None, 0, 0, N.stream())
+            dx = torch.empty(Nn, Ci, H, W, device=dyp.device)
+            N.call("mmg_conv_dgrad_gather", N.ptr(dcol), N.ptr(dx), Nn, Ci, H, W, kh, kw, pad, T, N.stream())
+        elif need_dx:
             K2 = Co * kh * kw
             K2p = _r16(K2)
             wf = _cached(w, "convT", lambda: w.flip(2, 3).permute(1, 0, 2, 3).reshape(Ci, K2).contiguous())

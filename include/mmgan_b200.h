@@ -103,7 +103,7 @@ int mmg_maxpool2_bwd_f32(const float* dy, const uint8_t* idx, float* dx, int64_t
  * row pitch in elements) or MN-major ([K][M]); B likewise.  dtype 0 = bf16, 1 = fp32 read as tf32 (K-major operands only).  Bases and row
  * pitches must be 16-byte aligned; M / N / K tails are zero-filled by TMA.  trans_out: element (m, n) is stored at
  * C[(m / inner) * N * inner + n * inner + m % inner] (inner = pixels per image gives NCHW, inner = M a plain transpose), else at
- * C[m * ldc + n].  split_k > 1 needs atomic = 1 and a zeroed C (bias / act then through mmg_bias_act_inplace_f32). */
+ * C[m * ldc + n]; trans_out = 2: C is a bf16 row-major matrix (plain stores only).  split_k > 1 needs atomic = 1 and a zeroed C (bias / act then through mmg_bias_act_inplace_f32). */
 int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, float* C, long long ldc, int M, int N, int K, int dtype,
                 int split_k, int trans_out, long long inner, int atomic, const float* bias, int bias_on_m, int act, void* stream);
 /* fp32 (d0,d1,d2) -> bf16 dst[i_pa * a_stride + i_pb * pitch + i_pc] with the dimensions permuted to (pa, pb, pc); columns [n_pc, pitch)
@@ -123,7 +123,11 @@ int mmg_bias_act_inplace_f32(float* y, const float* bias, long long rows, int co
  * yp / idx: (B, Co, OH/2, OW/2) pooled output and argmax codes (as mmg_maxpool2_fwd_f32), OH = H + 2 pad - kh + 1. */
 int mmg_conv_small_relu_pool_f32(const float* x, const float* w, const float* bias, float* yp, uint8_t* idx, int B, int Ci, int H, int W, int Co, int kh,
                                  int kw, int pad, void* stream);
-int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, int B, int C, int H, int W, long long Pp, void* stream);
+int mmg_pool_relu_bwd(const float* dyp, const uint8_t* idx, const float* yp, float* dz, void* dzt, void* dzn, int B, int C, int H, int W, long long Pp,
+                      void* stream);
+/* second half of a stride-1 convolution's data gradient: the tap columns dcol[b*OH*OW + p][(ky*kw + kx)*Ci + ci] (bf16, produced by mmg_gemm_tc
+ * with trans_out = 2 from dz in NHWC rows and the weights as [(ky,kx,ci)][oc]) -> dx fp32 NCHW (B, Ci, H, W), gather form.  Built for Ci = 16. */
+int mmg_conv_dgrad_gather(const void* dcol, float* dx, int B, int Ci, int H, int W, int kh, int kw, int pad, long long ldc, void* stream);
 
 /* ---- GAN-DES mel front end (GAN_DES/util.py:37-61: torchaudio MelSpectrogram + AmplitudeToDB) ----
  * mmg_stft_power_f32: wave (B, L) fp32 (row pitch wave_pitch) -> power [B*T][pitch >= 1025] fp32, T = 1 + L / hop: centred frames with

@@ -109,4 +109,5 @@ def test_gandes_entry_point_arg_checks_without_gpu():
     assert lib.mmg_conv_small_relu_pool_f32(p, p, p, p, p, 2, 3, 16, 16, 8, 2, 2, 1, None) == -2
     assert lib.mmg_stft_power_f32(p, 2, 40000, 40000, 1024, 186, p, 1028, None) == -2 and b"2048" in lib.mmg_last_error()
     assert lib.mmg_stft_power_f32(p, 2, 900, 900, 2048, 4, p, 1028, None) == -1 and b"reflect" in lib.mmg_last_error()
-    assert lib.mmg_pool_relu_bwd(p, p, p, None, None, 2, 4, 8, 8, 0, None) == -1
+    assert lib.mmg_pool_relu_bwd(p, p, p, None, None, None, 2, 4, 8, 8, 0, None) == -1
+    assert lib.mmg_conv_dgrad_gather(p, p, 2, 8, 16, 16, 3, 3, 1, 72, None) == -2
