@@ -31,6 +31,7 @@ struct GemmArgs {
     int M, N, BN;                          // BN = tile width (32 / 64 / 128 / 256)
     int a_mn, b_mn, tf32;
     int chunks, chunks_per_split;          // 128-byte K chunks: 64 bf16 or 32 tf32 elements
+    int tiles_m, tiles;                    // persistent mode (split_k == 1): a CTA walks over output tiles blockIdx.x, + gridDim.x, ... (tile = tn * tiles_m + tm)
     int stages;                            // depth of the shared-memory ring: min(GM_STAGES, chunks per CTA) -- short-K problems then fit several CTAs per SM
     float* C;
     long long ldc;
@@ -55,25 +56,31 @@ __device__ __forceinline__ void mma_tf32_ss_pred(uint32_t tmem_d, uint64_t desc_
 
 __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full;
+    __shared__ uint64_t full[GM_STAGES], empty[GM_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_s;
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * a.BN;
-    const int c0 = blockIdx.z * a.chunks_per_split;
+    // two launch shapes: split-K (grid = tiles_m x tiles_n x splits, one tile and one K range per CTA) and persistent (grid.x CTAs walk over
+    // all tiles with two TMEM accumulators: the epilogue of tile t runs under the loads and MMAs of tile t + 1)
+    const bool persistent = gridDim.z == 1 && gridDim.y == 1;
+    const int c0 = persistent ? 0 : blockIdx.z * a.chunks_per_split;
     const int nck = min(a.chunks, c0 + a.chunks_per_split) - c0;
     if (nck <= 0) return;                                                     // (split-K tail with nothing to add)
+    const int tile0 = persistent ? (int)blockIdx.x : (int)(blockIdx.y * a.tiles_m + blockIdx.x);
+    const int tile_step = persistent ? (int)gridDim.x : a.tiles;              // split-K: exactly one tile
+    const int tile_end = persistent ? a.tiles : tile0 + 1;
     const int b_bytes = a.BN * 128, stage_bytes = GM_A_BYTES + b_bytes;
     const int kelems = a.tf32 ? 32 : 64;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < GM_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(&acc_full, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_a);
         tc::tma_prefetch_desc(&map_b);
     }
-    const uint32_t tm_cols = a.BN < 32 ? 32u : (uint32_t)a.BN;
+    const uint32_t acc_cols = a.BN < 32 ? 32u : (uint32_t)a.BN;
+    const uint32_t tm_cols = persistent ? 2u * acc_cols : acc_cols;          // persistent: two accumulators (BN <= 256 -> at most all 512 columns)
     if (warp == 1) { tc::tmem_alloc(&tmem_s, tm_cols); tc::tmem_relinquish(); }
     tc::tc_fence_before();
     __syncthreads();
@@ -82,14 +89,17 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < nck; ++i) {
+            int i = 0;                                                        // chunk counter across tiles: the ring keeps rolling
+            for (int tile = tile0; tile < tile_end; tile += tile_step)
+            for (int ic = 0; ic < nck; ++ic, ++i) {
+                const int m0 = (tile % a.tiles_m) * 128, n0 = (tile / a.tiles_m) * a.BN;
                 const int stage = i % a.stages;
                 const uint32_t phase = (uint32_t)(i / a.stages) & 1u;
                 tc::mbar_wait(&empty[stage], phase ^ 1u);
                 tc::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                 unsigned char* sa = smem + stage * stage_bytes;
                 unsigned char* sb = sa + GM_A_BYTES;
-                const int kc = (c0 + i) * kelems;
+                const int kc = (c0 + ic) * kelems;
                 if (!a.a_mn) tc::tma_load_2d(sa, &map_a, &full[stage], kc, m0);                   // box (K chunk, 128 rows)
                 else {                                                                              // two boxes (64 m, 64 k rows)
                     tc::tma_load_2d(sa, &map_a, &full[stage], m0, kc);
@@ -108,7 +118,13 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_consta
                                       : tc::idesc_bf16(128, (uint32_t)a.BN, (uint32_t)a.a_mn, (uint32_t)a.b_mn);
         const uint64_t da = a.a_mn ? MN128 : KM128, db = a.b_mn ? MN128 : KM128;
         const uint32_t sa_step = a.a_mn ? 2048u : 32u, sb_step = a.b_mn ? 2048u : 32u;            // one MMA = 16 bf16 / 8 tf32 K elements = 32 B, or 16 K rows
-        for (int i = 0; i < nck; ++i) {
+        int i = 0, it = 0;
+        for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t tacc = tmem + (uint32_t)buf * acc_cols;
+        tc::mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);        // the epilogue has drained this accumulator (first two uses: free)
+        tc::tc_fence_after();
+        for (int ic = 0; ic < nck; ++ic, ++i) {
             const int stage = i % a.stages;
             const uint32_t phase = (uint32_t)(i / a.stages) & 1u;
             tc::mbar_wait(&full[stage], phase);
@@ -116,22 +132,28 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_consta
             const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes), sb = sa + GM_A_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (a.tf32) mma_tf32_ss_pred(tmem, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (i | k) != 0, leader);
-                else tc::mma_f16_ss_pred(tmem, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (i | k) != 0, leader);
+                if (a.tf32) mma_tf32_ss_pred(tacc, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (ic | k) != 0, leader);
+                else tc::mma_f16_ss_pred(tacc, tc::smem_desc(da, sa + k * sa_step), tc::smem_desc(db, sb + k * sb_step), idesc, (ic | k) != 0, leader);
             }
             tc::mma_commit_pred(&empty[stage], leader);
         }
-        tc::mma_commit_pred(&acc_full, leader);
+        tc::mma_commit_pred(&acc_full[buf], leader);
+        }
     } else {
         const int q = warp & 3;                                                                     // TMEM lane quadrant of this warp
+        int it = 0;
+        for (int tile = tile0; tile < tile_end; tile += tile_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t tacc = tmem + (uint32_t)buf * acc_cols;
+        const int m0 = (tile % a.tiles_m) * 128, n0 = (tile / a.tiles_m) * a.BN;
         const int m = m0 + q * 32 + lane;
-        tc::mbar_wait(&acc_full, 0);
+        tc::mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
         tc::tc_fence_after();
         const long long mo = a.trans_out ? (long long)(m / a.inner) * (long long)a.N * a.inner + (m % a.inner) : (long long)m * a.ldc;
         const float bm = (a.bias && a.bias_on_m && m < a.M) ? a.bias[m] : 0.f;
         for (int c = 0; c < a.BN; c += 32) {
             uint32_t r[32];
-            tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            tc::tmem_ld_32x32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             tc::tmem_ld_wait();
             if (a.out_bf16) {
                 // bf16 row-major output (the tap columns of a convolution data gradient): 32 columns = four 16-byte stores
@@ -181,7 +203,11 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tc_kernel(const __grid_consta
             }
         }
         tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);                   // this warp has read its lanes of the accumulator
+        }
     }
+    tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem, tm_cols);
 }
@@ -519,14 +545,27 @@ extern "C" int mmg_gemm_tc(const void* A, int a_mn, long long lda, const void* B
     if (!b_mn) r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * esz, (uint32_t)kelems, (uint32_t)a.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     else r = tc::make_map_2d(&map_b, dt, esz, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * esz, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     MMG_REQUIRE(r == 0, MMG_EINVAL, "gemm_tc: cuTensorMapEncodeTiled(B) failed (%d)", r);
-    a.stages = a.chunks_per_split < GM_STAGES ? a.chunks_per_split : GM_STAGES;
+    a.tiles_m = (M + 127) / 128;
+    const int tiles_n = (N + a.BN - 1) / a.BN;
+    a.tiles = a.tiles_m * tiles_n;
+    a.stages = split_k == 1 ? GM_STAGES : (a.chunks_per_split < GM_STAGES ? a.chunks_per_split : GM_STAGES);
+    if (split_k == 1 && a.chunks < GM_STAGES && a.tiles <= 2 * MMG_NUM_SMS) a.stages = a.chunks;      // few tiles: no ring to keep rolling
     const int smem = 1024 + a.stages * (GM_A_BYTES + a.BN * 128);
     static bool attr_done = false;
     if (!attr_done) {
         MMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + GM_STAGES * (GM_A_BYTES + 256 * 128)));
         attr_done = true;
     }
-    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + a.BN - 1) / a.BN), (unsigned)split_k);
+    dim3 grid((unsigned)a.tiles_m, (unsigned)tiles_n, (unsigned)split_k);
+    if (split_k == 1) {                                    // persistent: as many CTAs as fit (shared memory, 512 TMEM columns), each walks over tiles
+        int per_sm = (227 * 1024) / smem;
+        const int by_tmem = 512 / (2 * (a.BN < 32 ? 32 : a.BN));
+        if (per_sm > by_tmem) per_sm = by_tmem;
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        const int ctas = a.tiles < per_sm * MMG_NUM_SMS ? a.tiles : per_sm * MMG_NUM_SMS;
+        grid = dim3((unsigned)ctas, 1, 1);
+    }
     gemm_tc_kernel<<<grid, GM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
