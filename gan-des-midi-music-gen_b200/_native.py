@@ -86,6 +86,7 @@ SIGNATURES.update({
     "mmg_gen_packed_weight_bytes": (_Z, [_I, _I]),
     "mmg_gen_pack_weight": (_I, [_P, _I, _I, _P, _P]),
     "mmg_gen_layer_fwd": (_I, [ctypes.POINTER(GenLayerArgs), _P]),
+    "mmg_gen_set_worker_groups": (_I, [_I]),
     "mmg_gen_layer_stats_gram_workspace": (_Z, []),
     "mmg_gen_layer_stats_gram": (_I, [_P, _L, _I, _P, _L, _P, _P, _F, _P, _P, _I, _P, _P, _Z, _P]),
 })

@@ -16,6 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 FLAGS.remove("--use_fast_math=false")
+FLAGS += os.environ.get("MMG_NVCC_EXTRA", "").split()      # e.g. -DMMG_ABLATION for the experiment switches (never in a shipped build)
 
 
 def sources():

@@ -21,8 +21,9 @@
 
 namespace {
 
-constexpr int GT_WORKERS = 256;
-constexpr int GT_THREADS = 64 + GT_WORKERS;     // warp 0 TMA, warp 1 MMA, warps 2-9 builders + epilogue (two warps per TMEM lane quadrant)
+// warp 0 TMA, warp 1 MMA, then WG groups of four builder / epilogue warps (one warp per TMEM lane quadrant in each group; the groups take
+// alternate 32-column chunks of an accumulator and alternate feature slices of the A tile).  WG = 2 or 4: the epilogue is latency-bound
+// (MUFU, tcgen05.ld, the staging barriers), so more resident warps is what speeds it up.
 constexpr int GT_MAX_K = 256;
 constexpr int GT_A_CHUNK = 128 * 128;           // 128 rows x 64 bf16
 constexpr int GT_W_STAGES = 2;
@@ -39,6 +40,7 @@ struct GenDev {
     const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
     float momentum, eps; int update_running;
     long long M; int row_tiles;
+    int col_cache;                              // y_out only: scale / shift of every column group of this CTA are derived ONCE, before its first item
     double cnt;                                 // rows behind the batch sums (= M, or the global batch under SyncBN)
 };
 
@@ -83,8 +85,19 @@ __device__ __forceinline__ void bn_scale_shift(double s1, double s2, double coun
     var_f = (float)var;
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
-                                                                     const GenDev a) {
+#ifdef MMG_ABLATION
+__device__ long long g_gen_stamps[3][32][4];      // [role: producer / MMA / worker 0][item of CTA 0][event]
+#define GEN_STAMP(role, it, ev) do { if (blockIdx.x == 0 && (it) < 32) g_gen_stamps[role][it][ev] = clock64(); } while (0)
+#else
+#define GEN_STAMP(role, it, ev) do {} while (0)
+#endif
+
+template <int WG>
+__global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
+                                                                        const GenDev a) {
+    constexpr int GT_WORKERS = WG * 128, GT_THREADS = 64 + GT_WORKERS;
+    constexpr int PER = 64 / WG;                // features of a 64-feature chunk built by one thread
+    constexpr int NSTG = 4 / WG;                // output staging buffers per warp group (4 x 16 KB per CTA either way)
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t wfull[GT_W_STAGES], wempty[GT_W_STAGES], aready, tfull[2], tempty[2];
     __shared__ uint32_t tmem_s;
@@ -95,9 +108,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
     unsigned char* smem_a = smem;                                   // kchunks x 16 KB
     const int w_stage_bytes = kchunks * a.NG * 128;
     unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // GT_W_STAGES x w_stage_bytes
-    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // 2 warp groups x 2 x 16 KB output staging (only when y_out)
+    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // WG warp groups x NSTG x 16 KB output staging (only when y_out)
+    float* smem_part = reinterpret_cast<float*>(smem_y + (a.y_out ? 4 * GT_Y_STAGE : 0));      // [4 lane quadrants][sum | sumsq][NG] (only when out_sums)
+    float* col_scale = smem_part;                                   // col_cache: [n_groups * NG] scale then [n_groups * NG] shift (never together with out_sums)
+    float* col_shift = smem_part + a.n_groups * a.NG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // items = (row tile, column group) pairs, column group fastest; a CTA owns a CONTIGUOUS range, so it changes its row tile (= rebuilds
+    // its A operand) at most once or twice per launch
     const int items = a.row_tiles * a.n_groups;
+    const int item_begin = (int)((long long)blockIdx.x * items / gridDim.x), item_end = (int)((long long)(blockIdx.x + 1) * items / gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < GT_W_STAGES; ++i) { tc::mbar_init(&wfull[i], 1); tc::mbar_init(&wempty[i], 1); }
@@ -136,10 +155,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&map_w);
             int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+            for (int item = item_begin; item < item_end; ++item, ++it) {
                 const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
                 const int grp = item % a.n_groups;
+                GEN_STAMP(0, it, 0);
                 tc::mbar_wait(&wempty[stage], phase ^ 1);
+                GEN_STAMP(0, it, 1);
                 tc::mbar_expect_tx(&wfull[stage], w_stage_bytes);
                 for (int c = 0; c < kchunks; ++c)
                     tc::tma_load_2d(smem_w + stage * w_stage_bytes + c * a.NG * 128, &map_w, &wfull[stage], c * 64, grp * a.NG);
@@ -151,12 +172,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
             const uint32_t idesc = tc::idesc_bf16(128, (uint32_t)a.NG);
             const uint32_t a_addr = tc::smem_u32(smem_a), w_addr = tc::smem_u32(smem_w);
             int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+            for (int item = item_begin; item < item_end; ++item, ++it) {
                 const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                GEN_STAMP(1, it, 0);
                 tc::mbar_wait(&aready, it & 1);
+                GEN_STAMP(1, it, 1);
                 tc::mbar_wait(&wfull[stage], phase);
+                GEN_STAMP(1, it, 2);
                 tc::tc_fence_after();
                 const uint32_t wb = w_addr + stage * w_stage_bytes;
                 for (int c = 0; c < kchunks; ++c)
@@ -166,88 +190,157 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                                        tc::smem_desc(KM128, wb + c * a.NG * 128 + k * 32), idesc, (c | k) != 0);
                 tc::mma_commit(&wempty[stage]);
                 tc::mma_commit(&tfull[acc]);
+                GEN_STAMP(1, it, 3);
             }
         }
     } else {
         const int q = warp & 3, h = (warp - 2) >> 2, t = q * 32 + lane;     // t = row of the tile = TMEM lane; h = which half of the columns / features
-        const int et = threadIdx.x - 64;                                    // 0..255 over the builder/epilogue threads
+        const int et = threadIdx.x - 64;                                    // 0 .. GT_WORKERS - 1 over the builder/epilogue threads
         const int eg = et & 127;                                            // index inside the warp group h
-        // ---- A-tile builder: row t of row tile `rt`, features [32h, 32h + 32) of every 64-feature chunk, swizzled 16-byte pieces
+        // ---- A-tile builder: row t of row tile `rt`, features [PER h, PER h + PER) of every 64-feature chunk, swizzled 16-byte pieces
         auto build = [&](int rt) {
             const long long row = (long long)rt * 128 + t;
             const bool live = row < a.M;
             for (int c = 0; c < kchunks; ++c) {
                 const uint32_t dst = tc::smem_u32(smem_a) + c * GT_A_CHUNK + t * 128;
-                const int kb = c * 64 + 32 * h;
-                float v[32];                                       // all of the loads are issued before any is used
+                const int kb = c * 64 + PER * h;
+                float v[PER];                                      // all of the loads are issued before any is used
                 if (a.in_mode == 0) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < PER; ++e) {
                         const int kk = kb + e;
                         v[e] = !live ? 0.f : (kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < a.K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f));
                     }
                 } else {                                           // K is a multiple of 8 here (checked on the host)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < PER / 4; ++j) {
                         const int k = kb + j * 4;
                         const float4 p = (live && k < a.K) ? *reinterpret_cast<const float4*>(a.x0 + row * a.K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                         v[4 * j] = p.x; v[4 * j + 1] = p.y; v[4 * j + 2] = p.z; v[4 * j + 3] = p.w;
                     }
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < PER; ++e) {
                         const int k = kb + e;
                         v[e] = (live && k < a.K) ? fast_sigmoid_affine(v[e], in_scale[k], in_shift[k]) : 0.f;
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tc::sts128(dst + (((4 * h + j) ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                for (int j = 0; j < PER / 8; ++j)
+                    tc::sts128(dst + ((((PER / 8) * h + j) ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                                                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&aready);
         };
-        int it = 0, ychunk = 0;
-        int item = blockIdx.x;
-        if (item < items) build(item / a.n_groups);
-        for (; item < items; item += gridDim.x, ++it) {
-            const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int rt = item / a.n_groups, grp = item % a.n_groups, n0 = grp * a.NG;
-            // per-item column constants (bias; output-side BN folded to scale/shift)
-            asm volatile("bar.sync 3, 256;" ::: "memory");        // previous item's epilogue no longer reads ep_*
-            for (int c = et; c < a.NG; c += GT_WORKERS) {
-                const int n = n0 + c;
-                ep_bias[c] = (n < a.N && a.bias) ? a.bias[n] : 0.f;
-                if (a.y_out) {
-                    float sc = 0.f, sh = 0.f;
-                    if (n < a.N) {
-                        if (a.out_mode == 1) {
-                            float mu, var;
-                            bn_scale_shift(a.y_sums[n], a.y_sums[a.N + n], a.cnt, a.out_gamma[n], a.out_beta[n], a.eps, sc, sh, mu, var);
-                            if (a.update_running && rt == 0 && a.out_run_mean) {       // exactly one item owns (row tile 0, column n)
-                                const float unb = var * (float)(a.cnt / (a.cnt - 1.0));
-                                a.out_run_mean[n] = (1.f - a.momentum) * a.out_run_mean[n] + a.momentum * mu;
-                                a.out_run_var[n] = (1.f - a.momentum) * a.out_run_var[n] + a.momentum * unb;
-                            }
-                        } else {
-                            const float invstd = rsqrtf(a.out_run_var[n] + a.eps);
-                            sc = a.out_gamma[n] * invstd;
-                            sh = a.out_beta[n] - a.out_run_mean[n] * sc;
-                        }
+        // output-side BatchNorm of column n folded to y = sigmoid(acc * scale + shift) (bias folded in; both pre-multiplied by -log2 e);
+        // `owner` = this call makes the one running-statistics update of the column
+        auto column_constants = [&](int n, bool owner, float bias, float& scale, float& shift) {
+            float sc = 0.f, sh = 0.f;
+            if (n < a.N) {
+                if (a.out_mode == 1) {
+                    float mu, var;
+                    bn_scale_shift(a.y_sums[n], a.y_sums[a.N + n], a.cnt, a.out_gamma[n], a.out_beta[n], a.eps, sc, sh, mu, var);
+                    if (a.update_running && owner && a.out_run_mean) {
+                        const float unb = var * (float)(a.cnt / (a.cnt - 1.0));
+                        a.out_run_mean[n] = (1.f - a.momentum) * a.out_run_mean[n] + a.momentum * mu;
+                        a.out_run_var[n] = (1.f - a.momentum) * a.out_run_var[n] + a.momentum * unb;
                     }
-                    ep_scale[c] = sc * NEG_LOG2E;                  // bias folded in: (acc + b) * sc + sh = acc * sc + (b * sc + sh)
-                    ep_shift[c] = (ep_bias[c] * sc + sh) * NEG_LOG2E;
+                } else {
+                    const float invstd = rsqrtf(a.out_run_var[n] + a.eps);
+                    sc = a.out_gamma[n] * invstd;
+                    sh = a.out_beta[n] - a.out_run_mean[n] * sc;
                 }
             }
-            asm volatile("bar.sync 3, 256;" ::: "memory");
+            scale = sc * NEG_LOG2E;                                  // (acc + b) * sc + sh = acc * sc + (b * sc + sh)
+            shift = (bias * sc + sh) * NEG_LOG2E;
+        };
+        int it = 0, ychunk = 0;
+        int item = item_begin;
+        if (item < item_end) build(item / a.n_groups);
+        if (a.col_cache) {
+            // the per-item derivation (five dependent global loads + fp64 arithmetic between two CTA-wide barriers) cost 4.4 K of an item's 15 K
+            // cycles.  The groups of a contiguous item range are those of its first min(items, n_groups) items, and exactly one CTA meets
+            // (row tile 0, group g) = the owner of the running-statistics update.  Four columns per thread and step: all loads of a step are
+            // issued before the first fp64 operation; reciprocal count and rsqrt instead of two fp64 divisions and a square root per column.
+            // (A variant that derived the next item's group inside every item's epilogue needed a CTA-wide barrier per item, which couples the
+            // warp groups again: 96 us instead of 81.)
+            const int total = min(item_end - item_begin, a.n_groups) * a.NG;
+            const double inv_cnt = 1.0 / a.cnt;
+            const float unb_f = (float)(a.cnt / (a.cnt - 1.0));
+            for (int base = et; base < total; base += 4 * GT_WORKERS) {
+                double p0[4], p1[4];
+                float ga[4], be[4], bi[4], rm[4], rv[4];
+                int nn[4];
+                bool own[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * GT_WORKERS;
+                    const int itm = item_begin + i / a.NG, n = (itm % a.n_groups) * a.NG + i % a.NG;
+                    nn[u] = (i < total) ? n : -1;
+                    own[u] = a.out_mode == 1 && a.update_running && a.out_run_mean && itm / a.n_groups == 0;
+                    const bool live = i < total && n < a.N;
+                    p0[u] = p1[u] = 0.0; ga[u] = be[u] = bi[u] = rm[u] = rv[u] = 0.f;
+                    if (live) {
+                        if (a.out_mode == 1) { p0[u] = a.y_sums[n]; p1[u] = a.y_sums[a.N + n]; }
+                        if (a.out_mode != 1 || own[u]) { rm[u] = a.out_run_mean[n]; rv[u] = a.out_run_var[n]; }
+                        ga[u] = a.out_gamma[n]; be[u] = a.out_beta[n];
+                        bi[u] = a.bias ? a.bias[n] : 0.f;
+                    } else own[u] = false;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (nn[u] < 0) continue;
+                    float sc = 0.f, sh = 0.f;
+                    if (nn[u] < a.N) {
+                        if (a.out_mode == 1) {
+                            const double mu = p0[u] * inv_cnt;
+                            double var = p1[u] * inv_cnt - mu * mu;
+                            if (var < 0) var = 0;
+                            sc = ga[u] * (float)rsqrt(var + (double)a.eps);
+                            sh = be[u] - (float)mu * sc;
+                            if (own[u]) {
+                                a.out_run_mean[nn[u]] = (1.f - a.momentum) * rm[u] + a.momentum * (float)mu;
+                                a.out_run_var[nn[u]] = (1.f - a.momentum) * rv[u] + a.momentum * ((float)var * unb_f);
+                            }
+                        } else {
+                            sc = ga[u] * rsqrtf(rv[u] + a.eps);
+                            sh = be[u] - rm[u] * sc;
+                        }
+                    }
+                    col_scale[nn[u]] = sc * NEG_LOG2E;                // (acc + b) * sc + sh = acc * sc + (b * sc + sh)
+                    col_shift[nn[u]] = (bi[u] * sc + sh) * NEG_LOG2E;
+                }
+            }
+            asm volatile("bar.sync 7, %0;" ::"n"(GT_WORKERS) : "memory");
+        }
+        for (; item < item_end; ++item, ++it) {
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int rt = item / a.n_groups, grp = item % a.n_groups, n0 = grp * a.NG;
+            // per-item column constants (bias; output-side BN folded to scale/shift) unless they were derived up front
+            const float* scp = ep_scale;
+            const float* shp = ep_shift;
+            if (a.col_cache) { scp = col_scale + n0; shp = col_shift + n0; }
+            else {
+                asm volatile("bar.sync 7, %0;" ::"n"(GT_WORKERS) : "memory");      // previous item's epilogue no longer reads ep_*
+                for (int c = et; c < a.NG; c += GT_WORKERS) {
+                    const int n = n0 + c;
+                    ep_bias[c] = (n < a.N && a.bias) ? a.bias[n] : 0.f;
+                    if (a.y_out) column_constants(n, rt == 0, ep_bias[c], ep_scale[c], ep_shift[c]);      // exactly one item owns (row tile 0, column n)
+                }
+                asm volatile("bar.sync 7, %0;" ::"n"(GT_WORKERS) : "memory");
+            }
+            if (et == 0) GEN_STAMP(2, it, 0);
             tc::mbar_wait(&tfull[acc], acc_phase);
+            if (et == 0) GEN_STAMP(2, it, 1);
             tc::tc_fence_after();
             // the MMAs of this item are complete: the A buffer is free, build the next item's tile so its MMAs overlap this epilogue
-            const int next = item + gridDim.x;
-            if (next < items) build(next / a.n_groups);
+            if (item + 1 < item_end) {
+                if ((item + 1) / a.n_groups != rt) build((item + 1) / a.n_groups);
+                else tc::mbar_arrive(&aready);                       // same row tile: the operand in shared memory stays
+            }
             const long long row = (long long)rt * 128 + t;
             const bool live = row < a.M;
-            for (int c0 = 32 * h; c0 < a.NG; c0 += 64) {              // the two warps of a lane quadrant take alternate 32-column chunks
+            for (int c0 = 32 * h; c0 < a.NG; c0 += 32 * WG) {         // the WG warps of a lane quadrant take alternate 32-column chunks
                 uint32_t r[32];
                 tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, r);
                 tc::tmem_ld_wait();
@@ -273,13 +366,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
                 }
                 if (a.y_out) {
                     // y tile (128 rows x 32 fp32) -> 128-byte-swizzled staging buffer -> one TMA store (rows >= M and columns >= N are clipped)
-                    unsigned char* stg = smem_y + (2 * h + (ychunk & 1)) * GT_Y_STAGE;
-                    if (eg == 0) tc::bulk_wait_group_read<1>();        // the store this warp group issued from this buffer two chunks ago has read it
+                    unsigned char* stg = smem_y + (NSTG * h + (ychunk % NSTG)) * GT_Y_STAGE;
+                    if (eg == 0) tc::bulk_wait_group_read<NSTG - 1>(); // the store this warp group issued from this buffer NSTG chunks ago has read it
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
                     float y[32];
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 sc = reinterpret_cast<const float4*>(ep_scale + c0)[e4], sh = reinterpret_cast<const float4*>(ep_shift + c0)[e4];
+                        const float4 sc = reinterpret_cast<const float4*>(scp + c0)[e4], sh = reinterpret_cast<const float4*>(shp + c0)[e4];
                         y[4 * e4] = fast_sigmoid_affine(__uint_as_float(r[4 * e4]), sc.x, sh.x);
                         y[4 * e4 + 1] = fast_sigmoid_affine(__uint_as_float(r[4 * e4 + 1]), sc.y, sh.y);
                         y[4 * e4 + 2] = fast_sigmoid_affine(__uint_as_float(r[4 * e4 + 2]), sc.z, sh.z);
@@ -302,15 +395,28 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gen_layer_tc_kernel(const __gri
 #pragma unroll
                     for (int e = 0; e < 32; ++e) { s1[e] = live ? z[e] : 0.f; s2[e] = s1[e] * s1[e]; }
                     const float c1 = colsum32(s1, lane), c2 = colsum32(s2, lane);
-                    if (lane < ncols) {
-                        atomicAdd(&a.out_sums[n0 + c0 + lane], (double)c1);
-                        atomicAdd(&a.out_sums[a.N + n0 + c0 + lane], (double)c2);
+                    smem_part[(2 * q) * a.NG + c0 + lane] = c1;      // 32-row partial of this warp; the four quadrants are combined below
+                    smem_part[(2 * q + 1) * a.NG + c0 + lane] = c2;
+                }
+            }
+            if (a.out_sums) {
+                // one fp64 atomic per column and CTA instead of one per warp: same-address atomics serialise in L2 (128 row tiles x 4 warps on
+                // each of the 2 N addresses cost ~15 us per layer; the in-CTA combine of the four 32-row partials is done in fp64 as before)
+                asm volatile("bar.sync 7, %0;" ::"n"(GT_WORKERS) : "memory");
+                for (int c = et; c < 2 * a.NG; c += GT_WORKERS) {
+                    const int which = c >= a.NG ? 1 : 0, col = c - which * a.NG;
+                    if (n0 + col < a.N) {
+                        const double v = ((double)smem_part[which * a.NG + col] + (double)smem_part[(2 + which) * a.NG + col]) +
+                                         ((double)smem_part[(4 + which) * a.NG + col] + (double)smem_part[(6 + which) * a.NG + col]);
+                        atomicAdd(&a.out_sums[which * a.N + n0 + col], v);
                     }
                 }
             }
             tc::tc_fence_before();
             __syncwarp();
+            if (et == 0) GEN_STAMP(2, it, 2);
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+
         }
         if (eg == 0) tc::bulk_wait_group_read<0>();                // staging buffers must outlive the last TMA store's reads
     }
@@ -327,6 +433,8 @@ __global__ void gen_pack_weights_kernel(const float* __restrict__ w, int N, int 
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int g_worker_groups = 2;                           // builder / epilogue warp groups of gen_layer_tc_kernel (mmg_gen_set_worker_groups)
 
 // ------------------------------------------------------------------------------------------------
 // Analytic batch statistics of a WIDE layer fed by a NARROW one (the generator's 64 -> 4096 output layer): z = a W^T + b, so
@@ -501,6 +609,18 @@ int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double
     return MMG_OK;
 }
 
+// process-wide tuning switch: 2 or 4 groups of four builder / epilogue warps per CTA (default 2: measured equal or faster, B = 16 384); returns
+// the previous value
+int mmg_gen_set_worker_groups(int groups) {
+    const int prev = g_worker_groups;
+    if (groups == 2 || groups == 4) g_worker_groups = groups;
+    return prev;
+}
+
+#ifdef MMG_ABLATION
+int mmg_gen_get_stamps(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_gen_stamps, sizeof(long long) * 3 * 32 * 4); }
+#endif
+
 int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     MMG_REQUIRE(p && p->x0 && p->w_packed && p->M > 0 && p->N > 0 && p->k0 > 0 && p->k1 >= 0, MMG_EINVAL, "gen_layer_fwd: bad arguments");
     const int K = p->k0 + p->k1;
@@ -537,7 +657,13 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     MMG_REQUIRE(tc::make_map_2d_bf16(&map_w, p->w_packed, (uint64_t)a.Kp, (uint64_t)Np, (uint64_t)a.Kp * 2, 64, (uint32_t)a.NG, CU_TENSOR_MAP_SWIZZLE_128B) == 0,
                 MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(w) failed");
     const int kchunks = a.Kp / 64;
-    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 4 * GT_Y_STAGE : 0);
+    const int wg = g_worker_groups;
+    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 4 * GT_Y_STAGE : 0) +
+                  (p->out_sums ? (size_t)8 * a.NG * sizeof(float) : 0);
+    // a pure y pass (the wide output layer) keeps scale / shift of all its columns in shared memory when they fit
+    const size_t cache = (size_t)2 * a.n_groups * a.NG * sizeof(float);
+    a.col_cache = p->y_out && !p->z_out && !p->out_sums && smem + cache <= 220 * 1024;
+    if (a.col_cache) smem += cache;
     CUtensorMap map_y = map_w;
     if (p->y_out) {
         MMG_REQUIRE(((uintptr_t)p->y_out & 15) == 0 && (p->N & 3) == 0, MMG_EUNSUPPORTED, "gen_layer_fwd: y_out must be 16-byte aligned with N % 4 == 0");
@@ -548,8 +674,14 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
     MMG_REQUIRE(smem <= 220 * 1024, MMG_EUNSUPPORTED, "gen_layer_fwd: tile does not fit shared memory");
     const long long items = row_tiles * a.n_groups;
     const int grid = (int)(items < MMG_NUM_SMS ? items : MMG_NUM_SMS);
-    MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    gen_layer_tc_kernel<<<grid, GT_THREADS, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    if (wg == 4) gen_layer_tc_kernel<4><<<grid, 64 + 4 * 128, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
+    else gen_layer_tc_kernel<2><<<grid, 64 + 2 * 128, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
     MMG_LAUNCH_CHECK();
     return MMG_OK;
 }
