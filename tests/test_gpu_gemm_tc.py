@@ -263,10 +263,11 @@ def test_gandes_loop_body_on_tensor_cores(golden_dir):
     assert max(rep.values()) < 1.5e-2, rep
 
 
-@pytest.mark.parametrize("tcores", [False, True])
-def test_gandes_trainer_graph_replay_matches_module_loop(tcores):
+@pytest.mark.parametrize("tcores,batched", [(False, True), (True, True), (True, False)])
+def test_gandes_trainer_graph_replay_matches_module_loop(tcores, batched):
     """GANDESTrainer (segments of SIMNN.py:275-334, captured into CUDA graphs on the second call) against the same loop written with the
-    modules, FusedAdam and the fused BCE: identical kernels, so losses agree to fp32 atomics noise and the weights follow the same trajectory."""
+    modules, FusedAdam and the fused BCE: identical kernels, so losses agree to fp32 atomics noise and the weights follow the same trajectory.
+    ``batched``: the trainer's D step sends real and fake through the discriminator as one batch of 2B (no BatchNorm in D: same logits, same gradients)."""
     from gan_des_midi_music_gen_b200.GAN_DES import SIMNN
     from gan_des_midi_music_gen_b200 import optim as fo
     from gan_des_midi_music_gen_b200.gandes_trainer import GANDESTrainer
@@ -295,7 +296,7 @@ def test_gandes_trainer_graph_replay_matches_module_loop(tcores):
                 gl = crit(disc(fake).squeeze(), torch.ones(B, device=DEV))
                 losses.append((dl.item(), gl.item()))
         else:
-            tr = GANDESTrainer(gen, disc, lr=2e-4, betas=(0.5, 0.999))
+            tr = GANDESTrainer(gen, disc, lr=2e-4, betas=(0.5, 0.999), batch_d_passes=batched)
             for it in range(5):
                 gm = tr.generate(noise)
                 dl = tr.d_step(real, fake)
