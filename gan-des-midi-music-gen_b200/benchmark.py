@@ -187,13 +187,13 @@ def _gandes_leg(device):
     alg_bytes = 3 * (3 * act) + 9 * 128 * 55296 * 4 + 7.1e6 * 28
     peaks = _peaks()
     return {"spectrograms_per_sec": B / sec, "ms_per_step": sec * 1e3, "batch": B, "dtype": "bf16 operands, fp32 accumulation (tcgen05)",
-            "launches_per_step": launches, "api": "gandes_trainer.GANDESTrainer: generate / d_step / g_step, each replayed from its CUDA graph",
+            "launches_per_step": launches, "api": "gandes_trainer.GANDESTrainer: generate / d_step / g_step, each replayed from its CUDA graph; the D step runs real and fake as one batch of 2B (no BatchNorm in D: same logits and gradients)",
             "module_loop": {"ms_per_step": res["tensor_cores"][0] * 1e3, "spectrograms_per_sec": B / res["tensor_cores"][0], "launches_per_step": res["tensor_cores"][1],
                             "api": "the reference's loop written with the drop-in modules (enable_tensor_cores), FusedAdam and the fused BCE, eager launches"},
             "fp32_simt": {"ms_per_step": res["fp32_simt"][0] * 1e3, "spectrograms_per_sec": B / res["fp32_simt"][0], "launches_per_step": res["fp32_simt"][1]},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes": alg_bytes, "traffic": None, "peak_src": peaks["src"],
-                         "note": "whole iteration (about 150 small launches at B = 30: launch latency, not bandwidth, bounds it)"},
+                         "note": "whole iteration (about 90 small dependent launches at B = 30: launch latency, not bandwidth, bounds it)"},
             "cpu_baseline": {"value": B / cs, "unit": "spectrograms/s", "cores": os.cpu_count() or 1, "kind": "port",
                              "sample": f"{n} iterations of batch {B} through oracle/mmgan_oracle.gandes_iteration"}}
 
