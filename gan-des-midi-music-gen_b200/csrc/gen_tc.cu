@@ -28,7 +28,6 @@ constexpr int GT_MAX_K = 256;
 constexpr int GT_A_CHUNK = 128 * 128;           // 128 rows x 64 bf16
 constexpr int GT_W_STAGES = 2;
 constexpr int GT_Y_STAGE = 128 * 128;           // 128 rows x 32 fp32
-constexpr int GT_SMEM_MIN = 120 * 1024;         // keeps one CTA per SM (every CTA allocates all 512 TMEM columns)
 
 struct GenDev {
     const float* x0; const float* x1; int k0, k1;
@@ -40,6 +39,8 @@ struct GenDev {
     const double* y_sums; const float* out_gamma; const float* out_beta; float* out_run_mean; float* out_run_var;
     float momentum, eps; int update_running;
     long long M; int row_tiles;
+    int w_stages;                               // weight ring depth: 1 when every CTA has a single item (the hidden layers at B <= 148 row tiles), else 2
+    int tm_cols, acc_stride;                    // TMEM columns allocated (one accumulator of NG columns, or two) and the distance between the two
     int col_cache;                              // y_out only: scale / shift of every column group of this CTA are derived ONCE, before its first item
     double cnt;                                 // rows behind the batch sums (= M, or the global batch under SyncBN)
 };
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
     const int kchunks = a.Kp / 64;
     unsigned char* smem_a = smem;                                   // kchunks x 16 KB
     const int w_stage_bytes = kchunks * a.NG * 128;
-    unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // GT_W_STAGES x w_stage_bytes
-    unsigned char* smem_y = smem_w + GT_W_STAGES * w_stage_bytes;   // WG warp groups x NSTG x 16 KB output staging (only when y_out)
+    unsigned char* smem_w = smem + kchunks * GT_A_CHUNK;            // w_stages x w_stage_bytes
+    unsigned char* smem_y = smem_w + a.w_stages * w_stage_bytes;   // WG warp groups x NSTG x 16 KB output staging (only when y_out)
     float* smem_part = reinterpret_cast<float*>(smem_y + (a.y_out ? 4 * GT_Y_STAGE : 0));      // [4 lane quadrants][sum | sumsq][NG] (only when out_sums)
     float* col_scale = smem_part;                                   // col_cache: [n_groups * NG] scale then [n_groups * NG] shift (never together with out_sums)
     float* col_shift = smem_part + a.n_groups * a.NG;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
         tc::mbar_init(&aready, GT_WORKERS);
         tc::fence_barrier_init();
     }
-    if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
+    if (warp == 1) { tc::tmem_alloc(&tmem_s, (uint32_t)a.tm_cols); tc::tmem_relinquish(); }
     // input-side BatchNorm folded to scale/shift (every CTA needs all K features; CTA 0 also updates the running stats)
     if (a.in_mode != 0) {
         for (int k = threadIdx.x; k < a.K; k += GT_THREADS) {
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
             tc::tma_prefetch_desc(&map_w);
             int it = 0;
             for (int item = item_begin; item < item_end; ++item, ++it) {
-                const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
+                const int stage = it % a.w_stages, phase = (it / a.w_stages) & 1;
                 const int grp = item % a.n_groups;
                 GEN_STAMP(0, it, 0);
                 tc::mbar_wait(&wempty[stage], phase ^ 1);
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
             const uint32_t a_addr = tc::smem_u32(smem_a), w_addr = tc::smem_u32(smem_w);
             int it = 0;
             for (int item = item_begin; item < item_end; ++item, ++it) {
-                const int stage = it % GT_W_STAGES, phase = (it / GT_W_STAGES) & 1;
+                const int stage = it % a.w_stages, phase = (it / a.w_stages) & 1;
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 GEN_STAMP(1, it, 0);
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
                 for (int c = 0; c < kchunks; ++c)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc::mma_f16_ss(tmem + acc * 256, tc::smem_desc(KM128, a_addr + c * GT_A_CHUNK + k * 32),
+                        tc::mma_f16_ss(tmem + acc * a.acc_stride, tc::smem_desc(KM128, a_addr + c * GT_A_CHUNK + k * 32),
                                        tc::smem_desc(KM128, wb + c * a.NG * 128 + k * 32), idesc, (c | k) != 0);
                 tc::mma_commit(&wempty[stage]);
                 tc::mma_commit(&tfull[acc]);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
             const bool live = row < a.M;
             for (int c0 = 32 * h; c0 < a.NG; c0 += 32 * WG) {         // the WG warps of a lane quadrant take alternate 32-column chunks
                 uint32_t r[32];
-                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, r);
+                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * a.acc_stride + c0, r);
                 tc::tmem_ld_wait();
                 float z[32];
                 if (a.z_out || a.out_sums) {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(64 + WG * 128, 1) gen_layer_tc_kernel(const __
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+    if (warp == 1) tc::tmem_dealloc(tmem, (uint32_t)a.tm_cols);
 }
 
 __global__ void gen_pack_weights_kernel(const float* __restrict__ w, int N, int K, int Np, int Kp, __nv_bfloat16* __restrict__ out) {
@@ -434,7 +435,7 @@ __global__ void gen_pack_weights_kernel(const float* __restrict__ w, int N, int 
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-int g_worker_groups = 2;                           // builder / epilogue warp groups of gen_layer_tc_kernel (mmg_gen_set_worker_groups)
+int g_worker_groups = 4;                           // builder / epilogue warp groups of gen_layer_tc_kernel (mmg_gen_set_worker_groups)
 
 // ------------------------------------------------------------------------------------------------
 // Analytic batch statistics of a WIDE layer fed by a NARROW one (the generator's 64 -> 4096 output layer): z = a W^T + b, so
@@ -609,7 +610,7 @@ int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double
     return MMG_OK;
 }
 
-// process-wide tuning switch: 2 or 4 groups of four builder / epilogue warps per CTA (default 2: measured equal or faster, B = 16 384); returns
+// process-wide tuning switch: 2 or 4 groups of four builder / epilogue warps per CTA (default 4: G1 forward 151 us against 176 at B = 16 384); returns
 // the previous value
 int mmg_gen_set_worker_groups(int groups) {
     const int prev = g_worker_groups;
@@ -658,7 +659,15 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
                 MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(w) failed");
     const int kchunks = a.Kp / 64;
     const int wg = g_worker_groups;
-    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)GT_W_STAGES * kchunks * a.NG * 128 + (p->y_out ? 4 * GT_Y_STAGE : 0) +
+    const long long items = row_tiles * a.n_groups;
+    const int grid = (int)(items < MMG_NUM_SMS ? items : MMG_NUM_SMS);
+    const bool single = items <= grid;                       // one item per CTA: one weight stage, one accumulator
+    a.w_stages = single ? 1 : GT_W_STAGES;
+    a.acc_stride = single ? 0 : a.NG;
+    int cols = single ? a.NG : 2 * a.NG;
+    a.tm_cols = 32;
+    while (a.tm_cols < cols) a.tm_cols *= 2;
+    size_t smem = 1024 + (size_t)kchunks * GT_A_CHUNK + (size_t)a.w_stages * kchunks * a.NG * 128 + (p->y_out ? 4 * GT_Y_STAGE : 0) +
                   (p->out_sums ? (size_t)8 * a.NG * sizeof(float) : 0);
     // a pure y pass (the wide output layer) keeps scale / shift of all its columns in shared memory when they fit
     const size_t cache = (size_t)2 * a.n_groups * a.NG * sizeof(float);
@@ -670,16 +679,15 @@ int mmg_gen_layer_fwd(const mmg_gen_layer_args* p, void* stream) {
         MMG_REQUIRE(tc::make_map_2d(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->y_out, (uint64_t)p->N, (uint64_t)p->M, (uint64_t)p->N * 4, 32, 128,
                                     CU_TENSOR_MAP_SWIZZLE_128B) == 0, MMG_EINVAL, "gen_layer_fwd: cuTensorMapEncodeTiled(y) failed");
     }
-    if (smem < GT_SMEM_MIN) smem = GT_SMEM_MIN;
     MMG_REQUIRE(smem <= 220 * 1024, MMG_EUNSUPPORTED, "gen_layer_fwd: tile does not fit shared memory");
-    const long long items = row_tiles * a.n_groups;
-    const int grid = (int)(items < MMG_NUM_SMS ? items : MMG_NUM_SMS);
     static bool attr_done = false;
     if (!attr_done) {
         MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMG_CUDA(cudaFuncSetAttribute(gen_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
+    // (TMEM columns and shared memory are sized to need, so single-item launches of the two generators COULD share an SM; a 2-CTAs-per-SM build
+    // of the kernel (96 registers) was measured with the beat generator on its side stream: 224 us for both forwards instead of 213 -- dropped)
     if (wg == 4) gen_layer_tc_kernel<4><<<grid, 64 + 4 * 128, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
     else gen_layer_tc_kernel<2><<<grid, 64 + 2 * 128, smem, (cudaStream_t)stream>>>(map_w, map_y, a);
     MMG_LAUNCH_CHECK();

@@ -213,7 +213,7 @@ typedef struct mmg_gen_layer_args {
 size_t mmg_gen_packed_weight_bytes(int N, int K);
 int mmg_gen_pack_weight(const float* w, int N, int K, void* packed, void* stream);
 int mmg_gen_layer_fwd(const mmg_gen_layer_args* args, void* stream);
-int mmg_gen_set_worker_groups(int groups);   /* tuning aid, process-wide: 2 or 4 groups of four builder / epilogue warps per CTA of mmg_gen_layer_fwd (default 2); returns the previous value */
+int mmg_gen_set_worker_groups(int groups);   /* tuning aid, process-wide: 2 or 4 groups of four builder / epilogue warps per CTA of mmg_gen_layer_fwd (default 4); returns the previous value */
 /* Batch statistics of a wide layer fed by a narrow one (the generators' 64 -> 4096 output block, network_tests.py:71,78) without a GEMM pass:
  * with a = sigmoid(BN(z_prev)) (the layer's bf16 input operand), s = sum_r a_r and G = sum_r a_r a_r^T, the column sums of z = a W^T + b are
  * w_n.s + M b_n and those of z^2 are w_n^T G w_n + 2 b_n w_n.s + M b_n^2 (fp64).  Writes out_sums [2][N] for the M local rows; K <= 64;

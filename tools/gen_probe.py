@@ -38,6 +38,17 @@ def graph_time(fn, reps=10, rounds=5):
     return best
 
 
+side = torch.cuda.Stream()
+def both():          # what the trainer does: the beat generator on a side stream (fork / join, also under capture)
+    cur = torch.cuda.current_stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        g2.forward(n[2], n[3], out=o2)
+    g1.forward(n[0], n[1], out=o1)
+    cur.wait_stream(side)
+for wg in (2, 4):
+    N.lib().mmg_gen_set_worker_groups(wg)
+    print(f"G1 on the main stream + G2 on a side stream, {wg} worker groups: {graph_time(both):.1f} us", flush=True)
 outs = {}
 for wg in (2, 4):
     N.lib().mmg_gen_set_worker_groups(wg)
