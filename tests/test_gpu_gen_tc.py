@@ -56,6 +56,48 @@ def test_gen_tc_vs_torch_fp32(B, which, training):
         assert int(bn.num_batches_tracked) == (1 if training else 0)
 
 
+@pytest.mark.parametrize("training", [True, False])
+def test_gen_tc_many_items_per_cta_and_worker_groups(training):
+    """B = 2500: the output layer has 20 row tiles x 16 column groups = 320 items over 148 CTAs (contiguous ranges that cross a row tile, both
+    accumulators, the cached column constants, a partial last row tile); 2 and 4 builder / epilogue warp groups give identical bits."""
+    from gan_des_midi_music_gen_b200 import _native as N
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    B = 2500
+    torch.manual_seed(7)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device="cuda")
+    g = m.generator1
+    with torch.no_grad():
+        for blk in g.gen:
+            blk[1].weight.uniform_(0.5, 1.5); blk[1].bias.uniform_(-0.5, 0.5)
+            blk[1].running_mean.uniform_(-0.3, 0.3); blk[1].running_var.uniform_(0.5, 2.0)
+            blk[0].bias.uniform_(-0.2, 0.2)
+    g.train(training)
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    noise, inp = torch.randn(B, 50), torch.randn(B, 50)
+    want, stats = _torch_ref({k: v.cpu() for k, v in sd0.items()}, "generator1", torch.cat((noise, inp), 1), training)
+    outs = []
+    prev = N.lib().mmg_gen_set_worker_groups(4)
+    try:
+        for groups in (4, 2):
+            N.lib().mmg_gen_set_worker_groups(groups)
+            m.load_state_dict(sd0)
+            got = GenTC(g, max_batch=B).forward(noise.cuda(), inp.cuda())
+            torch.cuda.synchronize()
+            assert (got.cpu() - want).abs().max().item() < 2e-2 and (got.cpu() - want).abs().mean().item() < 3e-3
+            for i, (rm, rv) in enumerate(stats):
+                bn = g.gen[i][1]
+                assert torch.allclose(bn.running_mean.cpu(), rm, rtol=2e-2, atol=2e-3), (groups, i)
+                assert torch.allclose(bn.running_var.cpu(), rv, rtol=2e-2, atol=2e-3), (groups, i)
+            outs.append(got.clone())
+    finally:
+        N.lib().mmg_gen_set_worker_groups(prev)
+    if not training:                         # (train mode: the order of the fp64 atomics of the column sums is not fixed)
+        assert torch.equal(outs[0], outs[1])
+    else:
+        assert (outs[0] - outs[1]).abs().max().item() < 1e-5
+
+
 def test_gen_tc_vs_reference_golden(golden_dir):
     """Generator outputs of the unmodified reference (mmgan_b16.npz, first D-step forward) within the stated bf16 tolerance."""
     import mmgan_oracle as mo
