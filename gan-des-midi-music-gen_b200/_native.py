@@ -75,6 +75,16 @@ class GenLayerArgs(ctypes.Structure):
                 ("momentum", _F), ("eps", _F), ("update_running", _I), ("M", _L), ("stat_count", _L)]
 
 
+class GenHiddenArgs(ctypes.Structure):
+    """mmg_gen_hidden_args of include/mmgan_b200.h"""
+    _fields_ = [("x0", _P), ("x1", _P), ("k0", _I), ("k1", _I),
+                ("w_packed", _P * 3), ("bias", _P * 3), ("N", _I * 3),
+                ("gamma", _P * 3), ("beta", _P * 3), ("run_mean", _P * 3), ("run_var", _P * 3),
+                ("sums", _P * 3),
+                ("z_out", _P), ("gram_part", _P), ("barrier", _P),
+                ("momentum", _F), ("eps", _F), ("update_running", _I), ("M", _L), ("stat_count", _L)]
+
+
 SIGNATURES.update({
     "mmg_disc_fwd_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "mmg_disc_fwd_fused_gather": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
@@ -87,6 +97,9 @@ SIGNATURES.update({
     "mmg_gen_pack_weight": (_I, [_P, _I, _I, _P, _P]),
     "mmg_gen_layer_fwd": (_I, [ctypes.POINTER(GenLayerArgs), _P]),
     "mmg_gen_set_worker_groups": (_I, [_I]),
+    "mmg_gen_hidden_fused_supported": (_I, [_L, _I, ctypes.POINTER(_I), _I]),
+    "mmg_gen_hidden_fused": (_I, [ctypes.POINTER(GenHiddenArgs), _P]),
+    "mmg_gen_layer_stats_gram_finish": (_I, [_I, _P, _P, _I, _I, _L, _P, _P, _Z, _P]),
     "mmg_gen_layer_stats_gram_workspace": (_Z, []),
     "mmg_gen_layer_stats_gram": (_I, [_P, _L, _I, _P, _L, _P, _P, _F, _P, _P, _I, _P, _P, _Z, _P]),
 })

@@ -562,6 +562,252 @@ __global__ void __launch_bounds__(256) gen_gram_colstats_kernel(const double* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The three hidden [Linear -> BatchNorm1d -> Sigmoid] blocks of a generator (network_tests.py:68-71,103-106) in ONE cooperative launch, train mode:
+// one CTA per 128-row tile keeps its rows' pre-activations in TMEM (layer 1: columns 0.., layer 2 and 3 behind it) from layer to layer; a
+// layer's column sums leave the CTA as one fp64 atomic per column, a grid-wide barrier makes the batch statistics complete, and the next
+// layer's A operand is built from the TMEM accumulators exactly as gen_layer_tc_kernel builds it from the stored z (z = acc + bias in fp32,
+// then sigmoid(z * scale + shift), rounded to bf16).  Only the last hidden layer's z is written (the output layer's kernel reads it), and
+// the CTA's part of the output layer's Gram statistics (G = sum a a^T, s = sum a over its rows) is formed from the same TMEM columns.
+// All three weight matrices are fetched by TMA at kernel start.  3 launches + the Gram partial kernel become 1.
+struct HiddenDev {
+    const float* x0; const float* x1; int k0, k1;
+    const float* bias[3]; const float* gamma[3]; const float* beta[3]; float* run_mean[3]; float* run_var[3]; double* sums[3];
+    int N[3], NG[3], K[3], Kp[3], tcol[3];
+    int w_off[3];                               // byte offsets of the weight tiles behind the A buffer
+    int a_bytes, part_off;
+    float* z_out; double* gram_part; unsigned int* barrier;
+    float momentum, eps; int update_running; long long M; double cnt;
+};
+
+constexpr int GH_WORKERS = 256, GH_THREADS = 64 + GH_WORKERS;
+
+__global__ void __launch_bounds__(GH_THREADS, 1) gen_hidden_fused_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                                                                         const __grid_constant__ CUtensorMap map_w2, const HiddenDev a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t wbar[3], aready, accfull;
+    __shared__ uint32_t tmem_s;
+    __shared__ float in_scale[GT_MAX_K], in_shift[GT_MAX_K], in_bias[GT_MAX_K];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_a = smem;
+    float* smem_part = reinterpret_cast<float*>(smem + a.part_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int l = 0; l < 3; ++l) tc::mbar_init(&wbar[l], 1);
+        tc::mbar_init(&aready, GH_WORKERS);
+        tc::mbar_init(&accfull, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_s, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_s;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            const CUtensorMap* maps[3] = {&map_w0, &map_w1, &map_w2};
+            for (int l = 0; l < 3; ++l) {
+                tc::tma_prefetch_desc(maps[l]);
+                const int kch = a.Kp[l] / 64;
+                tc::mbar_expect_tx(&wbar[l], (uint32_t)(kch * a.NG[l] * 128));
+                for (int c = 0; c < kch; ++c) tc::tma_load_2d(smem + a.w_off[l] + c * a.NG[l] * 128, maps[l], &wbar[l], c * 64, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint64_t KM128 = tc::smem_desc_base(0, 1024, tc::SW_128B);
+            const uint32_t a_addr = tc::smem_u32(smem_a);
+            for (int l = 0; l < 3; ++l) {
+                const uint32_t idesc = tc::idesc_bf16(128, (uint32_t)a.NG[l]);
+                const uint32_t wb = tc::smem_u32(smem + a.w_off[l]);
+                tc::mbar_wait(&aready, (uint32_t)(l & 1));
+                tc::mbar_wait(&wbar[l], 0);
+                tc::tc_fence_after();
+                const int kch = a.Kp[l] / 64;
+                for (int c = 0; c < kch; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_f16_ss(tmem + a.tcol[l], tc::smem_desc(KM128, a_addr + c * GT_A_CHUNK + k * 32), tc::smem_desc(KM128, wb + c * a.NG[l] * 128 + k * 32), idesc,
+                                       (c | k) != 0);
+                tc::mma_commit(&accfull);
+            }
+        }
+    } else {
+        const int q = warp & 3, h = (warp - 2) >> 2, t = q * 32 + lane;     // t = row of the tile = TMEM lane; h = which half of a 64-feature chunk / alternate 32-column chunks
+        const int et = threadIdx.x - 64;
+        const long long row = (long long)rt * 128 + t;
+        const bool live = row < a.M;
+        auto bar_workers = [&]() { asm volatile("bar.sync 7, %0;" ::"n"(GH_WORKERS) : "memory"); };
+        // ---- layer 1 operand from the two raw inputs (the torch.cat of network_tests.py:86,122 never exists)
+        {
+            const int K = a.K[0], kch = a.Kp[0] / 64;
+            for (int c = 0; c < kch; ++c) {
+                const uint32_t dst = tc::smem_u32(smem_a) + c * GT_A_CHUNK + t * 128;
+                const int kb = c * 64 + 32 * h;
+                float v[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int kk = kb + e;
+                    v[e] = !live ? 0.f : (kk < a.k0 ? a.x0[row * a.k0 + kk] : (kk < K ? a.x1[row * a.k1 + (kk - a.k0)] : 0.f));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::sts128(dst + (((4 * h + j) ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&aready);
+        }
+        for (int l = 0; l < 3; ++l) {
+            const int N = a.N[l], NG = a.NG[l];
+            bar_workers();                                   // the previous layer's operand builders have read in_bias
+            for (int c = et; c < NG; c += GH_WORKERS) in_bias[c] = (c < N && a.bias[l]) ? a.bias[l][c] : 0.f;
+            bar_workers();
+            tc::mbar_wait(&accfull, (uint32_t)(l & 1));
+            tc::tc_fence_after();
+            // ---- epilogue: z = acc + bias; column sums of z and z^2 over this tile's rows (32-row partials in fp32, combined in fp64); the last layer's z is stored
+            for (int c0 = 32 * h; c0 < NG; c0 += 64) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a.tcol[l] + c0, r);
+                tc::tmem_ld_wait();
+                float s1[32], s2[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float z = __uint_as_float(r[e]) + in_bias[c0 + e];
+                    s1[e] = live ? z : 0.f;
+                    s2[e] = s1[e] * s1[e];
+                }
+                if (l == 2 && a.z_out && live) {
+                    float* zp = a.z_out + row * N + c0;
+                    if (c0 + 32 <= N && (N & 3) == 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(zp + e) = make_float4(s1[e], s1[e + 1], s1[e + 2], s1[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (c0 + e < N) zp[e] = s1[e];
+                    }
+                }
+                const float c1 = colsum32(s1, lane), c2 = colsum32(s2, lane);
+                smem_part[(2 * q) * NG + c0 + lane] = c1;
+                smem_part[(2 * q + 1) * NG + c0 + lane] = c2;
+            }
+            bar_workers();
+            for (int c = et; c < 2 * NG; c += GH_WORKERS) {
+                const int which = c >= NG ? 1 : 0, col = c - which * NG;
+                if (col < N) {
+                    const double v = ((double)smem_part[which * NG + col] + (double)smem_part[(2 + which) * NG + col]) +
+                                     ((double)smem_part[(4 + which) * NG + col] + (double)smem_part[(6 + which) * NG + col]);
+                    atomicAdd(&a.sums[l][which * N + col], v);
+                }
+            }
+            // ---- grid-wide barrier: every CTA's atomics are performed before any CTA reads the sums (cooperative launch: all CTAs are resident)
+            bar_workers();
+            if (et == 0) {
+                __threadfence();
+                atomicAdd(a.barrier, 1u);
+                const unsigned int target = gridDim.x * (unsigned int)(l + 1);
+                while (*reinterpret_cast<volatile unsigned int*>(a.barrier) < target) {}
+                __threadfence();
+            }
+            bar_workers();
+            // ---- this layer's BatchNorm folded to scale / shift (every CTA needs all N features; CTA 0 updates the running statistics)
+            for (int k = et; k < N; k += GH_WORKERS) {
+                float sc, sh, mu, var;
+                bn_scale_shift(__ldcg(&a.sums[l][k]), __ldcg(&a.sums[l][N + k]), a.cnt, a.gamma[l][k], a.beta[l][k], a.eps, sc, sh, mu, var);
+                if (a.update_running && blockIdx.x == 0 && a.run_mean[l]) {
+                    const float unb = var * (float)(a.cnt / (a.cnt - 1.0));
+                    a.run_mean[l][k] = (1.f - a.momentum) * a.run_mean[l][k] + a.momentum * mu;
+                    a.run_var[l][k] = (1.f - a.momentum) * a.run_var[l][k] + a.momentum * unb;
+                }
+                in_scale[k] = sc * NEG_LOG2E;
+                in_shift[k] = sh * NEG_LOG2E;
+            }
+            bar_workers();
+            if (l < 2) {
+                // ---- next layer's A operand from the TMEM accumulators: features [64 c + 32 h, + 32) of row t
+                const int kch = a.Kp[l + 1] / 64;                // = ceil(N / 64)
+                for (int c = 0; c < kch; ++c) {
+                    const int kb = c * 64 + 32 * h;
+                    uint32_t r[32];
+                    float v[32];
+                    if (kb < NG) {
+                        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a.tcol[l] + kb, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = (live && kb + e < N) ? fast_sigmoid_affine(__uint_as_float(r[e]) + in_bias[kb + e], in_scale[kb + e], in_shift[kb + e]) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                    }
+                    const uint32_t dst = tc::smem_u32(smem_a) + c * GT_A_CHUNK + t * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tc::sts128(dst + (((4 * h + j) ^ (t & 7)) << 4), make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                                                    pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+                }
+                tc::tc_fence_before();
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&aready);
+            } else if (a.gram_part) {
+                // ---- this CTA's part of the output layer's Gram statistics (see gen_gram_partial_kernel): a = bf16(sigmoid(BN(z))) of its 128 rows,
+                // two 64-row halves accumulated in fp32, added in fp64.  The tile lives where the layer-1 weights were.
+                float (*at)[GS_K + 1] = reinterpret_cast<float (*)[GS_K + 1]>(smem + a.w_off[0]);
+                {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a.tcol[2] + 32 * h, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int k = 32 * h + e;
+                        at[t][k] = (live && k < N) ? __bfloat162float(__float2bfloat16(fast_sigmoid_affine(__uint_as_float(r[e]) + in_bias[k], in_scale[k], in_shift[k]))) : 0.f;
+                    }
+                }
+                bar_workers();
+                const int i0 = (et >> 4) * 4, j0 = (et & 15) * 4;
+                double acc[16], ssum = 0.0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+                for (int half = 0; half < 2; ++half) {
+                    float f[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < GS_ROWS; ++rr) {
+                        const int r0 = half * GS_ROWS + rr;
+                        float ai[4], aj[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { ai[u] = at[r0][i0 + u]; aj[u] = at[r0][j0 + u]; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) f[4 * u + v] = fmaf(ai[u], aj[v], f[4 * u + v]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] += (double)f[e];
+                    if (et < GS_K) {
+                        float c = 0.f;
+                        for (int rr = 0; rr < GS_ROWS; ++rr) c += at[half * GS_ROWS + rr][et];
+                        ssum += (double)c;
+                    }
+                }
+                double* out = a.gram_part + (size_t)blockIdx.x * GS_PART;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) out[(i0 + u) * GS_K + j0 + v] = acc[4 * u + v];
+                if (et < GS_K) out[GS_K * GS_K + et] = ssum;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -604,6 +850,84 @@ int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double
     gen_gram_partial_kernel<<<grid, 256, 0, stream>>>(z_prev, (long long)M, K, in_sums, count, in_gamma, in_beta, eps, part);
     MMG_LAUNCH_CHECK();
     gen_gram_reduce_kernel<<<(GS_PART + 31) / 32, 256, 0, stream>>>(part, grid, red);
+    MMG_LAUNCH_CHECK();
+    gen_gram_colstats_kernel<<<(N + 63) / 64, 256, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// ---- the three hidden blocks in one cooperative launch (gen_hidden_fused_kernel); train mode, local batch statistics
+static int hidden_layout(const mmg_gen_hidden_args* p, HiddenDev& a, size_t& smem) {
+    int k_in = p->k0 + p->k1, tcol = 0, max_kch = 0, max_ng = 0;
+    for (int l = 0; l < 3; ++l) {
+        if (p->N[l] <= 0 || p->N[l] > 256 || k_in <= 0 || k_in > GT_MAX_K) return 0;
+        a.N[l] = p->N[l]; a.NG[l] = round_up(p->N[l], 32); a.K[l] = k_in; a.Kp[l] = round_up(k_in, 64);
+        a.tcol[l] = tcol;
+        tcol += a.NG[l];
+        max_kch = a.Kp[l] / 64 > max_kch ? a.Kp[l] / 64 : max_kch;
+        max_ng = a.NG[l] > max_ng ? a.NG[l] : max_ng;
+        k_in = p->N[l];
+    }
+    if (tcol > 512) return 0;
+    a.a_bytes = max_kch * GT_A_CHUNK;
+    int off = a.a_bytes;
+    for (int l = 0; l < 3; ++l) { a.w_off[l] = off; off += (a.Kp[l] / 64) * a.NG[l] * 128; }
+    a.part_off = off;
+    off += 8 * max_ng * (int)sizeof(float);
+    smem = 1024 + (size_t)off;
+    if (p->gram_part && ((a.Kp[0] / 64) * a.NG[0] * 128 < (int)(128 * (GS_K + 1) * sizeof(float)) || p->N[2] > GS_K)) return 0;     // the Gram tile reuses the layer-1 weight tile
+    return smem <= 220 * 1024;
+}
+
+int mmg_gen_hidden_fused_supported(int64_t M, int k_in, const int* N3, int with_gram) {
+    if (!N3 || M <= 1 || (M + 127) / 128 > MMG_NUM_SMS) return 0;
+    mmg_gen_hidden_args p = {};
+    p.k0 = k_in; p.k1 = 0;
+    for (int l = 0; l < 3; ++l) p.N[l] = N3[l];
+    p.gram_part = with_gram ? (double*)16 : nullptr;
+    HiddenDev a;
+    size_t smem;
+    return hidden_layout(&p, a, smem);
+}
+
+int mmg_gen_hidden_fused(const mmg_gen_hidden_args* p, void* stream) {
+    MMG_REQUIRE(p && p->x0 && p->M > 1 && p->k0 > 0 && p->k1 >= 0 && (p->k1 == 0 || p->x1) && p->barrier && p->z_out, MMG_EINVAL, "gen_hidden_fused: bad arguments");
+    MMG_REQUIRE(p->stat_count == 0 || p->stat_count == p->M, MMG_EUNSUPPORTED, "gen_hidden_fused: local batch statistics only (SyncBN runs the per-layer kernels)");
+    for (int l = 0; l < 3; ++l)
+        MMG_REQUIRE(p->w_packed[l] && p->gamma[l] && p->beta[l] && p->sums[l], MMG_EINVAL, "gen_hidden_fused: missing tensors of layer %d", l);
+    HiddenDev a;
+    size_t smem;
+    const long long row_tiles = (p->M + 127) / 128;
+    MMG_REQUIRE(row_tiles <= MMG_NUM_SMS && hidden_layout(p, a, smem), MMG_EUNSUPPORTED, "gen_hidden_fused: shape does not fit one cooperative launch (see mmg_gen_hidden_fused_supported)");
+    a.x0 = p->x0; a.x1 = p->x1; a.k0 = p->k0; a.k1 = p->k1;
+    CUtensorMap maps[3];
+    for (int l = 0; l < 3; ++l) {
+        a.bias[l] = p->bias[l]; a.gamma[l] = p->gamma[l]; a.beta[l] = p->beta[l]; a.run_mean[l] = p->run_mean[l]; a.run_var[l] = p->run_var[l]; a.sums[l] = p->sums[l];
+        MMG_REQUIRE(tc::make_map_2d_bf16(&maps[l], p->w_packed[l], (uint64_t)a.Kp[l], (uint64_t)a.NG[l], (uint64_t)a.Kp[l] * 2, 64, (uint32_t)a.NG[l], CU_TENSOR_MAP_SWIZZLE_128B) == 0,
+                    MMG_EINVAL, "gen_hidden_fused: cuTensorMapEncodeTiled(w%d) failed", l);
+    }
+    a.z_out = p->z_out; a.gram_part = p->gram_part; a.barrier = p->barrier;
+    a.momentum = p->momentum; a.eps = p->eps; a.update_running = p->update_running; a.M = p->M; a.cnt = (double)p->M;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMG_CUDA(cudaFuncSetAttribute(gen_hidden_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    void* args[] = {&maps[0], &maps[1], &maps[2], &a};
+    MMG_CUDA(cudaLaunchCooperativeKernel((const void*)gen_hidden_fused_kernel, dim3((unsigned)row_tiles), dim3(GH_THREADS), args, smem, (cudaStream_t)stream));
+    MMG_LAUNCH_CHECK();
+    return MMG_OK;
+}
+
+// second half of mmg_gen_layer_stats_gram for partials that mmg_gen_hidden_fused wrote (nparts = row tiles of 128): reduce + column statistics
+int mmg_gen_layer_stats_gram_finish(int nparts, const float* weight, const float* bias, int N, int K, int64_t M, double* out_sums, void* workspace,
+                                    size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMG_REQUIRE(weight && out_sums && workspace && nparts > 0 && nparts <= MMG_NUM_SMS && N > 0 && K > 0 && K <= GS_K && M > 1, MMG_EINVAL, "gen_layer_stats_gram_finish: bad arguments");
+    MMG_REQUIRE(ws_bytes >= mmg_gen_layer_stats_gram_workspace(), MMG_EINVAL, "gen_layer_stats_gram_finish: workspace too small");
+    double* part = (double*)workspace;
+    double* red = part + (size_t)GS_PART * MMG_NUM_SMS;
+    gen_gram_reduce_kernel<<<(GS_PART + 31) / 32, 256, 0, stream>>>(part, nparts, red);
     MMG_LAUNCH_CHECK();
     gen_gram_colstats_kernel<<<(N + 63) / 64, 256, 0, stream>>>(red, weight, bias, N, K, (double)M, out_sums);
     MMG_LAUNCH_CHECK();

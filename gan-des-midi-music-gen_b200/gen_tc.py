@@ -19,7 +19,7 @@ from . import _native as N
 
 
 class GenTC:
-    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=True, sum_views=None):
+    def __init__(self, gen, max_batch, process_group=None, sync_bn=False, gram_stats=True, sum_views=None, fused_hidden=True):
         self.g = gen
         dist = torch.distributed
         self.pg = process_group
@@ -50,7 +50,18 @@ class GenTC:
         last = self.blocks[-1][0]
         self.gram_stats = bool(gram_stats) and last.in_features <= 64 and last.in_features % 8 == 0 and last.out_features >= 512
         self.gram_ws = torch.empty(N.lib().mmg_gen_layer_stats_gram_workspace(), dtype=torch.uint8, device=dev) if self.gram_stats else None
+        # train mode with local statistics: the three hidden blocks run as ONE cooperative launch (mmg_gen_hidden_fused) when the batch fits
+        self.fused_hidden = bool(fused_hidden) and len(self.blocks) == 4 and not self.sync_bn
+        self.barrier = torch.zeros(2, dtype=torch.int32, device=dev) if self.fused_hidden else None
+        self._fused_ok = {}
         self.pack()
+
+    def _fused_supported(self, B):
+        ok = self._fused_ok.get(B)
+        if ok is None:
+            n3 = (ctypes.c_int * 3)(*self.widths[:3])
+            ok = self._fused_ok[B] = bool(N.lib().mmg_gen_hidden_fused_supported(B, self.blocks[0][0].in_features, n3, int(self.gram_stats)))
+        return ok
 
     def pack(self, force=True):
         """Re-derive the bf16 operand copies from the fp32 master weights (cheap; skipped when nothing changed)."""
@@ -99,7 +110,23 @@ class GenTC:
         y = out if out is not None else torch.empty(B, self.widths[-1], device=self.dev)
         mode = 1 if training else 2
         last = len(self.blocks) - 1
+        fused = training and self.fused_hidden and self._fused_supported(B)
+        if fused:
+            N.call("mmg_zero", N.ptr(self.barrier), 8, s)
+            h = N.GenHiddenArgs()
+            h.x0, h.k0, h.x1, h.k1 = N.ptr(noise), noise.shape[1], N.ptr(input_tensor), input_tensor.shape[1]
+            for l in range(3):
+                lin, bn = self.blocks[l]
+                h.w_packed[l], h.bias[l], h.N[l] = N.ptr(self.packed[l]), N.ptr(lin.bias.data), lin.out_features
+                h.gamma[l], h.beta[l], h.run_mean[l], h.run_var[l] = N.ptr(bn.weight.data), N.ptr(bn.bias.data), N.ptr(bn.running_mean), N.ptr(bn.running_var)
+                h.sums[l] = N.ptr(self.sum_views[l])
+            bn0 = self.blocks[0][1]             # (the reference's blocks share momentum / eps: nn.BatchNorm1d defaults)
+            h.z_out, h.gram_part, h.barrier = N.ptr(self.z[2]), (N.ptr(self.gram_ws) if self.gram_stats else None), N.ptr(self.barrier)
+            h.momentum, h.eps, h.update_running, h.M, h.stat_count = (bn0.momentum if bn0.momentum is not None else 0.1), bn0.eps, 1, B, 0
+            N.call("mmg_gen_hidden_fused", ctypes.byref(h), s)
         for i, (lin, bn) in enumerate(self.blocks):
+            if fused and i < last:
+                continue
             a = N.GenLayerArgs()
             if i == 0:
                 a.x0, a.k0, a.x1, a.k1, a.in_mode = N.ptr(noise), noise.shape[1], N.ptr(input_tensor), input_tensor.shape[1], 0
@@ -109,6 +136,8 @@ class GenTC:
                 a.in_sums = N.ptr(self.sum_views[i - 1]) if training else None
                 a.in_gamma, a.in_beta = N.ptr(pbn.weight.data), N.ptr(pbn.bias.data)
                 a.in_run_mean, a.in_run_var = N.ptr(pbn.running_mean), N.ptr(pbn.running_var)
+                if fused:                      # the fused launch has made the one update of the hidden layers' running statistics
+                    a.in_run_mean = a.in_run_var = None
             a.w_packed, a.bias, a.N = N.ptr(self.packed[i]), N.ptr(lin.bias.data), lin.out_features
             a.momentum = bn.momentum if bn.momentum is not None else 0.1
             a.eps, a.M = bn.eps, B
@@ -123,7 +152,10 @@ class GenTC:
             else:
                 a.out_gamma, a.out_beta = N.ptr(bn.weight.data), N.ptr(bn.bias.data)
                 a.out_run_mean, a.out_run_var = N.ptr(bn.running_mean), N.ptr(bn.running_var)
-                if training and self.gram_stats:   # batch sums of this layer from the Gram matrix of its input: no GEMM pass for the statistics
+                if training and self.gram_stats and fused:      # the fused launch left the per-CTA Gram partials: reduce + column statistics
+                    N.call("mmg_gen_layer_stats_gram_finish", (B + 127) // 128, N.ptr(lin.weight.data), N.ptr(lin.bias.data), lin.out_features,
+                           self.widths[i - 1], B, N.ptr(self.sum_views[i]), N.ptr(self.gram_ws), self.gram_ws.numel(), s)
+                elif training and self.gram_stats:   # batch sums of this layer from the Gram matrix of its input: no GEMM pass for the statistics
                     pbn = self.blocks[i - 1][1]
                     N.call("mmg_gen_layer_stats_gram", N.ptr(self.z[i - 1]), B, self.widths[i - 1], N.ptr(self.sum_views[i - 1]), B * self.world,
                            N.ptr(pbn.weight.data), N.ptr(pbn.bias.data), pbn.eps, N.ptr(lin.weight.data), N.ptr(lin.bias.data), lin.out_features,

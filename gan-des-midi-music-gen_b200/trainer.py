@@ -109,8 +109,11 @@ class MMGANTrainer:
                     if i < len(w2):
                         sv2.append(self._sync_sums[o:o + 2 * w2[i]]); o += 2 * w2[i]
                     self._sync_pairs.append(self._sync_sums[a:o])
-            self.gtc1 = GenTC(mmgan.generator1, max_batch, process_group, self.sync_bn, sum_views=sv1)
-            self.gtc2 = GenTC(mmgan.generator2, max_batch, process_group, self.sync_bn, sum_views=sv2)
+            # the one-launch form of the hidden blocks is a cooperative kernel (grid-wide barriers): used by the single-GPU trainer only, so that it never
+            # shares the device with an in-flight NCCL kernel of the gradient all-reduce
+            fuse = self.world == 1
+            self.gtc1 = GenTC(mmgan.generator1, max_batch, process_group, self.sync_bn, sum_views=sv1, fused_hidden=fuse)
+            self.gtc2 = GenTC(mmgan.generator2, max_batch, process_group, self.sync_bn, sum_views=sv2, fused_hidden=fuse)
         dev = self.flat_grad.device
         if inner_rng not in ("reference", "device"):
             raise ValueError("inner_rng must be 'reference' or 'device'")

@@ -222,6 +222,26 @@ size_t mmg_gen_layer_stats_gram_workspace(void);
 int mmg_gen_layer_stats_gram(const float* z_prev, int64_t M, int K, const double* in_sums, int64_t stat_count, const float* in_gamma,
                              const float* in_beta, float eps, const float* weight, const float* bias, int N, double* out_sums, void* workspace,
                              size_t ws_bytes, void* stream);
+/* The three hidden [Linear -> BatchNorm1d -> Sigmoid] blocks of a generator (network_tests.py:68-71,75-80 / :103-106) in ONE cooperative launch, train
+ * mode with the local batch statistics (what mmg_gen_layer_fwd does in three launches): one CTA per 128-row tile keeps the pre-activations in TMEM,
+ * a grid-wide barrier per layer completes the column sums.  x0 / x1 as in mmg_gen_layer_args (in_mode 0); w_packed[l] = mmg_gen_pack_weight of
+ * layer l; sums[l] fp64 [2][N_l] and the 4-byte barrier word are ZEROED by the caller before every call; z_out (M, N[2]) fp32 = the last hidden
+ * layer's pre-activations (input of the output block's mmg_gen_layer_fwd, in_mode 1); run_mean / run_var updated once if update_running.
+ * gram_part (NULL = skip): workspace of mmg_gen_layer_stats_gram_workspace() bytes receiving the per-CTA Gram partials of the output block's
+ * statistics -- follow with mmg_gen_layer_stats_gram_finish(nparts = ceil(M / 128), ...).  stat_count must be 0 or M.
+ * mmg_gen_hidden_fused_supported: 1 when (M rows, k_in input features, widths N3[3]) fits (at most one row tile per SM, N_l <= 256, shared memory). */
+typedef struct mmg_gen_hidden_args {
+    const float* x0; const float* x1; int k0; int k1;
+    const void* w_packed[3]; const float* bias[3]; int N[3];
+    const float* gamma[3]; const float* beta[3]; float* run_mean[3]; float* run_var[3];
+    double* sums[3];
+    float* z_out; double* gram_part; unsigned int* barrier;
+    float momentum; float eps; int update_running; int64_t M; int64_t stat_count;
+} mmg_gen_hidden_args;
+int mmg_gen_hidden_fused_supported(int64_t M, int k_in, const int* N3, int with_gram);
+int mmg_gen_hidden_fused(const mmg_gen_hidden_args* args, void* stream);
+int mmg_gen_layer_stats_gram_finish(int nparts, const float* weight, const float* bias, int N, int K, int64_t M, double* out_sums, void* workspace,
+                                    size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,41 @@ def test_gen_tc_many_items_per_cta_and_worker_groups(training):
         assert (outs[0] - outs[1]).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("B,which", [(16, "generator1"), (300, "generator2"), (2500, "generator1"), (2500, "generator2"), (16384, "generator1")])
+def test_gen_tc_fused_hidden_matches_per_layer_launches(B, which):
+    """Train mode: the three hidden blocks as ONE cooperative launch (mmg_gen_hidden_fused: pre-activations kept in TMEM, grid-wide barrier per
+    layer, Gram partials of the output block's statistics) against the per-layer launches: same arithmetic per element, so outputs and running
+    statistics agree to the order of the fp64 column-sum atomics; and against the torch fp32 restatement at the stated bf16 tolerance."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import network_tests as nt
+    from gan_des_midi_music_gen_b200.gen_tc import GenTC
+    torch.manual_seed(B + 1)
+    m = nt.MultiModalGAN(z_dim=50, adj_size=(64, 64), roll_size=(2, 128, 50), input_dim=50, output_dim=20, instrument=0, start=100, end=150, device="cuda")
+    g = getattr(m, which).train()
+    with torch.no_grad():
+        for blk in g.gen:
+            blk[1].weight.uniform_(0.5, 1.5); blk[1].bias.uniform_(-0.5, 0.5)
+            blk[1].running_mean.uniform_(-0.3, 0.3); blk[1].running_var.uniform_(0.5, 2.0)
+            blk[0].bias.uniform_(-0.2, 0.2)
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    noise = torch.randn(B, 50)
+    inp = torch.randn(B, 50) if which == "generator1" else 25 * torch.rand(B, 50)
+    res = {}
+    for fused in (False, True):
+        m.load_state_dict(sd0)
+        tc = GenTC(g, max_batch=B, fused_hidden=fused)
+        assert tc.fused_hidden == fused and (not fused or tc._fused_supported(B))
+        for _ in range(2):                                   # twice: the barrier word and the sums are re-zeroed per call
+            got = tc.forward(noise.cuda(), inp.cuda())
+        torch.cuda.synchronize()
+        res[fused] = (got.clone(), [(blk[1].running_mean.clone(), blk[1].running_var.clone(), int(blk[1].num_batches_tracked)) for blk in g.gen])
+    (y0, st0), (y1, st1) = res[False], res[True]
+    assert torch.isfinite(y1).all() and (y0 - y1).abs().max().item() < 1e-5, (y0 - y1).abs().max().item()
+    for (m0, v0, n0), (m1, v1, n1) in zip(st0, st1):
+        assert n0 == n1 == 2 and torch.allclose(m0, m1, rtol=1e-5, atol=1e-6) and torch.allclose(v0, v1, rtol=1e-5, atol=1e-6)
+    want, _ = _torch_ref({k: v.cpu() for k, v in sd0.items()}, which, torch.cat((noise, inp), 1), True)
+    assert (y1.cpu() - want).abs().max().item() < 2e-2
+
+
 def test_gen_tc_vs_reference_golden(golden_dir):
     """Generator outputs of the unmodified reference (mmgan_b16.npz, first D-step forward) within the stated bf16 tolerance."""
     import mmgan_oracle as mo

@@ -38,6 +38,10 @@ def graph_time(fn, reps=10, rounds=5):
     return best
 
 
+g1u, g2u = GenTC(m.generator1, B, fused_hidden=False), GenTC(m.generator2, B, fused_hidden=False)
+for name, fn in (("G1 per-layer launches", lambda: g1u.forward(n[0], n[1], out=o1)), ("G1 fused hidden blocks", lambda: g1.forward(n[0], n[1], out=o1)),
+                 ("G2 per-layer launches", lambda: g2u.forward(n[2], n[3], out=o2)), ("G2 fused hidden blocks", lambda: g2.forward(n[2], n[3], out=o2))):
+    print(f"{name}: {graph_time(fn):.1f} us", flush=True)
 side = torch.cuda.Stream()
 def both():          # what the trainer does: the beat generator on a side stream (fork / join, also under capture)
     cur = torch.cuda.current_stream()
