@@ -108,15 +108,24 @@ __global__ void __launch_bounds__(256) adam_multi_tensor_dev_kernel(AdamTable ta
     float* __restrict__ v = tab.v[t];
     const float w = 1.f - beta1;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i] * grad_scale;
-        float mi = m[i], vi = v[i];
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 16-byte accesses when the four tensors allow it (the scalar form moved fc1's 198 MB at 2.6 TB/s); same arithmetic per element either way
+    const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    const long long n4 = vec ? n / 4 : 0;
+    auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+        gi *= grad_scale;
         mi = (w < 0.5f) ? mi + w * (gi - mi) : gi - (gi - mi) * (1.f - w);      // at::lerp
         vi = vi * beta2 + (1.f - beta2) * gi * gi;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
-        m[i] = mi; v[i] = vi;
+        pi = pi - step_size * (mi / denom);
+    };
+    for (long long i = i0; i < n4; i += stride) {
+        float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        upd(p4.x, g4.x, m4.x, v4.x); upd(p4.y, g4.y, m4.y, v4.y); upd(p4.z, g4.z, m4.z, v4.z); upd(p4.w, g4.w, m4.w, v4.w);
+        reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
     }
+    for (long long i = n4 * 4 + i0; i < n; i += stride) upd(p[i], g[i], m[i], v[i]);
 }
 __global__ void adam_step_inc_kernel(long long* step_dev) { step_dev[0] += 1; }
 
