@@ -92,6 +92,33 @@ def test_gram_stats_arg_checks_without_gpu():
     assert rc < 0 and b"workspace too small" in lib.mmg_last_error()
 
 
+def test_gen_hidden_fused_support_and_arg_checks_without_gpu():
+    """mmg_gen_hidden_fused_supported is host arithmetic (row tiles <= SMs, TMEM columns, shared memory); mmg_gen_hidden_fused / the Gram finish
+    validate their arguments before any launch."""
+    from gan_des_midi_music_gen_b200 import _native as N
+    lib = N.lib()
+    n3 = lambda *w: (ctypes.c_int * 3)(*w)
+    sup = lib.mmg_gen_hidden_fused_supported
+    assert sup(16384, 100, n3(256, 128, 64), 1) == 1 and sup(16, 100, n3(256, 128, 64), 0) == 1          # the reference's generators (network_tests.py:68-71)
+    assert sup(148 * 128, 100, n3(256, 128, 64), 1) == 1 and sup(148 * 128 + 1, 100, n3(256, 128, 64), 1) == 0      # one row tile per SM at most
+    assert sup(1, 100, n3(256, 128, 64), 1) == 0                                                        # train-mode statistics need > 1 row
+    assert sup(4096, 100, n3(512, 128, 64), 1) == 0 and sup(4096, 300, n3(256, 128, 64), 1) == 0         # N <= 256, K <= 256
+    assert sup(4096, 100, n3(256, 256, 256), 0) == 0                                                    # 768 TMEM columns
+    assert sup(4096, 100, n3(128, 128, 128), 1) == 0 and sup(4096, 100, n3(128, 128, 128), 0) == 1       # the Gram path takes <= 64 features
+    assert sup(4096, 100, n3(256, 128, 128), 0) == 0                                                    # 233 KB of shared memory
+    a = N.GenHiddenArgs()
+    assert lib.mmg_gen_hidden_fused(ctypes.byref(a), None) == -1 and b"bad arguments" in lib.mmg_last_error()
+    one = ctypes.c_void_p(4096)
+    a.x0, a.k0, a.k1, a.M, a.stat_count, a.barrier, a.z_out = one, 100, 0, 4096, 8192, one, one
+    assert lib.mmg_gen_hidden_fused(ctypes.byref(a), None) == -2 and b"SyncBN" in lib.mmg_last_error()
+    a.stat_count = 0
+    assert lib.mmg_gen_hidden_fused(ctypes.byref(a), None) == -1 and b"missing tensors of layer 0" in lib.mmg_last_error()
+    ws = lib.mmg_gen_layer_stats_gram_workspace()
+    assert lib.mmg_gen_layer_stats_gram_finish(0, one, one, 4096, 64, 4096, one, one, ws, None) == -1
+    assert lib.mmg_gen_layer_stats_gram_finish(32, one, one, 4096, 64, 4096, one, one, 16, None) == -1 and b"workspace too small" in lib.mmg_last_error()
+    assert lib.mmg_gen_set_worker_groups(3) in (2, 4) and lib.mmg_gen_set_worker_groups(4) in (2, 4)     # invalid values leave the setting alone
+
+
 def test_gandes_entry_point_arg_checks_without_gpu():
     """argument errors of the GAN-DES entry points are reported before any CUDA call (codes: -1 invalid, -2 unsupported)"""
     from gan_des_midi_music_gen_b200 import _native as N
