@@ -84,6 +84,34 @@ def test_gandes_iteration(golden_dir):
     _close(mo.gandes_gen_forward(gsd, torch.from_numpy(g["noise"]), training=False), g["eval.gen_out"])
 
 
+def test_gandes_d_step_one_batch_of_2b_equals_two_passes():
+    """The identity GANDESTrainer.d_step relies on (batch_d_passes): the discriminator (SIMNN.py:123-142) has no BatchNorm, so one pass over
+    cat(real, fake) with targets [0.9 ... | 0.1 ...] and 2 x the mean over 2B gives the logits, the loss and the gradients of the reference's two
+    passes (SIMNN.py:279-313).  Checked on the oracle in float64, where the only difference is the summation order."""
+    _, dshapes = mo.gandes_shapes()
+    dsd = {k: v.double() for k, v in mo.synth_state(dshapes, seed=12).items()}
+    g = torch.Generator().manual_seed(5)
+    B = 2
+    real, fake = torch.randn(B, 128, 216, generator=g).double(), torch.randn(B, 128, 216, generator=g).double()
+    res = []
+    for batched in (False, True):
+        params = {k: dsd[k].detach().clone().requires_grad_(True) for k in mo.GD_KEYS}
+        if batched:
+            p = mo.gandes_disc_forward(params, torch.cat([real, fake]))
+            tgt = torch.cat([torch.full((B, 1), 0.9, dtype=torch.float64), torch.full((B, 1), 0.1, dtype=torch.float64)])
+            loss = 2.0 * mo.bce_with_logits(p, tgt)
+        else:
+            p_real, p_fake = mo.gandes_disc_forward(params, real), mo.gandes_disc_forward(params, fake)
+            loss = mo.bce_with_logits(p_fake, torch.full_like(p_fake, 0.1)) + mo.bce_with_logits(p_real, torch.full_like(p_real, 0.9))
+            p = torch.cat([p_real, p_fake])
+        grads = torch.autograd.grad(loss, [params[k] for k in mo.GD_KEYS])
+        res.append((p.detach(), loss.detach(), grads))
+    (p0, l0, g0), (p1, l1, g1) = res
+    assert torch.allclose(p0, p1, rtol=0, atol=1e-13) and abs(l0.item() - l1.item()) < 1e-13
+    for k, a, b in zip(mo.GD_KEYS, g0, g1):
+        assert (a - b).abs().max().item() <= 1e-12 * max(1.0, a.abs().max().item()), k
+
+
 def test_bn_rejects_single_sample():
     sd = mo.synth_state(mo.mmgan_shapes(adj_size=(16, 16)), seed=0)
     with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
