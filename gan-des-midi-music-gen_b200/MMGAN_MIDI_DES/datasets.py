@@ -11,6 +11,7 @@ is defined as the post-mido event stream.
 
 There is no CPU fallback: rasterisation needs a CUDA device and the built library.
 """
+import ctypes
 import glob
 import os
 import pickle
@@ -63,109 +64,49 @@ class EventStream:
 
 
 # ----------------------------------------------------------------------------------------------
-# Standard MIDI File reader (host side; follows mido 1.3.2: merge_tracks, tick2second, running tempo)
+# Standard MIDI File reader: native (csrc/smf.cu, mmg_smf_parse); follows mido 1.3.2: merge_tracks, tick2second, running tempo
 # ----------------------------------------------------------------------------------------------
-def _vlq(buf, i):
-    v = 0
-    while True:
-        b = buf[i]
-        i += 1
-        v = (v << 7) | (b & 0x7F)
-        if not b & 0x80:
-            return v, i
-
-
-def _parse_track(buf):
-    """-> list of (abs_tick, kind, pitch, velocity, tempo_or_None, is_end_of_track)"""
-    i, t, status, out = 0, 0, 0, []
-    n = len(buf)
-    while i < n:
-        d, i = _vlq(buf, i)
-        t += d
-        b = buf[i]
-        if b == 0xFF:                                   # meta
-            typ = buf[i + 1]
-            ln, j = _vlq(buf, i + 2)
-            data = buf[j:j + ln]
-            i = j + ln
-            tempo = int.from_bytes(data, "big") if typ == 0x51 and ln == 3 else None
-            out.append((t, KIND_OTHER, 0, 0, tempo, typ == 0x2F))
-        elif b in (0xF0, 0xF7):                         # sysex
-            ln, j = _vlq(buf, i + 1)
-            i = j + ln
-            out.append((t, KIND_OTHER, 0, 0, None, False))
-        else:
-            if b & 0x80:
-                status = b
-                i += 1
-            hi = status & 0xF0
-            nbytes = 1 if hi in (0xC0, 0xD0) else 2
-            if status >= 0xF0:                           # system common / realtime
-                nbytes = {0xF1: 1, 0xF2: 2, 0xF3: 1}.get(status, 0)
-            d1 = buf[i] if nbytes >= 1 else 0
-            d2 = buf[i + 1] if nbytes >= 2 else 0
-            i += nbytes
-            kind = KIND_ON if hi == 0x90 else KIND_OFF if hi == 0x80 else KIND_OTHER
-            out.append((t, kind, d1 if kind else 0, d2 if kind else 0, None, False))
-    return out
-
-
 def read_smf(path):
     """Parses a type-0/1 Standard MIDI File into an EventStream the way ``for msg in mido.MidiFile``
     yields it (datasets.py:18,34): tracks merged by absolute tick (stable), end_of_track metas
     dropped and one re-appended, delta seconds = ticks * (tempo * 1e-6 / ticks_per_beat) with the
-    tempo switching after each set_tempo message."""
+    tempo switching after each set_tempo message.  The parsing is ``mmg_smf_parse`` of the C-ABI library (host code);
+    ``oracle/smf_oracle.py`` is its Python checker."""
     with open(path, "rb") as f:
         raw = f.read()
-    if raw[:4] != b"MThd":
-        raise ValueError(f"{path}: not a Standard MIDI File")
-    hlen, fmt, ntrk, div = struct.unpack(">IHHH", raw[4:14])
+    return parse_smf_bytes(raw, filename=path)
+
+
+def parse_smf_bytes(raw, filename=None):
+    """``read_smf`` for a file image already in memory (bytes)."""
+    name = filename if filename is not None else "<bytes>"
+    if raw[:4] != b"MThd" or len(raw) < 14:
+        raise ValueError(f"{name}: not a Standard MIDI File")
+    fmt, _, div = struct.unpack(">HHH", raw[8:14])
     if div & 0x8000:
         raise ValueError("SMPTE time division is not supported")
     if fmt == 2:
         raise TypeError("can't merge tracks in type 2 (asynchronous) file")
-    pos, events = 8 + hlen, []
-    for _ in range(ntrk):
-        while raw[pos:pos + 4] != b"MTrk":
-            pos += 8 + struct.unpack(">I", raw[pos + 4:pos + 8])[0]
-        ln = struct.unpack(">I", raw[pos + 4:pos + 8])[0]
-        events.extend(_parse_track(raw[pos + 8:pos + 8 + ln]))
-        pos += 8 + ln
-    events.sort(key=lambda e: e[0])                      # stable, like mido.merge_tracks
-    end_tick = max([e[0] for e in events], default=0)
-    events = [e for e in events if not e[5]] + [(end_tick, KIND_OTHER, 0, 0, None, True)]
-    ticks = np.array([e[0] for e in events], dtype=np.int64)
-    dticks = np.diff(ticks, prepend=0)
-    tempo, dt = 500000, np.zeros(len(events), dtype=np.float64)
-    for i, e in enumerate(events):
-        if dticks[i] > 0:
-            dt[i] = int(dticks[i]) * (tempo * 1e-6 / div)
-        if e[4] is not None:
-            tempo = e[4]
-    kind = np.array([e[1] for e in events], dtype=np.uint32)
-    meta = kind | (np.array([e[2] for e in events], dtype=np.uint32) << 8) | (np.array([e[3] for e in events], dtype=np.uint32) << 16)
+    lib = N.lib()
+    cap = int(lib.mmg_smf_max_messages(len(raw)))
+    dt, meta, ticks = np.empty(cap, dtype=np.float64), np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.int64)
+    t_tick, t_us = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int32)
+    n, tpb, nt = ctypes.c_int64(0), ctypes.c_int(0), ctypes.c_int64(0)
+    buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+    rc = lib.mmg_smf_parse(buf, len(raw), dt.ctypes.data, meta.ctypes.data, ticks.ctypes.data, cap, ctypes.byref(n), ctypes.byref(tpb),
+                           t_tick.ctypes.data, t_us.ctypes.data, cap, ctypes.byref(nt))
+    if rc != 0:
+        raise ValueError(f"{name}: {lib.mmg_last_error().decode()}")
+    n, nt = n.value, nt.value
+    dt, meta, ticks = dt[:n].copy(), meta[:n].copy(), ticks[:n]
     # beat grid: quarter-note beats along the tempo map up to the last note event (host-side estimate of
     # pretty_midi.get_beats; parity at this boundary is unpinned)
-    note_ticks = ticks[kind != 0]
-    beats = _beat_grid(events, div, int(note_ticks.max()) if len(note_ticks) else 0)
-    return EventStream(dt, meta, beats, filename=path)
-
-
-def _beat_grid(events, div, last_tick):
-    changes = [(0, 500000)] + [(e[0], e[4]) for e in events if e[4] is not None]
-    beats, t_sec, tick, k = [], 0.0, 0, 0
-    tempo = changes[0][1]
-    while tick <= last_tick:
-        beats.append(t_sec)
-        nxt = tick + div
-        while k + 1 < len(changes) and changes[k + 1][0] < nxt:      # integrate across tempo changes
-            k += 1
-            c_tick = max(changes[k][0], tick)
-            t_sec += (c_tick - tick) * (tempo * 1e-6 / div)
-            tick, tempo = c_tick, changes[k][1]
-        t_sec += (nxt - tick) * (tempo * 1e-6 / div)
-        tick = nxt
-    return np.array(beats, dtype=np.float64)
+    note_ticks = ticks[(meta & 0xFF) != 0]
+    last = int(note_ticks.max()) if len(note_ticks) else 0
+    beats = np.empty(last // tpb.value + 1, dtype=np.float64)
+    nb = ctypes.c_int64(0)
+    N.check(lib.mmg_smf_beat_grid(t_tick.ctypes.data, t_us.ctypes.data, nt, tpb.value, last, beats.ctypes.data, len(beats), ctypes.byref(nb)), "mmg_smf_beat_grid")
+    return EventStream(dt, meta, beats, filename=filename)
 
 
 # ----------------------------------------------------------------------------------------------

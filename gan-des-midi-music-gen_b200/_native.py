@@ -21,6 +21,9 @@ SIGNATURES = {
     "mmg_raster_out_width": (_I, [_I, _I]),
     "mmg_raster_workspace_bytes": (_Z, [_L, _L]),
     "mmg_raster_set_mode": (_I, [_I]),
+    "mmg_smf_max_messages": (_L, [_Z]),
+    "mmg_smf_parse": (_I, [_P, _Z, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P]),
+    "mmg_smf_beat_grid": (_I, [_P, _P, _L, _I, _L, _P, _L, _P]),
     "mmg_raster_piano_roll": (_I, [_P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mmg_bce_logits_f32": (_I, [_P, _P, _F, _L, _P, _I, _P, _F, _P, _P]),
     "mmg_fill_scalar_f32": (_I, [_P, _P, _L, _P]),

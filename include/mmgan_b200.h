@@ -46,6 +46,20 @@ int mmg_raster_piano_roll(const double* dt, const uint32_t* meta, const int64_t*
                           int64_t total_events, int sequence_length, int start, int end, int out_dtype, void* out,
                           int32_t* status, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- Standard MIDI File reader (host code, no device work): what `for msg in mido.MidiFile(path)` yields, datasets.py:18,34 (mido 1.3.2:
+ * merge_tracks by absolute tick, stable; end_of_track metas dropped and one re-appended at the last tick; delta seconds with the RUNNING tempo,
+ * ticks * (tempo * 1e-6 / ticks_per_beat)).  data / len = the file image.  Outputs for message i: dt[i] seconds, meta[i] in the rasteriser's
+ * record format (above), abs_tick[i] (may be NULL); capacity >= mmg_smf_max_messages(len) always suffices.  tempo_tick / tempo_us (may be NULL):
+ * the set_tempo messages in stream order (for the beat grid); *n_tempo their count.  -1: not an SMF / malformed (the message says where),
+ * -2: SMPTE division or a type-2 file (mido raises for those too), -3: capacity too small. */
+int64_t mmg_smf_max_messages(size_t len);
+int mmg_smf_parse(const unsigned char* data, size_t len, double* dt, uint32_t* meta, int64_t* abs_tick, int64_t capacity, int64_t* n_messages,
+                  int* ticks_per_beat, int64_t* tempo_tick, int32_t* tempo_us, int64_t tempo_capacity, int64_t* n_tempo);
+/* quarter-note beat grid along that tempo map up to last_tick (stand-in for pretty_midi.get_beats, datasets.py:57): last_tick / ticks_per_beat + 1
+ * values (= *n_beats; -3 when capacity is smaller) */
+int mmg_smf_beat_grid(const int64_t* tempo_tick, const int32_t* tempo_us, int64_t n_tempo, int ticks_per_beat, int64_t last_tick, double* beats,
+                      int64_t capacity, int64_t* n_beats);
+
 /* ---- losses / optimiser ----
  * nn.BCEWithLogitsLoss() mean (network_tests.py:248,304-306,313; SIMNN.py:257): loss[0] (+)= mean(l_i);
  * dlogits = (sigmoid(x) - y) * gscale * (*gscale_dev if not NULL).  targets NULL -> constant target. */

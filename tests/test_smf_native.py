@@ -1,0 +1,131 @@
+"""The native Standard MIDI File reader (csrc/smf.cu: mmg_smf_parse, what datasets.read_smf calls) against its Python checker
+(oracle/smf_oracle.py, the restatement of mido 1.3.2's reader): bit-exact message streams (delta seconds as float64, packed records, absolute
+ticks, tempo map) on the reference's shipped .mid files, on generated multi-track files that use every event class (running status, metas,
+sysex, one- and two-byte channel messages, tempo changes, unknown chunks), and the same refusals for what mido refuses."""
+import os
+import struct
+import time
+
+import numpy as np
+import pytest
+
+import smf_oracle as so
+from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+
+REF = "/root/reference"
+HAVE_REF = os.path.isdir(REF)
+
+
+def _vlq(n):
+    out = [n & 0x7F]
+    n >>= 7
+    while n:
+        out.append(0x80 | (n & 0x7F))
+        n >>= 7
+    return bytes(reversed(out))
+
+
+def _random_smf(rng, ntrk, events_per_track, tpb=480, junk_chunk=False):
+    tracks = []
+    for _ in range(ntrk):
+        body, status = b"", None
+        for _ in range(events_per_track):
+            body += _vlq(int(rng.choice([0, 0, 1, 7, 120, 480, 5000, 70000])))
+            r = rng.random()
+            if r < 0.70:                                    # note on / off (velocity 0 note_ons included), often with running status
+                st = int(rng.choice([0x90, 0x80])) | int(rng.integers(0, 16))
+                if st != status or rng.random() < 0.3:
+                    body += bytes([st])
+                    status = st
+                body += bytes([int(rng.integers(0, 128)), int(rng.choice([0, 1, 64, 127]))])
+            elif r < 0.78:                                  # program change / channel pressure: one data byte
+                st = int(rng.choice([0xC0, 0xD0])) | int(rng.integers(0, 16))
+                body += bytes([st, int(rng.integers(0, 128))])
+                status = st
+            elif r < 0.84:                                  # controller / pitch bend: two data bytes
+                st = int(rng.choice([0xB0, 0xE0, 0xA0])) | int(rng.integers(0, 16))
+                body += bytes([st, int(rng.integers(0, 128)), int(rng.integers(0, 128))])
+                status = st
+            elif r < 0.92:                                  # set_tempo
+                body += b"\xff\x51\x03" + int(rng.integers(100000, 2000000)).to_bytes(3, "big")
+            elif r < 0.96:                                  # other metas (text of a VLQ-sized length, an early end_of_track)
+                if rng.random() < 0.3:
+                    body += b"\xff\x2f\x00"
+                else:
+                    n = int(rng.choice([0, 5, 200]))
+                    body += b"\xff\x01" + _vlq(n) + bytes(n)
+            else:                                           # sysex
+                n = int(rng.integers(0, 20))
+                body += bytes([int(rng.choice([0xF0, 0xF7]))]) + _vlq(n) + bytes(n)
+        body += _vlq(int(rng.integers(0, 100))) + b"\xff\x2f\x00"
+        tracks.append(b"MTrk" + struct.pack(">I", len(body)) + body)
+    chunks = b"".join(tracks)
+    if junk_chunk:
+        chunks = b"XFIH" + struct.pack(">I", 3) + b"abc" + chunks
+    return b"MThd" + struct.pack(">IHHH", 6, 1 if ntrk > 1 else 0, ntrk, tpb) + chunks
+
+
+def _check(raw):
+    dt, meta, ticks, div, changes = so.read_smf_bytes(raw)
+    ev = ds.parse_smf_bytes(raw)
+    assert ev.dt.dtype == np.float64 and np.array_equal(ev.dt, dt) and np.array_equal(ev.meta, meta)
+    note = ticks[(meta & 0xFF) != 0]
+    want_beats = so.beat_grid([(0, 500000)] + changes, div, int(note.max()) if len(note) else 0)
+    assert np.array_equal(ev.beats, want_beats)
+    return len(dt)
+
+
+@pytest.mark.parametrize("seed,ntrk,n,tpb,junk", [(0, 1, 50, 480, False), (1, 3, 400, 96, False), (2, 7, 2000, 960, True), (3, 2, 1, 24, False), (4, 16, 300, 32767, True)])
+def test_native_reader_equals_oracle_on_generated_files(seed, ntrk, n, tpb, junk):
+    total = _check(_random_smf(np.random.default_rng(seed), ntrk, n, tpb, junk))
+    assert total >= 1
+
+
+def test_native_reader_empty_tracks():
+    raw = b"MThd" + struct.pack(">IHHH", 6, 1, 2, 480) + b"MTrk" + struct.pack(">I", 0) + b"MTrk" + struct.pack(">I", 4) + b"\x00\xff\x2f\x00"
+    assert _check(raw) == 1                                 # only the re-appended end_of_track
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_native_reader_equals_oracle_on_shipped_files(golden_dir):
+    names = list(np.load(os.path.join(golden_dir, "midi_streams.npz"))["names"])
+    assert len(names) == 30
+    for rel in names:
+        with open(os.path.join(REF, rel), "rb") as f:
+            _check(f.read())
+
+
+def test_native_reader_refusals(tmp_path):
+    ok = _random_smf(np.random.default_rng(9), 2, 20)
+    with pytest.raises(ValueError, match="not a Standard MIDI File"):
+        ds.parse_smf_bytes(b"RIFF" + ok[4:])
+    with pytest.raises(ValueError, match="SMPTE"):
+        ds.parse_smf_bytes(ok[:12] + struct.pack(">H", 0xE728) + ok[14:])
+    with pytest.raises(TypeError, match="type 2"):
+        ds.parse_smf_bytes(ok[:8] + struct.pack(">H", 2) + ok[10:])
+    with pytest.raises(ValueError, match="truncated|missing"):
+        ds.parse_smf_bytes(ok[:-7])
+    with pytest.raises(ValueError, match="missing"):
+        ds.parse_smf_bytes(ok[:10] + struct.pack(">H", 3) + ok[12:])          # header promises a third track
+    # the C entry point itself: capacity and argument checks
+    import ctypes
+    from gan_des_midi_music_gen_b200 import _native as N
+    lib = N.lib()
+    dt, meta = np.empty(4), np.empty(4, dtype=np.uint32)
+    n, tpb = ctypes.c_int64(0), ctypes.c_int(0)
+    buf = (ctypes.c_ubyte * len(ok)).from_buffer_copy(ok)
+    rc = lib.mmg_smf_parse(buf, len(ok), dt.ctypes.data, meta.ctypes.data, None, 4, ctypes.byref(n), ctypes.byref(tpb), None, None, 0, None)
+    assert rc == -3 and b"more than 4 messages" in lib.mmg_last_error()
+    assert lib.mmg_smf_parse(None, 0, None, None, None, 0, None, None, None, None, 0, None) == -1
+    assert lib.mmg_smf_max_messages(100) >= 51
+
+
+def test_native_reader_is_the_fast_one():
+    """MAESTRO-scale file (7 tracks x 8000 events): the native reader must beat the per-message Python loop it replaced by a wide margin."""
+    raw = _random_smf(np.random.default_rng(5), 7, 8000)
+    t0 = time.perf_counter(); so.read_smf_bytes(raw); t_py = time.perf_counter() - t0
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter(); ev = ds.parse_smf_bytes(raw); best = min(best, time.perf_counter() - t0)
+    print(f"{len(ev)} messages: oracle {t_py * 1e3:.1f} ms, native reader incl. beat grid {best * 1e3:.2f} ms")
+    assert best < t_py / 3
