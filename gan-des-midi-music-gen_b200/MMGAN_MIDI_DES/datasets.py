@@ -77,6 +77,18 @@ def read_smf(path):
     return parse_smf_bytes(raw, filename=path)
 
 
+def read_smf_many(paths, workers=None):
+    """``[read_smf(p) for p in paths]`` on a thread pool (the file read and the native parse both run without the interpreter lock): the
+    MAESTRO corpus is 1276 files (notebook cell 10).  Results are in input order."""
+    paths = list(paths)
+    workers = min(32, os.cpu_count() or 1) if workers is None else int(workers)
+    if len(paths) <= 1 or workers <= 1:
+        return [read_smf(p) for p in paths]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(read_smf, paths))
+
+
 def parse_smf_bytes(raw, filename=None):
     """``read_smf`` for a file image already in memory (bytes)."""
     name = filename if filename is not None else "<bytes>"
@@ -238,7 +250,9 @@ def preprocess_maestro(inputs, sample_size=300, sequence_length=50, beats_length
     (path or :class:`EventStream`) is rasterised over a ``sample_size``-step window, cut into ``sequence_length``-step slices, slice 0 is
     skipped, and each kept slice becomes a ``(piano_roll (128,L), durations (128,L), beats (beats_length,))`` triple of float32 CPU
     tensors -- the list ``MaestroDatasetPickle`` unpickles (datasets.py:73-87)."""
-    streams = [_as_stream(x) for x in inputs]
+    inputs = list(inputs)
+    parsed = iter(read_smf_many([x for x in inputs if isinstance(x, str)]))              # all paths at once, on a thread pool
+    streams = [next(parsed) if isinstance(x, str) else _as_stream(x) for x in inputs]
     if not streams:
         return []
     rolls = rasterize_batch(streams, sample_size, 0, sample_size, device=device).cpu()       # (S, 2, 128, sample_size), bit-exact

@@ -129,3 +129,23 @@ def test_native_reader_is_the_fast_one():
         t0 = time.perf_counter(); ev = ds.parse_smf_bytes(raw); best = min(best, time.perf_counter() - t0)
     print(f"{len(ev)} messages: oracle {t_py * 1e3:.1f} ms, native reader incl. beat grid {best * 1e3:.2f} ms")
     assert best < t_py / 3
+
+
+def test_read_smf_many_equals_serial(tmp_path):
+    paths = []
+    for i in range(12):
+        p = str(tmp_path / f"f{i}.mid")
+        with open(p, "wb") as f:
+            f.write(_random_smf(np.random.default_rng(100 + i), 1 + i % 4, 200 + 50 * i))
+        paths.append(p)
+    serial = [ds.read_smf(p) for p in paths]
+    for workers in (None, 1, 3):
+        many = ds.read_smf_many(paths, workers=workers)
+        assert [m.filename for m in many] == paths
+        for a, b in zip(serial, many):
+            assert np.array_equal(a.dt, b.dt) and np.array_equal(a.meta, b.meta) and np.array_equal(a.beats, b.beats)
+    assert ds.read_smf_many([]) == []
+    with pytest.raises(ValueError, match="not a Standard MIDI File"):       # an error in one file surfaces
+        bad = str(tmp_path / "bad.mid")
+        open(bad, "wb").write(b"not midi at all....")
+        ds.read_smf_many(paths[:2] + [bad])
