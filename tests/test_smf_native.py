@@ -149,3 +149,27 @@ def test_read_smf_many_equals_serial(tmp_path):
         bad = str(tmp_path / "bad.mid")
         open(bad, "wb").write(b"not midi at all....")
         ds.read_smf_many(paths[:2] + [bad])
+
+
+def test_preprocess_maestro_reads_paths_in_order(tmp_path, monkeypatch):
+    """host logic of preprocess_maestro with paths and EventStreams mixed (the device rasterisation is replaced by a stand-in that writes each
+    stream's message count into its roll): the thread-pooled reader keeps every file at its position."""
+    import torch
+    paths, want = [], []
+    for i in range(5):
+        p = str(tmp_path / f"g{i}.mid")
+        raw = _random_smf(np.random.default_rng(200 + i), 2, 300 + 40 * i, tpb=480)
+        open(p, "wb").write(raw)
+        paths.append(p)
+        want.append(len(so.read_smf_bytes(raw)[0]))
+    extra = ds.EventStream(np.full(700, 0.5), np.zeros(700, dtype=np.uint32), np.arange(3.0))
+    inputs = [paths[0], extra, paths[1], paths[2], paths[3], paths[4]]
+    want = [want[0], 700, want[1], want[2], want[3], want[4]]
+
+    def fake_rasterize_batch(streams, sequence_length, start, end, device="cuda", out_dtype=torch.float32):
+        return torch.stack([torch.full((2, 128, end - start), float(len(s))) for s in streams])
+
+    monkeypatch.setattr(ds, "rasterize_batch", fake_rasterize_batch)
+    monkeypatch.setattr(ds, "total_time_steps", lambda s, sample_size: 2 * 50)      # two slices per song -> slice 1 is kept
+    out = ds.preprocess_maestro(inputs, sample_size=300, sequence_length=50, device="cpu")
+    assert [int(r[0][0, 0]) for r in out] == want
