@@ -230,18 +230,62 @@ def process_adjsim_log(n=5000, baseline=70, range=50, instruments=np.arange(0, 1
     return ds.generate_piano_roll(stream, start=start, end=end)
 
 
-def sim_logs_to_event_batch(logs, instruments, note_levels, gen2_outputs, generate=False):
+def _log_text(lines):
+    """the log lines as one '\\n'-separated byte string (what ``readlines`` split); a str / bytes object is taken as the file's text"""
+    if isinstance(lines, bytes):
+        return lines
+    if isinstance(lines, str):
+        return lines.encode()
+    return "".join(l if l.endswith("\n") else l + "\n" for l in lines).encode()
+
+
+def _gen2_rows(g):
+    g = np.asarray(g)
+    return (np.ascontiguousarray(g, dtype=np.float32), 1) if g.dtype == np.float32 else (np.ascontiguousarray(g, dtype=np.float64), 0)
+
+
+def sim_log_to_event_stream_native(log_lines, instruments, note_levels, gen2_output, generate=False):
+    """``sim_log_to_event_stream(...)[0]`` through the C-ABI library (``mmg_simlog_to_events``, csrc/simlog.cu): the same message stream, bit for
+    bit, without the Python state machine (no ``MidiGenerator`` object comes back and no .mid is written)."""
+    import ctypes
+    lib = ds.N.lib()
+    text = _log_text(log_lines)
+    ins, nl = np.ascontiguousarray(np.asarray(instruments), dtype=np.int64), np.ascontiguousarray(np.asarray(note_levels), dtype=np.int64)
+    g, is_f32 = _gen2_rows(gen2_output)
+    cap = lib.mmg_simlog_max_messages()
+    dt, meta, n = np.empty(cap, dtype=np.float64), np.empty(cap, dtype=np.uint32), ctypes.c_int64(0)
+    rc = lib.mmg_simlog_to_events(text, len(text), ins.ctypes.data, len(ins), nl.ctypes.data, len(nl), g.ctypes.data, len(g), is_f32, int(bool(generate)),
+                                  dt.ctypes.data, meta.ctypes.data, cap, ctypes.byref(n))
+    if rc != 0:
+        raise ValueError(lib.mmg_last_error().decode())
+    return ds.EventStream(dt[:n.value].copy(), meta[:n.value].copy())
+
+
+def sim_logs_to_event_batch(logs, instruments, note_levels, gen2_outputs, generate=False, threads=0):
     """A batch of simulated songs -> pinned ``(dt float64, meta int32, offsets int64)`` host tensors, the ``fake_*_events`` entry of a
-    ``trainer.HostBatchPipeline`` batch.  ``logs[i]`` are song i's log lines; ``instruments[i]`` / ``note_levels[i]`` / ``gen2_outputs[i]`` the
-    per-song arguments ``matrix_to_midi`` passes (matrix_sim_process.py:171)."""
+    ``trainer.HostBatchPipeline`` batch.  ``logs[i]`` are song i's log lines (or its log text); ``instruments[i]`` / ``note_levels[i]`` /
+    ``gen2_outputs[i]`` the per-song arguments ``matrix_to_midi`` passes (matrix_sim_process.py:171).  The conversion runs natively on ``threads``
+    host threads (0 = all cores): ``mmg_simlog_batch_to_events``; ``sim_log_to_event_stream`` is the same thing per song in Python."""
     import torch
-    streams = [sim_log_to_event_stream(lg, ins, nl, g2, generate)[0] for lg, ins, nl, g2 in zip(logs, instruments, note_levels, gen2_outputs)]
-    lens = np.array([len(s) for s in streams], dtype=np.int64)
-    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    dt = np.concatenate([s.dt for s in streams]) if streams else np.zeros(0)
-    meta = np.concatenate([s.meta for s in streams]) if streams else np.zeros(0, dtype=np.uint32)
-    return tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if torch.cuda.is_available() else torch.from_numpy(np.ascontiguousarray(a))
-                 for a in (dt.astype(np.float64), meta.astype(np.uint32).view(np.int32), off))
+    lib = ds.N.lib()
+    texts = [_log_text(lg) for lg in logs]
+    S = len(texts)
+    log_off = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum([len(t) for t in texts], out=log_off[1:])
+    blob = b"".join(texts)
+    ins = np.ascontiguousarray(np.asarray(instruments), dtype=np.int64).reshape(S, -1) if S else np.zeros((0, 1), dtype=np.int64)
+    nl = np.ascontiguousarray(np.asarray(note_levels), dtype=np.int64).reshape(S, -1) if S else np.zeros((0, 1), dtype=np.int64)
+    g, is_f32 = _gen2_rows(gen2_outputs)
+    g = g.reshape(S, -1) if S else np.zeros((0, 6), dtype=g.dtype)
+    slot = lib.mmg_simlog_max_messages()
+    dt, meta, off = np.empty(S * slot, dtype=np.float64), np.empty(S * slot, dtype=np.uint32), np.zeros(S + 1, dtype=np.int64)
+    rc = lib.mmg_simlog_batch_to_events(blob, log_off.ctypes.data, S, ins.ctypes.data, ins.shape[1], nl.ctypes.data, nl.shape[1], g.ctypes.data, g.shape[1],
+                                        is_f32, int(bool(generate)), dt.ctypes.data, meta.ctypes.data, off.ctypes.data, int(threads))
+    if rc != 0:
+        raise ValueError(lib.mmg_last_error().decode())
+    total = int(off[-1])
+    arrays = (dt[:total].copy(), meta[:total].view(np.int32).copy(), off)
+    return tuple(torch.from_numpy(a).pin_memory() if torch.cuda.is_available() else torch.from_numpy(a) for a in arrays)
 
 
 # ----------------------------------------------------------------------------------------------

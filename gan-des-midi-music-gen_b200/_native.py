@@ -24,6 +24,9 @@ SIGNATURES = {
     "mmg_smf_max_messages": (_L, [_Z]),
     "mmg_smf_parse": (_I, [_P, _Z, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P]),
     "mmg_smf_beat_grid": (_I, [_P, _P, _L, _I, _L, _P, _L, _P]),
+    "mmg_simlog_max_messages": (_I, []),
+    "mmg_simlog_to_events": (_I, [_P, _Z, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "mmg_simlog_batch_to_events": (_I, [_P, _P, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I]),
     "mmg_raster_piano_roll": (_I, [_P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mmg_bce_logits_f32": (_I, [_P, _P, _F, _L, _P, _I, _P, _F, _P, _P]),
     "mmg_fill_scalar_f32": (_I, [_P, _P, _L, _P]),

@@ -60,6 +60,20 @@ int mmg_smf_parse(const unsigned char* data, size_t len, double* dt, uint32_t* m
 int mmg_smf_beat_grid(const int64_t* tempo_tick, const int32_t* tempo_us, int64_t n_tempo, int ticks_per_beat, int64_t last_tick, double* beats,
                       int64_t capacity, int64_t* n_beats);
 
+/* ---- simulator log -> note-event stream (host code, all cores): MMGAN_MIDI_DES/sim_log_to_midi.py:13-277 (MidiGenerator, LogLineProcessor,
+ * process_adjsim_log up to the generate_piano_roll call) followed by mido's playback of the saved track (datasets.py:34) = the message stream the
+ * rasteriser above consumes.  log = the DES log lines, '\n'-separated; instruments / note_levels = int(v) of the reference's arguments; gen2 = the beat
+ * generator's output row (>= 6 values) as float32 (gen2_is_f32: products are formed in single precision like numpy float32 scalars) or float64;
+ * generate as in process_adjsim_log.  dt / meta: room for mmg_simlog_max_messages() (512) messages per song.  -1 "Error in processing log file" where
+ * the reference raises it (unknown server id, non-integer customer id, modulo by zero ...).  The batch form runs n_threads host threads (0 = all
+ * cores), takes rows per song and returns the streams packed: song s at [offsets[s], offsets[s+1]). */
+int mmg_simlog_max_messages(void);
+int mmg_simlog_to_events(const char* log, size_t log_len, const int64_t* instruments, int n_instruments, const int64_t* note_levels, int n_note_levels,
+                         const void* gen2, int gen2_len, int gen2_is_f32, int generate, double* dt, uint32_t* meta, int64_t capacity, int64_t* n_messages);
+int mmg_simlog_batch_to_events(const char* logs, const int64_t* log_offsets, int64_t n_songs, const int64_t* instruments, int n_instruments,
+                               const int64_t* note_levels, int n_note_levels, const void* gen2, int gen2_len, int gen2_is_f32, int generate, double* dt,
+                               uint32_t* meta, int64_t* offsets, int n_threads);
+
 /* ---- losses / optimiser ----
  * nn.BCEWithLogitsLoss() mean (network_tests.py:248,304-306,313; SIMNN.py:257): loss[0] (+)= mean(l_i);
  * dlogits = (sigmoid(x) - y) * gscale * (*gscale_dev if not NULL).  targets NULL -> constant target. */

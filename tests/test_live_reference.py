@@ -87,6 +87,8 @@ def test_simlog_mirror_vs_reference_random_logs(ref):
         want_dt = np.array([x[1] for x in seen["msgs"]], dtype=np.float64)
         want_meta = np.array([(kinds[x[0]] | (x[2] << 8) | (x[3] << 16)) if x[0] in kinds else 0 for x in seen["msgs"]], dtype=np.uint32)
         assert np.array_equal(stream.dt, want_dt) and np.array_equal(stream.meta, want_meta), case
+        native = sl.sim_log_to_event_stream_native(lines, instruments, note_levels, gen2, generate)      # csrc/simlog.cu against the unmodified reference
+        assert np.array_equal(native.dt, want_dt) and np.array_equal(native.meta, want_meta), case
         k, p, v = ro.unpack_meta(stream.meta)
         a, b = ro.raster_events(stream.dt, k, p, v, 100, 0, 50)
         assert np.array_equal(a, roll) and np.array_equal(b, dur), case

@@ -55,6 +55,94 @@ def test_quirks_kept(golden_dir, tmp_path):
     assert np.array_equal(back.meta, stream.meta) and np.allclose(back.dt, stream.dt, rtol=0, atol=0)
 
 
+def test_native_converter_matches_reference_vectors(golden_dir):
+    """csrc/simlog.cu (mmg_simlog_to_events) on the vectors frozen from the unmodified reference: float64 delta seconds and records, bit-exact."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
+    n = 0
+    for name, c, lines, generate, _, _ in _cases(golden_dir):
+        stream = sl.sim_log_to_event_stream_native(lines, c[name + ".instruments"], c[name + ".note_levels"], c[name + ".gen2"], generate)
+        assert np.array_equal(stream.dt, c[name + ".dt"]) and np.array_equal(stream.meta, c[name + ".meta"]), name
+        n += 1
+    assert n == 11
+
+
+def _fuzz_log(rng, n_lines, t_max):
+    """synthetic logs that also visit the corners: integer and fractional times, times past 200, '.5'-style numbers, junk, huge queues"""
+    sys_path_oracle()
+    from make_golden import synth_sim_log
+    lines = synth_sim_log(rng, n_lines, t_max, n_servers=int(rng.choice([3, 16])), n_customers=int(rng.choice([5, 40, 4000])), junk=0.15)
+    for _ in range(int(rng.integers(0, 6))):
+        i = int(rng.integers(0, len(lines)))
+        lines[i] = str(rng.choice(["INFO:root:.5 - 4 - 2 - arrival\n", "INFO:root:7 - 4 - 2 - departure trailing\n", "INFO:root:12..5 - 4 - 2 - arrival\n",
+                                   "INFO:root:3.25 - 8 - 1 - processing\n", " INFO:root:3 - 8 - 1 - arrival\n", "INFO:root:3 - 8 - 1 -arrival\n", "\n",
+                                   "INFO:root:250.5 - 2 - 3 - arrival\n", "INFO:root:199.99 - 6 - 0 - departure"]))
+    return lines
+
+
+def sys_path_oracle():
+    import sys
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+
+
+def test_native_converter_equals_python_mirror_on_random_logs():
+    """300 random logs through the Python state machine (itself pinned to the reference by the vectors above and the live test) and through the
+    native converter: identical streams; float32 and float64 gen2 rows (products in the row's own precision), generate on and off."""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
+    rng = np.random.default_rng(11)
+    with_notes = 0
+    for case in range(300):
+        lines = _fuzz_log(rng, int(rng.choice([100, 200, 300, 137, 500, 1200])), float(rng.choice([20.0, 60.0, 150.0, 320.0])))
+        g = np.concatenate([rng.random(6) * np.array([1, 1, 1.3, 1, float(rng.choice([1.0, 1.0, 12.0, 0.0])), float(rng.choice([1.0, 0.0]))]), rng.random(4)])
+        g = g.astype(np.float32) if case % 2 == 0 else g
+        ins, nl = rng.integers(0, 100, 16), rng.integers(0, 128, 16)
+        generate = bool(case % 3 == 0)
+        want, _ = sl.sim_log_to_event_stream(lines, ins, nl, g, generate)
+        got = sl.sim_log_to_event_stream_native(lines, ins, nl, g, generate)
+        assert np.array_equal(got.dt, want.dt) and np.array_equal(got.meta, want.meta), case
+        with_notes += int((want.meta != 0).any())
+    assert with_notes >= 100
+
+
+def test_native_converter_refuses_what_the_reference_refuses():
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
+    g = np.full(10, 0.2, dtype=np.float32)
+    for bad in (["INFO:root:1.0 - 4 - 99 - arrival\n"],                 # unknown server: KeyError
+                ["INFO:root:1.0 - 4 - 03 - arrival\n"],                 # '03' is not a key either
+                ["INFO:root:1.0 - 4.5 - 3 - arrival\n"],                # int('4.5')
+                ):
+        with pytest.raises(ValueError, match="Error in processing log file"):
+            sl.sim_log_to_event_stream(bad, np.arange(16), np.arange(16), g)
+        with pytest.raises(ValueError, match="Error in processing log file"):
+            sl.sim_log_to_event_stream_native(bad, np.arange(16), np.arange(16), g)
+    # the same lines are harmless where the reference never evaluates them: a departure of an unknown server, a customer the skips reject
+    ok = ["INFO:root:1.0 - 4 - 99 - departure\n", "INFO:root:1.0 - 7 - 99 - arrival\n", "INFO:root:300 - 4.5 - 3 - arrival\n"]
+    a, _ = sl.sim_log_to_event_stream(ok, np.arange(16), np.arange(16), g, True)
+    b = sl.sim_log_to_event_stream_native(ok, np.arange(16), np.arange(16), g, True)
+    assert np.array_equal(a.dt, b.dt) and np.array_equal(a.meta, b.meta)
+    with pytest.raises(ValueError, match="Error in processing log file"):       # one bad song fails the batch, naming it
+        sl.sim_logs_to_event_batch([ok, ["INFO:root:1.0 - 4 - 99 - arrival\n"]], [np.arange(16)] * 2, [np.arange(16)] * 2, [g, g], True)
+
+
+def test_native_batch_equals_per_song_and_is_thread_count_independent():
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
+    rng = np.random.default_rng(3)
+    S = 37
+    logs = [_fuzz_log(rng, int(rng.choice([100, 200, 300])), 60.0) for _ in range(S)]
+    ins, nl = rng.integers(0, 100, (S, 16)), rng.integers(0, 128, (S, 16))
+    g = rng.random((S, 10)).astype(np.float32)
+    per_song = [sl.sim_log_to_event_stream(lg, ins[i], nl[i], g[i], False)[0] for i, lg in enumerate(logs)]
+    for threads in (1, 4, 0):
+        dt, meta, off = sl.sim_logs_to_event_batch(logs, ins, nl, g, False, threads=threads)
+        assert off.numel() == S + 1 and int(off[-1]) == sum(len(s) for s in per_song) == dt.numel() == meta.numel()
+        for i, s in enumerate(per_song):
+            a, b = int(off[i]), int(off[i + 1])
+            assert np.array_equal(dt[a:b].numpy(), s.dt) and np.array_equal(meta[a:b].numpy().view(np.uint32), s.meta), (threads, i)
+    dt, meta, off = sl.sim_logs_to_event_batch([], [], [], np.zeros((0, 10), dtype=np.float32))
+    assert dt.numel() == 0 and off.tolist() == [0]
+
+
 def test_event_batch_packing(golden_dir):
     from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
     cs = list(_cases(golden_dir))[:4]
