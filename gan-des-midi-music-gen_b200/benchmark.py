@@ -249,6 +249,64 @@ def _inference_leg(mmgan, device):
     return out
 
 
+def _host_front_end_leg():
+    """The host code on the input side of the rasteriser (no GPU involved): the native sim-log -> note-event conversion of a batch of simulated songs
+    (csrc/simlog.cu, all host threads) beside the Python state machine it mirrors, and the native Standard MIDI File reader (csrc/smf.cu) beside its
+    Python checker.  Synthetic inputs; a few seconds of CPU time."""
+    import struct
+    import smf_oracle as so                      # cpu baseline sample only
+    from .MMGAN_MIDI_DES import datasets as ds, sim_log_to_midi as sl
+    rng = np.random.default_rng(0)
+    S, n_lines = 2048, 320
+    one = []
+    for _ in range(32):
+        t = np.sort(rng.random(n_lines) * 60.0)
+        one.append("".join(f"INFO:root:{t[i]:.4f} - {int(rng.integers(0, 40))} - {int(rng.integers(0, 16))} - {'arrival' if rng.random() < 0.55 else 'departure'}\n"
+                           for i in range(n_lines)).encode())
+    logs = [one[i % 32] for i in range(S)]
+    ins, nl, g = rng.integers(0, 100, (S, 16)), rng.integers(0, 128, (S, 16)), rng.random((S, 10)).astype(np.float32)
+    sl.sim_logs_to_event_batch(logs[:64], ins[:64], nl[:64], g[:64], True)
+    t0 = time.perf_counter()
+    dt, _, _ = sl.sim_logs_to_event_batch(logs, ins, nl, g, True)
+    t_native = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_py = 16
+    for i in range(n_py):
+        sl.sim_log_to_event_stream(logs[i].decode().splitlines(True), ins[i], nl[i], g[i], True)
+    t_py = (time.perf_counter() - t0) / n_py
+    # one MAESTRO-scale file: 3 tracks x 12 000 note events with running status and tempo changes
+    def vlq(n):
+        out = [n & 0x7F]
+        n >>= 7
+        while n:
+            out.append(0x80 | (n & 0x7F))
+            n >>= 7
+        return bytes(reversed(out))
+    tracks = []
+    for _ in range(3):
+        body = bytearray()
+        for k in range(12000):
+            body += vlq(int(rng.integers(0, 240)))
+            body += (b"\xff\x51\x03" + int(rng.integers(300000, 900000)).to_bytes(3, "big")) if k % 500 == 0 else bytes([0x90 if k % 2 == 0 else 0x80, int(rng.integers(21, 109)), int(rng.integers(1, 128))])
+        body += b"\x00\xff\x2f\x00"
+        tracks.append(b"MTrk" + struct.pack(">I", len(body)) + bytes(body))
+    raw = b"MThd" + struct.pack(">IHHH", 6, 1, 3, 480) + b"".join(tracks)
+    ev = ds.parse_smf_bytes(raw)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ds.parse_smf_bytes(raw)
+    t_smf = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    so.read_smf_bytes(raw)
+    t_smf_py = time.perf_counter() - t0
+    return {"simlog_songs_per_sec": S / t_native, "simlog_messages_per_sec": int(dt.numel()) / t_native, "songs": S, "log_lines_per_song": n_lines,
+            "host_threads": os.cpu_count() or 1, "api": "sim_log_to_midi.sim_logs_to_event_batch -> mmg_simlog_batch_to_events (pinned dt / meta / offsets of one H2D copy)",
+            "cpu_baseline": {"value": 1.0 / t_py, "unit": "songs/s", "cores": 1, "kind": "port",
+                             "sample": f"{n_py} songs through the Python mirror of MidiGenerator (sim_log_to_midi.sim_log_to_event_stream)"},
+            "smf_messages_per_sec": len(ev) / t_smf, "smf_messages": len(ev),
+            "smf_cpu_baseline": {"value": len(ev) / t_smf_py, "unit": "messages/s", "cores": 1, "kind": "port", "sample": "the same file through oracle/smf_oracle.py"}}
+
+
 def run(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -444,6 +502,10 @@ def run(args):
             line["inference_sweep"] = _inference_leg(mmgan, device)
             line["gandes"] = _gandes_leg(device)
             line["gandes_mel"] = _mel_leg(device, peaks)
+            try:
+                line["host_front_end"] = _host_front_end_leg()
+            except Exception as e:                  # a secondary, CPU-only leg must never cost the headline line
+                line["host_front_end"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()
