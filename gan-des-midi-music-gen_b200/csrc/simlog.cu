@@ -28,6 +28,12 @@ struct Msg {
 
 struct PyError {};                                           // any exception inside the reference's try block
 
+struct Tok {                                                 // a matched group of the log line (points into the log text)
+    const char* p;
+    int n;
+    std::string str() const { return std::string(p, (size_t)n); }
+};
+
 inline long long pymod(long long x, long long m) {           // Python's %: the result has the sign of the divisor; ZeroDivisionError
     if (m == 0) throw PyError();
     long long r = x % m;
@@ -50,8 +56,14 @@ struct Song {
     std::vector<Msg> track;
     bool saved = false;
     long long previous_time = 0, current_instrument = 0;
+    // the reference keys its dictionaries by the server id AS WRITTEN ('3', '03' and '3.0' are three keys).  Canonical ids below 64 -- every id a
+    // real log holds -- live in arrays; any other spelling goes to the maps
+    struct Future { long long time, velocity, service; bool set; };
+    static constexpr int FAST = 64;
+    long long ql_fast[FAST];
+    bool ql_set[FAST];
+    Future fut_fast[FAST];
     std::unordered_map<std::string, long long> queue_lengths;
-    struct Future { long long time, velocity, service; };
     std::unordered_map<std::string, Future> future_events;
 
     template <typename T>
@@ -65,78 +77,92 @@ struct Song {
         var = trunc_mul<T>(g[5], 63);
         if (var == 0) var = 30;
         (void)pymod(trunc_mul<T>(g[5], 11), 11);             // the key signature's index (no effect on the stream)
+        track.reserve(512);
         track = {{SET_TEMPO, 0, tempo, 0}, {TIME_SIG, 0, 0, 0}, {KEY_SIG, 0, 0, 0}, {PROGRAM, 0, 0, 0}};      // generate_midi, :72-96
+        for (int i = 0; i < FAST; ++i) { ql_fast[i] = 0; ql_set[i] = false; fut_fast[i] = {0, 0, 0, false}; }
     }
 
     // index of a server id as the reference's dictionaries know it: keys are str(i), so only the canonical decimal spelling matches
-    int node_index(const std::string& s, int n) const {
-        if (s.empty() || s.size() > 9 || (s.size() > 1 && s[0] == '0')) return -1;
+    static long long canonical(const Tok& s) {               // value of a canonical decimal spelling (no dot, no leading zero), else -1
+        if (s.n <= 0 || s.n > 9 || (s.n > 1 && s.p[0] == '0')) return -1;
         long long v = 0;
-        for (char c : s) {
-            if (c < '0' || c > '9') return -1;
-            v = v * 10 + (c - '0');
+        for (int i = 0; i < s.n; ++i) {
+            if (s.p[i] < '0' || s.p[i] > '9') return -1;
+            v = v * 10 + (s.p[i] - '0');
         }
-        return v < n ? (int)v : -1;
+        return v;
     }
 
-    void process_line(const std::string& a1, const std::string& a2, const std::string& a3, bool arrival) {      // :99-180
+    void process_line(const Tok& a1, const Tok& a2, const Tok& a3, bool arrival) {      // :99-180
         // int(float(array1)); the regex admits digits and one dot only.  Up to 15 characters the nearest double cannot reach the next integer, so
         // the truncation is the integer part as written; longer spellings go through strtod (correctly rounded, like float())
         double tf;
-        if (a1.size() <= 15) {
+        if (a1.n <= 15) {
             long long ip = 0;
-            for (char c : a1) {
-                if (c == '.') break;
-                ip = ip * 10 + (c - '0');
-            }
+            for (int i = 0; i < a1.n && a1.p[i] != '.'; ++i) ip = ip * 10 + (a1.p[i] - '0');
             tf = (double)ip;
-        } else tf = strtod(a1.c_str(), nullptr);
+        } else tf = strtod(a1.str().c_str(), nullptr);
         if (!(tf < 200.0) || track.size() >= 500) return;    // max(0, .) of a non-negative number; `midi_time < 200 and len(track) < 500`
         long long midi_time = (long long)tf;
         if (previous_time > midi_time) midi_time = previous_time;
-        if (a2.find('.') != std::string::npos || a2.size() > 18) throw PyError();     // int('1.5') raises; (19+ digits: outside this port)
-        const long long cust = strtoll(a2.c_str(), nullptr, 10);
+        long long cust = 0;                                  // int(array2): int('1.5') raises; (19+ digits: outside this port)
+        if (a2.n > 18) throw PyError();
+        for (int i = 0; i < a2.n; ++i) {
+            if (a2.p[i] == '.') throw PyError();
+            cust = cust * 10 + (a2.p[i] - '0');
+        }
         const bool hit = pymod(cust, skip[0]) == 0 || pymod(cust, skip[1]) == 0 || pymod(cust, skip[2]) == 0;
         if (!hit) return;
+        const long long id = canonical(a3);
+        const bool fast = id >= 0 && id < FAST;
         if (arrival) {
-            long long ql = ++queue_lengths[a3];
+            long long ql;
+            if (fast) { ql = ++ql_fast[id]; ql_set[id] = true; }
+            else ql = ++queue_lengths[a3.str()];
             if (ql >= 127 && ql < 254) { ql = 254 - ql; ql = ql < 0 ? 0 : ql; ql = ql > 127 ? 127 : ql; }
             else if (ql >= 254) { ql = pymod(ql, 127); ql = ql > 127 ? 127 : ql; }
             const long long max_c = base + var;
             long long cid = base - var + cust;
             if (cid > max_c) cid = max_c - pymod(cid, max_c);
-            Future& ev = future_events[a3];
-            ev = {midi_time, pymod(cid, 126), ql};
+            const Future ev = {midi_time, pymod(cid, 126), ql, true};
+            if (fast) fut_fast[id] = ev;
+            else future_events[a3.str()] = ev;
             const long long on_time = previous_time > ev.time ? previous_time : ev.time;
             previous_time = on_time;
-            const int ii = node_index(a3, n_instr);
-            if (ii < 0) throw PyError();                      // KeyError: self.instruments[array3]
-            if (current_instrument != instruments[ii]) {
-                current_instrument = instruments[ii];
-                track.push_back({PROGRAM, on_time, instruments[ii], 0});
+            if (id < 0 || id >= n_instr) throw PyError();     // KeyError: self.instruments[array3]
+            if (current_instrument != instruments[id]) {
+                current_instrument = instruments[id];
+                track.push_back({PROGRAM, on_time, instruments[id], 0});
             }
-            const int ni = node_index(a3, n_notes);
-            if (ni < 0) throw PyError();                      // KeyError: self.note_offsets[array3]
-            track.push_back({NOTE_ON, on_time, note_levels[ni], ev.velocity});
+            if (id >= n_notes) throw PyError();               // KeyError: self.note_offsets[array3]
+            track.push_back({NOTE_ON, on_time, note_levels[id], ev.velocity});
         } else {
-            auto it = future_events.find(a3);
-            if (it != future_events.end()) {
-                const Future& ev = it->second;
-                const long long t = midi_time + (ev.service > 0 ? ev.service : 0);      // ev.time + (midi_time - ev.time) + max(0, service_time)
+            const Future* ev = nullptr;
+            if (fast) { if (fut_fast[id].set) ev = &fut_fast[id]; }
+            else {
+                auto it = future_events.find(a3.str());
+                if (it != future_events.end()) ev = &it->second;
+            }
+            if (ev) {
+                const long long t = midi_time + (ev->service > 0 ? ev->service : 0);    // ev.time + (midi_time - ev.time) + max(0, service_time)
                 const long long off_time = previous_time > t ? previous_time : t;
                 previous_time = off_time;
-                const int ii = node_index(a3, n_instr), ni = node_index(a3, n_notes);
-                if (ii < 0) throw PyError();
-                if (current_instrument != instruments[ii]) {
-                    current_instrument = instruments[ii];
-                    track.push_back({PROGRAM, off_time, instruments[ii], 0});
+                if (id < 0 || id >= n_instr) throw PyError();
+                if (current_instrument != instruments[id]) {
+                    current_instrument = instruments[id];
+                    track.push_back({PROGRAM, off_time, instruments[id], 0});
                 }
-                if (ni < 0) throw PyError();
-                track.push_back({NOTE_OFF, off_time, note_levels[ni], ev.velocity});
+                if (id >= n_notes) throw PyError();
+                track.push_back({NOTE_OFF, off_time, note_levels[id], ev->velocity});
             }
-            auto q = queue_lengths.find(a3);
-            if (q != queue_lengths.end()) q->second -= 1;
-            else queue_lengths[a3] = 0;
+            if (fast) {
+                if (ql_set[id]) ql_fast[id] -= 1;
+                else { ql_fast[id] = 0; ql_set[id] = true; }
+            } else {
+                auto q = queue_lengths.find(a3.str());
+                if (q != queue_lengths.end()) q->second -= 1;
+                else queue_lengths[a3.str()] = 0;
+            }
         }
     }
 
@@ -202,14 +228,14 @@ struct Song {
 
 // `INFO:root:<num> - <num> - <num> - (arrival|departure)` matched at the start of the line like re.match; <num> = [0-9]*\.[0-9]+|[0-9]+ .
 // What follows a number is the literal " - ", so the alternation has one way to succeed: the longest digits[.digits] token.
-inline bool take_number(const char*& p, const char* end, std::string& out) {
+inline bool take_number(const char*& p, const char* end, Tok& out) {
     const char* s = p;
     while (p < end && *p >= '0' && *p <= '9') ++p;
     if (p + 1 < end && *p == '.' && p[1] >= '0' && p[1] <= '9') {
         ++p;
         while (p < end && *p >= '0' && *p <= '9') ++p;
     } else if (p == s) return false;
-    out.assign(s, (size_t)(p - s));
+    out = {s, (int)(p - s)};
     return true;
 }
 inline bool take_lit(const char*& p, const char* end, const char* lit) {
@@ -229,7 +255,7 @@ long long convert_song(const char* log, size_t len, const long long* instruments
     const long long cap = 5000;
     const char* p = log;
     const char* end = log + len;
-    std::string a1, a2, a3;
+    Tok a1, a2, a3;
     while (p < end) {                                        // process_adjsim_log, :254-266
         const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
         const char* le = eol ? eol : end;
