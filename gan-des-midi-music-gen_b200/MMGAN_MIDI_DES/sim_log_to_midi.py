@@ -226,7 +226,11 @@ def process_adjsim_log(n=5000, baseline=70, range=50, instruments=np.arange(0, 1
                 log_lines = f.readlines()
         except Exception:
             raise ValueError("Error in processing log file")
-    stream, _ = sim_log_to_event_stream(log_lines, instruments, note_levels, gen2_output, generate, midi_path)
+    if midi_path is None and instruments is not None and isinstance(gen2_output, np.ndarray) and gen2_output.ndim == 1 and len(gen2_output) >= 6:
+        # nothing to write to disk: the native conversion (csrc/simlog.cu), same stream bit for bit
+        stream = sim_log_to_event_stream_native(log_lines, instruments, note_levels, gen2_output, generate)
+    else:
+        stream, _ = sim_log_to_event_stream(log_lines, instruments, note_levels, gen2_output, generate, midi_path)
     return ds.generate_piano_roll(stream, start=start, end=end)
 
 

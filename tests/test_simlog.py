@@ -143,6 +143,39 @@ def test_native_batch_equals_per_song_and_is_thread_count_independent():
     assert dt.numel() == 0 and off.tolist() == [0]
 
 
+def test_process_adjsim_log_hands_the_reference_stream_to_the_rasteriser(golden_dir, monkeypatch, tmp_path):
+    """host half of process_adjsim_log on the reference vectors (the device rasterisation is replaced by a recorder): the native conversion when
+    nothing is written to disk, the Python state machine when a .mid is asked for -- the same stream either way; argument errors as in the reference"""
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import datasets as ds
+    from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
+    seen = {}
+
+    def recorder(stream, start=0, end=50, **kw):
+        seen["stream"], seen["window"] = stream, (start, end)
+        return "roll", "dur", "beats"
+
+    monkeypatch.setattr(ds, "generate_piano_roll", recorder)
+    calls = {"native": 0, "python": 0}
+    real_native, real_py = sl.sim_log_to_event_stream_native, sl.sim_log_to_event_stream
+    monkeypatch.setattr(sl, "sim_log_to_event_stream_native", lambda *a, **k: (calls.__setitem__("native", calls["native"] + 1), real_native(*a, **k))[1])
+    monkeypatch.setattr(sl, "sim_log_to_event_stream", lambda *a, **k: (calls.__setitem__("python", calls["python"] + 1), real_py(*a, **k))[1])
+    for name, c, lines, generate, start, end in _cases(golden_dir):
+        for midi_path in (None, str(tmp_path / "x.mid")):
+            out = sl.process_adjsim_log(instruments=c[name + ".instruments"], note_levels=c[name + ".note_levels"], gen2_output=c[name + ".gen2"],
+                                        start=start, end=end, generate=generate, log_lines=lines, midi_path=midi_path)
+            assert out == ("roll", "dur", "beats") and seen["window"] == (start, end)
+            assert np.array_equal(seen["stream"].dt, c[name + ".dt"]) and np.array_equal(seen["stream"].meta, c[name + ".meta"]), (name, midi_path)
+    assert calls == {"native": 11, "python": 11}
+    with pytest.raises(TypeError):
+        sl.process_adjsim_log(gen2_output=None, log_lines=[])
+    with pytest.raises(TypeError):                                      # MidiGenerator's `range` quirk (:14,52) is still what instruments=None meets
+        sl.process_adjsim_log(instruments=None, note_levels=np.arange(16), gen2_output=np.full(10, 0.5, dtype=np.float32), log_lines=[])
+    with pytest.raises(ValueError, match="Error in processing log file"):
+        sl.process_adjsim_log(note_levels=np.arange(16), gen2_output=np.full(10, 0.2, dtype=np.float32), log_lines=["INFO:root:1.0 - 4 - 99 - arrival\n"])
+    with pytest.raises(ValueError, match="Error in processing log file"):
+        sl.process_adjsim_log(note_levels=np.arange(16), gen2_output=np.full(10, 0.2, dtype=np.float32), log_path=str(tmp_path / "missing.log"))
+
+
 def test_event_batch_packing(golden_dir):
     from gan_des_midi_music_gen_b200.MMGAN_MIDI_DES import sim_log_to_midi as sl
     cs = list(_cases(golden_dir))[:4]
