@@ -61,7 +61,9 @@ class GenTC:
         if ok is None:
             n3 = (ctypes.c_int * 3)(*self.widths[:3])
             ok = self._fused_ok[B] = bool(N.lib().mmg_gen_hidden_fused_supported(B, self.blocks[0][0].in_features, n3, int(self.gram_stats)))
-        return ok
+        # one momentum / eps for the three hidden BatchNorm1d layers (the reference's are the nn defaults); checked per call, they are plain attributes
+        bns = [bn for _, bn in self.blocks[:3]]
+        return ok and all(bn.momentum == bns[0].momentum and bn.eps == bns[0].eps for bn in bns)
 
     def pack(self, force=True):
         """Re-derive the bf16 operand copies from the fp32 master weights (cheap; skipped when nothing changed)."""
